@@ -1,0 +1,169 @@
+/* vjepa2_b200 -- C ABI of the B200 (sm_100a) kernels behind the V-JEPA 2 pre-training step.
+ *
+ * The reference (weipeilun/vjepa2) is pure Python/PyTorch and has no FFI of its own: the seam it
+ * offers is Python name lookup + nn.Module duck typing (app/vjepa/utils.py:159-190).  This header
+ * is therefore the boundary a maintainer binds (ctypes); every entry point
+ * cites the reference call site whose vendor kernel(s) it replaces.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - returns 0 on success, negative on error; vj_last_error() gives a thread-local message.
+ *   - enqueues on `stream` (a cudaStream_t passed as void*) and never synchronises, allocates or
+ *     frees caller memory.  Scratch is passed in by the caller where needed.
+ *   - all pointers are device pointers unless named host_*; matrices are row-major.
+ *   - no CPU fallback: on a machine without an sm_100 device every launch fails loudly.
+ */
+#ifndef VJEPA2_B200_H
+#define VJEPA2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { VJ_BF16 = 0, VJ_F32 = 1 };
+
+/* ------------------------------------------------------------------ library */
+const char* vj_last_error(void);
+int vj_abi_version(void);
+/* sm count / compute capability of the current device; <0 if no usable device */
+int vj_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ GEMM (tcgen05 + TMEM + TMA)
+ * out[M,N] = epilogue( A[M,K] * B[N,K]^T ), bf16 operands, fp32 accumulation in tensor memory.
+ * Replaces nn.Linear / nn.Conv3d-as-GEMM forward, dgrad and wgrad:
+ *   modules.py:330 (qkv), :380 (proj), :78-81 (fc1/fc2), patch_embed.py:51, predictor.py:182,244.
+ * Operand storage: a_mn_major==0 -> A stored [M][K] (K contiguous, ld=lda);
+ *                  a_mn_major==1 -> A stored [K][M] (M contiguous, ld=lda)   (same for B / N).
+ *   forward  y = x W^T      : A=x  [M][K],        B=W  [N][K]            (0,0)
+ *   dgrad    dx = dy W      : A=dy [M][N'],       B=W  [N'][K'] as [K][N] (0,1)
+ *   wgrad    dW = dy^T x    : A=dy [tok][N'] (1), B=x  [tok][K'] (1)
+ * Epilogue order: v = acc; +bias[n]; aux_out=bf16(v); v=bf16round(v) if ROUND; gelu; *gelu'(aux_in);
+ *                 +residual; store (bf16 or fp32).
+ */
+enum {
+  VJ_EPI_BIAS = 1,       /* v += bias[n] (fp32 [N]) */
+  VJ_EPI_GELU = 2,       /* v = gelu_erf(v)  (nn.GELU default, modules.py:73) */
+  VJ_EPI_DGELU = 4,      /* v *= gelu'(aux_in[m,n])  (backward through the activation) */
+  VJ_EPI_RESIDUAL = 8,   /* v += residual[m,n] */
+  VJ_EPI_OUT_F32 = 16,   /* out is fp32 (else bf16) */
+  VJ_EPI_RES_F32 = 32,   /* residual is fp32 (else bf16) */
+  VJ_EPI_ROUND_BF16 = 64,/* round v to bf16 before gelu/residual (mirrors autocast's bf16 Linear output) */
+  VJ_EPI_AUX_OUT = 128   /* also write the pre-activation v as bf16 to aux_out */
+};
+
+typedef struct {
+  const void* a;       /* bf16 */
+  const void* b;       /* bf16 */
+  void* out;           /* [M][N], ld = ldo */
+  int64_t M, N, K;
+  int64_t lda, ldb, ldo; /* leading dimensions in elements */
+  int32_t a_mn_major, b_mn_major;
+  int32_t flags;
+  const float* bias;
+  const void* residual;  /* ld = ldr; may alias out (fp32 accumulate) */
+  int64_t ldr;
+  void* aux_out;         /* bf16, ld = ld_aux */
+  const void* aux_in;    /* bf16, ld = ld_aux */
+  int64_t ld_aux;
+} vj_gemm_args;
+
+int vj_gemm(const vj_gemm_args* a, void* stream);
+
+/* ------------------------------------------------------------------ LayerNorm
+ * nn.LayerNorm(eps=1e-6) norm1/norm2/norm/predictor_norm (modules.py:558,562;
+ * vision_transformer.py:211; predictor.py:233) and F.layer_norm without affine, eps 1e-5
+ * (train.py:417; gamma/beta NULL).  Statistics in fp32.  mean/rstd may be NULL in forward. */
+int vj_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_dtype,
+                     float* mean, float* rstd, int64_t rows, int64_t D, float eps, void* stream);
+/* dx = LN'(dy) (+ dres if given, same dtype as dx); dgamma/dbeta (fp32 [D]) are ACCUMULATED (+=).
+ * scratch: at least vj_layernorm_bwd_scratch(rows, D) bytes. */
+size_t vj_layernorm_bwd_scratch(int64_t rows, int64_t D);
+int vj_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
+                     const float* mean, const float* rstd, const void* dres, void* dx, int dx_dtype,
+                     float* dgamma, float* dbeta, void* scratch, int64_t rows, int64_t D, void* stream);
+
+/* ------------------------------------------------------------------ 3-axis RoPE
+ * rotate_queries_or_keys + separate_positions (modules.py:26-50, 311-365).
+ * vj_rope_table: token ids (int64, as produced by MaskCollator) -> cos/sin tables
+ *   [n][3*(seg/2)] fp32 with seg = 2*((head_dim/3)/2); axis order frame, height, width.
+ * vj_rope_apply: in place on the q and k thirds of qkv [rows][3*D] (bf16); transpose!=0 applies the
+ *   adjoint map (backward).  The per-pair map is [[cos a, -sin a],[sin b, cos b]] with the TILED
+ *   angle layout of the reference (not a rotation). */
+int vj_rope_table(const int64_t* ids, int64_t n, int Hp, int Wp, int head_dim, float* cos_t, float* sin_t,
+                  void* stream);
+int vj_rope_apply(void* qkv, int64_t rows, int64_t D, int heads, int head_dim, const float* cos_t,
+                  const float* sin_t, int transpose, void* stream);
+
+/* ------------------------------------------------------------------ attention (tcgen05 flash fwd/bwd)
+ * F.scaled_dot_product_attention, non-causal, no mask, dropout 0, scale 1/sqrt(d) (modules.py:369).
+ * qkv: [B*S][3*D] bf16, feature = which*D + head*d + i (modules.py:330-331), q/k already rotated.
+ * out: [B*S][D] bf16 (head-major features = x.transpose(1,2).reshape, modules.py:379).
+ * lse: [B][H][S] fp32, log2-domain log-sum-exp (saved for backward).
+ * head_dim in {32, 64}.  S arbitrary >= 1. */
+int vj_attn_fwd(const void* qkv, void* out, float* lse, int B, int S, int H, int head_dim, void* stream);
+/* dqkv: [B*S][3*D] bf16 (gradient w.r.t. the rotated q/k and v).
+ * scratch: vj_attn_bwd_scratch bytes (fp32 dq accumulators + delta). */
+size_t vj_attn_bwd_scratch(int B, int S, int H, int head_dim);
+int vj_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* scratch,
+                int B, int S, int H, int head_dim, void* stream);
+
+/* ------------------------------------------------------------------ row gather / scatter
+ * apply_masks (masks/utils.py:9-21): dst[r,:] = src[index[r],:]; index[r] < 0 -> fill[:] (or 0).
+ * Bit-exact copy when dtypes match; converts otherwise.  index holds ABSOLUTE source rows. */
+int vj_gather_rows(const void* src, int src_dtype, void* dst, int dst_dtype, const int64_t* index,
+                   const float* fill, int64_t n_out, int64_t D, void* stream);
+/* dst[index[r],:] += src[r,:]  (fp32 atomics; adjoint of gather for duplicate-capable indices) */
+int vj_scatter_add_rows(const void* src, int src_dtype, float* dst, const int64_t* index, int64_t n_src,
+                        int64_t D, void* stream);
+/* absolute gather index for apply_masks: out[b*K+k] = b*N + masks[b*K+k] */
+int vj_mask_to_rows(const int64_t* masks, int64_t* out, int64_t B, int64_t K, int64_t N, void* stream);
+
+/* ------------------------------------------------------------------ patch embed im2col
+ * PatchEmbed3D (patch_embed.py:49-52): Conv3d k=s=(tub,p,p) as im2col (+ vj_gemm).
+ * clips fp32 [B][C][T][H][W]; ids int64 [B][K] token ids to keep (NULL = all T/tub*H/p*W/p tokens,
+ * K ignored); cols bf16 [B*K][C*tub*p*p], K order (c,kt,kh,kw). */
+int vj_im2col_tubelets(const float* clips, const int64_t* ids, void* cols, int B, int C, int T, int H, int W,
+                       int tubelet, int patch, int64_t K, void* stream);
+
+/* ------------------------------------------------------------------ reductions / loss
+ * out[D] (+)= sum_r x[r,:]   (bias gradients).  scratch >= vj_colsum_scratch bytes. */
+size_t vj_colsum_scratch(int64_t rows, int64_t D);
+int vj_colsum(const void* x, int x_dtype, float* out, int accumulate, void* scratch, int64_t rows, int64_t D,
+              void* stream);
+/* loss_fn (train.py:425-435) for one mask: loss_accum += loss_scale * sum |z - h[idx]|,
+ * dz = grad_scale * sign(z - h[idx]) (bf16; NULL to skip).  z bf16 [B][K][D]; h fp32 [B][N][D];
+ * idx int64 [B][K].  scratch >= vj_l1_scratch bytes.  Deterministic two-stage reduction. */
+size_t vj_l1_scratch(int64_t B, int64_t K, int64_t D);
+int vj_l1_loss(const void* z, const float* h, const int64_t* idx, float* loss_accum, void* dz, float loss_scale,
+               float grad_scale, void* scratch, int64_t B, int64_t K, int64_t N, int64_t D, void* stream);
+
+/* ------------------------------------------------------------------ predictor token order
+ * predictor.py:210-217,240-241: rank[b][i] = position of element i in the ascending (stable) order
+ * of ids[b][:]  (== argsort(argsort(ids))). */
+int vj_argsort_rank(const int64_t* ids, int32_t* rank, int64_t B, int64_t S, void* stream);
+
+/* ------------------------------------------------------------------ flat optimizer kernels
+ * EMA (train.py:457-465): tgt = fma(1-m, src, tgt*m) over a flat fp32 buffer (the rounding order of
+ * torch._foreach_mul_ followed by _foreach_add_(alpha=1-m)); optionally refreshes the bf16 shadow of
+ * the target weights.  m and 1-m are both passed (computed in double on the host). */
+int vj_ema_update(float* tgt, const float* src, void* tgt_bf16, int64_t n, float m, float one_minus_m,
+                  void* stream);
+/* found_inf[0] = 1.0f if any g*inv_scale is non-finite (GradScaler.unscale_ check, train.py:446). */
+int vj_grad_check(const float* g, int64_t n, float* found_inf, void* stream);
+/* torch.optim.AdamW (app/vjepa/utils.py:239) over a flat buffer, grads multiplied by *inv_scale,
+ * skipped entirely when *found_inf != 0 (GradScaler.step).  tile_flags: one byte per 1024
+ * elements: bit0 = weight decay applies, bit1 = frozen (no grad ever produced).  Also refreshes
+ * the bf16 shadow.  bias corrections are passed in (host scalars: 1-b1^t, 1-b2^t). */
+int vj_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* p_bf16,
+                  const uint8_t* tile_flags, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
+                  float bias_c1, float bias_c2, const float* inv_scale, const float* found_inf, void* stream);
+/* fp32 -> bf16 flat cast (weight shadow refresh) */
+int vj_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VJEPA2_B200_H */

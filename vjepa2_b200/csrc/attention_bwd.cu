@@ -1,0 +1,353 @@
+// Flash-attention backward on tcgen05 for sm_100a.
+//
+// One CTA = one (batch, head, 128-key tile); it loops over 128-query tiles.  192 threads:
+//   warps 0-3  compute: thread r owns key row r (TMEM lane r) of S^T / dP^T, and query row r of dQ
+//   warp  4    TMA producer (K,V once; Q_i / dO_i double-buffered) + TMEM allocate/free
+//   warp  5    MMA issuer, five GEMMs per query tile:
+//                S^T  = K Q_i^T          (128 keys x 128 q, K=d)        -> TMEM [0,128)
+//                dP^T = V dO_i^T         (128 keys x 128 q, K=d)        -> TMEM [128,256)
+//                dV  += P^T dO_i         (128 keys x d,   K=128 q)      -> TMEM [256,256+d)
+//                dK  += dS^T Q_i         (128 keys x d,   K=128 q)      -> TMEM [256+d,256+2d)
+//                dQ_i = dS K             (128 q x d,      K=128 keys)   -> TMEM [256+2d,256+3d)
+//   P^T and dS^T are written to smem as bf16 K-major tiles; the same dS^T buffer is consumed as an
+//   MN-major A operand for dQ (no transpose).  dQ partial tiles are accumulated across key tiles with
+//   fp32 reductions into a scratch buffer and converted to bf16 by a small follow-up kernel.
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/vjepa2_b200.h"
+
+namespace vj {
+
+template <int HD>
+struct AttnBwdCfg {
+  static constexpr int BT = 128;                       // keys per CTA == queries per iteration
+  static constexpr int SWB = HD * 2;
+  static constexpr int TILE_BYTES = BT * HD * 2;       // K, V, Q_i, dO_i tiles
+  static constexpr int PT_BYTES = BT * BT * 2;         // 32 KB: two [128 rows][128 B] atoms
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + TILE_BYTES;
+  static constexpr int OFF_Q = OFF_V + TILE_BYTES;     // 2 stages
+  static constexpr int OFF_DO = OFF_Q + 2 * TILE_BYTES; // 2 stages
+  static constexpr int OFF_PT = OFF_DO + 2 * TILE_BYTES;
+  static constexpr int OFF_DS = OFF_PT + PT_BYTES;
+  static constexpr int OFF_LSE = OFF_DS + PT_BYTES;    // 128 floats lse + 128 floats delta
+  static constexpr int OFF_BAR = OFF_LSE + 1024;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int COL_ST = 0, COL_DPT = 128, COL_DV = 256, COL_DK = 256 + HD, COL_DQ = 256 + 2 * HD;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(HD == 64 || HD == 32, "head_dim 64 or 32");
+};
+
+// delta[b][h][q] = sum_i dO[q, h, i] * O[q, h, i]
+__global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout,
+                                                         float* __restrict__ delta, int B, int S, int H, int hd) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)B * S * H) return;
+  const int h = (int)(t % H);
+  const long long row = t / H;
+  const long long b = row / S;
+  const int q = (int)(row - b * S);
+  const bf16* o = out + row * (long long)H * hd + h * hd;
+  const bf16* d = dout + row * (long long)H * hd + h * hd;
+  float acc = 0.f;
+  for (int i = 0; i < hd; i += 8) {
+    const uint4 a = *reinterpret_cast<const uint4*>(o + i);
+    const uint4 c = *reinterpret_cast<const uint4*>(d + i);
+    acc += bf16_lo(a.x) * bf16_lo(c.x) + bf16_hi(a.x) * bf16_hi(c.x) + bf16_lo(a.y) * bf16_lo(c.y) +
+           bf16_hi(a.y) * bf16_hi(c.y) + bf16_lo(a.z) * bf16_lo(c.z) + bf16_hi(a.z) * bf16_hi(c.z) +
+           bf16_lo(a.w) * bf16_lo(c.w) + bf16_hi(a.w) * bf16_hi(c.w);
+  }
+  delta[(b * H + h) * S + q] = acc;
+}
+
+// dq accumulators fp32 [B*S][D] -> bf16 q-third of dqkv [B*S][3D]
+__global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ dq_acc,
+                                                              bf16* __restrict__ dqkv, long long rows, int D) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int vec_per_row = D >> 3;
+  if (t >= rows * vec_per_row) return;
+  const long long row = t / vec_per_row;
+  const int c = (int)(t - row * vec_per_row) * 8;
+  const float4 a = *reinterpret_cast<const float4*>(dq_acc + row * D + c);
+  const float4 b = *reinterpret_cast<const float4*>(dq_acc + row * D + c + 4);
+  uint4 u;
+  u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
+  u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+  *reinterpret_cast<uint4*>(dqkv + row * 3 * (long long)D + c) = u;
+}
+
+template <int HD>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
+                bf16* __restrict__ dqkv, int S, int H, int D, float scale, float scale_log2) {
+  using Cfg = AttnBwdCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sDO = smem + Cfg::OFF_DO;
+  uint8_t* sPT = smem + Cfg::OFF_PT;
+  uint8_t* sDS = smem + Cfg::OFF_DS;
+  float* s_lse = reinterpret_cast<float*>(smem + Cfg::OFF_LSE);
+  float* s_delta = s_lse + 128;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* kv_full = bars;          // 1
+  uint64_t* qdo_full = bars + 1;     // 2
+  uint64_t* qdo_empty = bars + 3;    // 2
+  uint64_t* sdp_full = bars + 5;     // 1
+  uint64_t* pds_full = bars + 6;     // 1 (128 arrivals)
+  uint64_t* dq_full = bars + 7;      // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * Cfg::BT;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_q = (S + Cfg::BT - 1) / Cfg::BT;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(dq_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQKV);
+      tma_prefetch_desc(&tmDO);
+      mbar_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
+      tma_load_3d(sK, &tmQKV, kv_full, D + h * HD, k0, b);
+      tma_load_3d(sV, &tmQKV, kv_full, 2 * D + h * HD, k0, b);
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i & 1;
+        mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[st], 2 * Cfg::TILE_BYTES);
+        tma_load_3d(sQ + st * Cfg::TILE_BYTES, &tmQKV, &qdo_full[st], h * HD, i * Cfg::BT, b);
+        tma_load_3d(sDO + st * Cfg::TILE_BYTES, &tmDO, &qdo_full[st], h * HD, i * Cfg::BT, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------------------------------------------------------- MMA issuer
+    constexpr uint32_t id_s = make_idesc(128, 128, false, false);
+    constexpr uint32_t id_dv = make_idesc(128, HD, false, true);
+    constexpr uint32_t id_dq = make_idesc(128, HD, true, true);
+    const uint64_t kd_k = desc_kmajor<Cfg::SWB>(smem_u32(sK));
+    const uint64_t vd_k = desc_kmajor<Cfg::SWB>(smem_u32(sV));
+    const uint64_t kd_mn = desc_mnmajor<Cfg::SWB>(smem_u32(sK), Cfg::TILE_BYTES);
+    const uint64_t pt_k = desc_kmajor<128>(smem_u32(sPT));
+    const uint64_t ds_k = desc_kmajor<128>(smem_u32(sDS));
+    const uint64_t ds_mn = desc_mnmajor<128>(smem_u32(sDS), 16384);
+    mbar_wait(kv_full, 0);
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i & 1;
+      mbar_wait(&qdo_full[st], (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
+      const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
+      if (lane == 0) {
+        const uint64_t qd_k = desc_kmajor<Cfg::SWB>(q_addr);
+        const uint64_t dod_k = desc_kmajor<Cfg::SWB>(do_addr);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tmem_base + Cfg::COL_ST, desc_advance(kd_k, k * 32), desc_advance(qd_k, k * 32), id_s, k != 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tmem_base + Cfg::COL_DPT, desc_advance(vd_k, k * 32), desc_advance(dod_k, k * 32), id_s, k != 0);
+        umma_commit(sdp_full);
+      }
+      __syncwarp();
+      mbar_wait(pds_full, i & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t qd_mn = desc_mnmajor<Cfg::SWB>(q_addr, Cfg::TILE_BYTES);
+        const uint64_t dod_mn = desc_mnmajor<Cfg::SWB>(do_addr, Cfg::TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dV += P^T dO
+          umma_bf16(tmem_base + Cfg::COL_DV, desc_advance(pt_k, (k >> 2) * 16384 + (k & 3) * 32),
+                    desc_advance(dod_mn, k * 16 * Cfg::SWB), id_dv, (i | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dK += dS^T Q
+          umma_bf16(tmem_base + Cfg::COL_DK, desc_advance(ds_k, (k >> 2) * 16384 + (k & 3) * 32),
+                    desc_advance(qd_mn, k * 16 * Cfg::SWB), id_dv, (i | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dQ_i = dS K
+          umma_bf16(tmem_base + Cfg::COL_DQ, desc_advance(ds_mn, k * 2048), desc_advance(kd_mn, k * 16 * Cfg::SWB),
+                    id_dq, k != 0);
+        umma_commit(&qdo_empty[st]);
+        umma_commit(dq_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------------------------------------- compute warps
+    const int r = threadIdx.x;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const bool key_ok = (k0 + r) < S;
+    const float* lse_bh = lse + ((long long)b * H + h) * S;
+    const float* delta_bh = delta + ((long long)b * H + h) * S;
+    for (int i = 0; i < n_q; ++i) {
+      const int q = i * Cfg::BT + r;
+      s_lse[r] = q < S ? lse_bh[q] : INFINITY;
+      s_delta[r] = q < S ? delta_bh[q] : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(sdp_full, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(lane_addr + Cfg::COL_ST + c * 32, sv);
+        tmem_ld32(lane_addr + Cfg::COL_DPT + c * 32, dv);
+        tmem_ld_wait();
+        uint32_t pp[16], dd[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float p0 = exp2f(__uint_as_float(sv[j]) * scale_log2 - s_lse[c * 32 + j]);
+          float p1 = exp2f(__uint_as_float(sv[j + 1]) * scale_log2 - s_lse[c * 32 + j + 1]);
+          if (!key_ok) { p0 = 0.f; p1 = 0.f; }
+          const float d0 = p0 * (__uint_as_float(dv[j]) - s_delta[c * 32 + j]);
+          const float d1 = p1 * (__uint_as_float(dv[j + 1]) - s_delta[c * 32 + j + 1]);
+          pp[j >> 1] = pack_bf16x2(p0, p1);
+          dd[j >> 1] = pack_bf16x2(d0, d1);
+        }
+        // 4 x 16-byte chunks per buffer; chunk cc of the row -> atom cc/8, position (cc%8) ^ (r&7)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int cc = c * 4 + u;
+          const uint32_t off = (cc >> 3) * 16384 + r * 128 + (((cc & 7) ^ (r & 7)) << 4);
+          *reinterpret_cast<uint4*>(sPT + off) = make_uint4(pp[u * 4], pp[u * 4 + 1], pp[u * 4 + 2], pp[u * 4 + 3]);
+          *reinterpret_cast<uint4*>(sDS + off) = make_uint4(dd[u * 4], dd[u * 4 + 1], dd[u * 4 + 2], dd[u * 4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+      // dQ_i tile: lane r == query row r
+      mbar_wait(dq_full, i & 1);
+      tc_fence_after();
+      float* dq_row = dq_acc + ((long long)b * S + q) * D + h * HD;
+#pragma unroll
+      for (int c0 = 0; c0 < HD; c0 += 32) {
+        uint32_t o[32];
+        tmem_ld32(lane_addr + Cfg::COL_DQ + c0, o);
+        tmem_ld_wait();
+        if (q < S) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(dq_row + c0 + j, __uint_as_float(o[j]) * scale);
+        }
+      }
+      tc_fence_before();
+    }
+    // dK / dV epilogue (all MMAs retired: dq_full of the last iteration was committed after them)
+    const int key = k0 + r;
+    bf16* dk_row = dqkv + ((long long)b * S + key) * 3 * D + D + h * HD;
+    bf16* dv_row = dk_row + D;
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 32) {
+      uint32_t a[32], c[32];
+      tmem_ld32(lane_addr + Cfg::COL_DK + c0, a);
+      tmem_ld32(lane_addr + Cfg::COL_DV + c0, c);
+      tmem_ld_wait();
+      if (key_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 u, w;
+          u.x = pack_bf16x2(__uint_as_float(a[j]) * scale, __uint_as_float(a[j + 1]) * scale);
+          u.y = pack_bf16x2(__uint_as_float(a[j + 2]) * scale, __uint_as_float(a[j + 3]) * scale);
+          u.z = pack_bf16x2(__uint_as_float(a[j + 4]) * scale, __uint_as_float(a[j + 5]) * scale);
+          u.w = pack_bf16x2(__uint_as_float(a[j + 6]) * scale, __uint_as_float(a[j + 7]) * scale);
+          w.x = pack_bf16x2(__uint_as_float(c[j]), __uint_as_float(c[j + 1]));
+          w.y = pack_bf16x2(__uint_as_float(c[j + 2]), __uint_as_float(c[j + 3]));
+          w.z = pack_bf16x2(__uint_as_float(c[j + 4]), __uint_as_float(c[j + 5]));
+          w.w = pack_bf16x2(__uint_as_float(c[j + 6]), __uint_as_float(c[j + 7]));
+          *reinterpret_cast<uint4*>(dk_row + c0 + j) = u;
+          *reinterpret_cast<uint4*>(dv_row + c0 + j) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int HD>
+static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                           void* scratch, int B, int S, int H, cudaStream_t stream) {
+  using Cfg = AttnBwdCfg<HD>;
+  const int D = H * HD;
+  float* dq_acc = reinterpret_cast<float*>(scratch);
+  float* delta = dq_acc + (size_t)B * S * D;
+  VJ_CUDA(cudaMemsetAsync(dq_acc, 0, (size_t)B * S * D * sizeof(float), stream));
+  {
+    const long long n = (long long)B * S * H;
+    attn_delta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(out), reinterpret_cast<const bf16*>(dout), delta, B, S, H, HD);
+    VJ_LAUNCH_CHECK();
+  }
+  CUtensorMap tmQKV, tmDO;
+  {
+    const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)S, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)S * 3 * D * 2};
+    const uint32_t box[3] = {HD, Cfg::BT, 1};
+    int r = make_tmap_bf16(&tmQKV, qkv, 3, dims, strides, box, Cfg::SWB);
+    if (r) return r;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)S, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)S * D * 2};
+    const uint32_t box[3] = {HD, Cfg::BT, 1};
+    int r = make_tmap_bf16(&tmDO, dout, 3, dims, strides, box, Cfg::SWB);
+    if (r) return r;
+  }
+  auto kern = attn_bwd_kernel<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((S + Cfg::BT - 1) / Cfg::BT, H, B);
+  const float scale = 1.0f / sqrtf((float)HD);
+  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmQKV, tmDO, lse, delta, dq_acc, reinterpret_cast<bf16*>(dqkv), S, H, D,
+                                              scale, scale * 1.4426950408889634f);
+  VJ_LAUNCH_CHECK();
+  {
+    const long long n = (long long)B * S * (D / 8);
+    attn_dq_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dq_acc, reinterpret_cast<bf16*>(dqkv),
+                                                                          (long long)B * S, D);
+    VJ_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace vj
+
+extern "C" size_t vj_attn_bwd_scratch(int B, int S, int H, int head_dim) {
+  return ((size_t)B * S * H * head_dim + (size_t)B * H * S) * sizeof(float);
+}
+
+extern "C" int vj_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
+                           void* scratch, int B, int S, int H, int head_dim, void* stream) {
+  using namespace vj;
+  VJ_CHECK(qkv && out && dout && lse && dqkv && scratch, "vj_attn_bwd: null pointer");
+  VJ_CHECK(B > 0 && S > 0 && H > 0, "vj_attn_bwd: bad shape B=%d S=%d H=%d", B, S, H);
+  VJ_CHECK(B <= 65535 && H <= 65535, "vj_attn_bwd: B/H exceed grid limits");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (head_dim == 64) return launch_attn_bwd<64>(qkv, out, dout, lse, dqkv, scratch, B, S, H, st);
+  if (head_dim == 32) return launch_attn_bwd<32>(qkv, out, dout, lse, dqkv, scratch, B, S, H, st);
+  set_error("vj_attn_bwd: head_dim %d not supported (32, 64)", head_dim);
+  return -1;
+}

@@ -1,0 +1,274 @@
+// Flash-attention forward on tcgen05 for sm_100a (non-causal, no mask, scale 1/sqrt(d)).
+//
+// One CTA = one (batch, head, 128-query tile).  192 threads:
+//   warps 0-3  softmax: thread r owns query row r == TMEM lane r (S row in, P row out, O row rescale)
+//   warp  4    TMA producer (Q once, K/V ring of 3 stages) + TMEM allocate/free
+//   warp  5    MMA issuer:  S_j = Q K_j^T  (M128 x N64 x K=d),  O += P_j V_j  (M128 x N=d x K64)
+// TMEM (256 columns): S ping-pong [0,64) [64,128), O at [128,128+d).  ~82 KB smem -> 2 CTAs / SM so one
+// CTA's softmax overlaps the other's MMAs.  Q/K/V tiles are read straight out of the fused qkv
+// activation [B*S][3D] with a 3-D tensor map (d, S, B) -- no head-major relayout pass.
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/vjepa2_b200.h"
+
+namespace vj {
+
+template <int HD>
+struct AttnFwdCfg {
+  static constexpr int BM = 128, BN = 64, KV_STAGES = 3;
+  static constexpr int SWB = HD * 2;                 // operand row bytes == swizzle width (128 or 64)
+  static constexpr int Q_BYTES = BM * HD * 2;
+  static constexpr int KV_BYTES = BN * HD * 2;
+  static constexpr int P_BYTES = BM * BN * 2;        // 16 KB, 128-B rows
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;
+  static constexpr int OFF_BAR = OFF_P + P_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int O_COL = 128;
+  static_assert(HD == 64 || HD == 32, "head_dim 64 or 32");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(192, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                bf16* __restrict__ out, float* __restrict__ lse, int S, int H, int D, float scale_log2) {
+  using Cfg = AttnFwdCfg<HD>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sP = smem + Cfg::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars;           // 1
+  uint64_t* k_full = bars + 1;       // 3
+  uint64_t* k_empty = bars + 4;      // 3
+  uint64_t* v_full = bars + 7;       // 3
+  uint64_t* v_empty = bars + 10;     // 3
+  uint64_t* s_full = bars + 13;      // 2
+  uint64_t* p_full = bars + 15;      // 1 (128 arrivals)
+  uint64_t* pv_done = bars + 16;     // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * Cfg::BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (S + Cfg::BN - 1) / Cfg::BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 3; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmKV);
+      mbar_expect_tx(q_full, Cfg::Q_BYTES);
+      tma_load_3d(sQ, &tmQ, q_full, h * HD, q0, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int st = j % 3;
+        const uint32_t ph = (j / 3) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
+        tma_load_3d(sK + st * Cfg::KV_BYTES, &tmKV, &k_full[st], D + h * HD, j * Cfg::BN, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], Cfg::KV_BYTES);
+        tma_load_3d(sV + st * Cfg::KV_BYTES, &tmKV, &v_full[st], 2 * D + h * HD, j * Cfg::BN, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_qk = make_idesc(128, Cfg::BN, false, false);
+    constexpr uint32_t idesc_pv = make_idesc(128, HD, false, true);
+    const uint64_t qd = desc_kmajor<Cfg::SWB>(smem_u32(sQ));
+    const uint64_t pd = desc_kmajor<128>(smem_u32(sP));
+    mbar_wait(q_full, 0);
+    auto issue_qk = [&](int j) {
+      const int st = j % 3;
+      mbar_wait(&k_full[st], (j / 3) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t kd = desc_kmajor<Cfg::SWB>(smem_u32(sK + st * Cfg::KV_BYTES));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_bf16(tmem_base + (j & 1) * Cfg::BN, desc_advance(qd, k * 32), desc_advance(kd, k * 32), idesc_qk,
+                    k != 0 ? 1u : 0u);
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[j & 1]);
+      }
+      __syncwarp();
+    };
+    issue_qk(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      if (j + 1 < n_tiles) issue_qk(j + 1);
+      const int st = j % 3;
+      mbar_wait(&v_full[st], (j / 3) & 1);
+      mbar_wait(p_full, j & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t vd = desc_mnmajor<Cfg::SWB>(smem_u32(sV + st * Cfg::KV_BYTES), Cfg::KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < Cfg::BN / 16; ++k)
+          umma_bf16(tmem_base + Cfg::O_COL, desc_advance(pd, k * 32), desc_advance(vd, k * 16 * Cfg::SWB), idesc_pv,
+                    (j | k) != 0 ? 1u : 0u);
+        umma_commit(&v_empty[st]);
+        umma_commit(pv_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax / correction / epilogue
+    const int r = threadIdx.x;                              // query row in tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = sP + r * 128;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sr[64];
+      {
+        uint32_t a[32], c[32];
+        tmem_ld32(lane_addr + (j & 1) * Cfg::BN, a);
+        tmem_ld32(lane_addr + (j & 1) * Cfg::BN + 32, c);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { sr[i] = a[i]; sr[32 + i] = c[i]; }
+      }
+      const int valid = S - j * Cfg::BN;                    // >= 1
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        float v = __uint_as_float(sr[i]);
+        if (i >= valid) v = -INFINITY;
+        sr[i] = __float_as_uint(v);
+        mx = fmaxf(mx, v);
+      }
+      const float m_new = fmaxf(m_run, mx * scale_log2);
+      const float alpha = exp2f(m_run - m_new);             // 0 on the first tile
+      float rs = 0.f;
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        const float p0 = exp2f(__uint_as_float(sr[i]) * scale_log2 - m_new);
+        const float p1 = exp2f(__uint_as_float(sr[i + 1]) * scale_log2 - m_new);
+        rs += p0 + p1;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+      }
+      l_run = l_run * alpha + rs;
+      m_run = m_new;
+      if (j > 0) {
+        // PV_{j-1} finished: P buffer is free and O holds tiles < j
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+#pragma unroll
+          for (int c0 = 0; c0 < HD; c0 += 32) {
+            uint32_t o[32];
+            tmem_ld32(lane_addr + Cfg::O_COL + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(lane_addr + Cfg::O_COL + c0, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // P row -> smem, K-major 128-B swizzled rows: 16-B chunk c lands at c ^ (r & 7)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 u = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = u;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    tc_fence_after();
+    const int qrow = q0 + r;
+    const float inv_l = 1.0f / l_run;
+    bf16* orow = out + ((long long)b * S + qrow) * D + h * HD;
+#pragma unroll
+    for (int c0 = 0; c0 < HD; c0 += 32) {
+      uint32_t o[32];
+      tmem_ld32(lane_addr + Cfg::O_COL + c0, o);
+      tmem_ld_wait();
+      if (qrow < S) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
+          u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
+          u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
+          u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + c0 + i) = u;
+        }
+      }
+    }
+    if (qrow < S) lse[((long long)b * H + h) * S + qrow] = m_run + log2f(l_run);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int HD>
+static int launch_attn_fwd(const void* qkv, void* out, float* lse, int B, int S, int H, cudaStream_t stream) {
+  using Cfg = AttnFwdCfg<HD>;
+  const int D = H * HD;
+  CUtensorMap tmQ, tmKV;
+  const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)S, (uint64_t)B};
+  const uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)S * 3 * D * 2};
+  const uint32_t boxq[3] = {HD, Cfg::BM, 1};
+  const uint32_t boxkv[3] = {HD, Cfg::BN, 1};
+  int r = make_tmap_bf16(&tmQ, qkv, 3, dims, strides, boxq, Cfg::SWB);
+  if (r) return r;
+  r = make_tmap_bf16(&tmKV, qkv, 3, dims, strides, boxkv, Cfg::SWB);
+  if (r) return r;
+  auto kern = attn_fwd_kernel<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((S + Cfg::BM - 1) / Cfg::BM, H, B);
+  const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
+  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmQ, tmKV, reinterpret_cast<bf16*>(out), lse, S, H, D, scale_log2);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace vj
+
+extern "C" int vj_attn_fwd(const void* qkv, void* out, float* lse, int B, int S, int H, int head_dim, void* stream) {
+  using namespace vj;
+  VJ_CHECK(qkv && out && lse, "vj_attn_fwd: null pointer");
+  VJ_CHECK(B > 0 && S > 0 && H > 0, "vj_attn_fwd: bad shape B=%d S=%d H=%d", B, S, H);
+  VJ_CHECK(B <= 65535 && H <= 65535, "vj_attn_fwd: B/H exceed grid limits");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (head_dim == 64) return launch_attn_fwd<64>(qkv, out, lse, B, S, H, st);
+  if (head_dim == 32) return launch_attn_fwd<32>(qkv, out, lse, B, S, H, st);
+  set_error("vj_attn_fwd: head_dim %d not supported (32, 64)", head_dim);
+  return -1;
+}

@@ -1,0 +1,754 @@
+// Bandwidth-class kernels of the step: LayerNorm fwd/bwd, 3-axis RoPE, apply_masks row gather /
+// scatter, tubelet im2col, bias-gradient column sums, fused gather+L1 loss, predictor token ranks,
+// flat EMA / AdamW / grad check.  All HBM-bound: 128-bit coalesced accesses, warp-shuffle reductions,
+// deterministic two-stage reductions (no fp32 atomics except the documented scatter-add).
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/vjepa2_b200.h"
+
+namespace vj {
+
+// ---------------------------------------------------------------- 8-wide typed load/store
+__device__ __forceinline__ void load8(const void* base, int dtype, long long elem_off, float (&v)[8]) {
+  if (dtype == VJ_BF16) {
+    const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + elem_off);
+    v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+    v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + elem_off);
+    const float4 a = p[0], b = p[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+__device__ __forceinline__ void store8(void* base, int dtype, long long elem_off, const float (&v)[8]) {
+  if (dtype == VJ_BF16) {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + elem_off) = u;
+  } else {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm forward
+constexpr int LN_MAXV = 8;  // vectors of 8 per lane -> D <= 2048
+
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x, int x_dtype,
+                                                     const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, void* __restrict__ y,
+                                                     int y_dtype, float* __restrict__ mean_out,
+                                                     float* __restrict__ rstd_out, long long rows, int D, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const int nvec = D >> 3;
+  float v[LN_MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      load8(x, x_dtype, row * D + vi * 8, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / D;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; ss += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float o[8];
+      if (gamma) {
+        float g[8], b[8];
+        load8(gamma, VJ_F32, vi * 8, g);
+        if (beta) load8(beta, VJ_F32, vi * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + (beta ? b[j] : 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd;
+      }
+      store8(y, y_dtype, row * D + vi * 8, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- LayerNorm backward (dx)
+__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const void* __restrict__ dy, int dy_dtype,
+                                                        const void* __restrict__ x, int x_dtype,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ mean_in,
+                                                        const float* __restrict__ rstd_in,
+                                                        const void* __restrict__ dres, void* __restrict__ dx,
+                                                        int dx_dtype, long long rows, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const int nvec = D >> 3;
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  float xh[LN_MAXV][8], g[LN_MAXV][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float xv[8], dv[8], gm[8];
+      load8(x, x_dtype, row * D + vi * 8, xv);
+      load8(dy, dy_dtype, row * D + vi * 8, dv);
+      if (gamma) load8(gamma, VJ_F32, vi * 8, gm);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[i][j] = (xv[j] - mean) * rstd;
+        g[i][j] = gamma ? dv[j] * gm[j] : dv[j];
+        s1 += g[i][j];
+        s2 += g[i][j] * xh[i][j];
+      }
+    }
+  }
+  const float c1 = warp_sum(s1) / D, c2 = warp_sum(s2) / D;
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - c1 - xh[i][j] * c2);
+      if (dres) {
+        float r[8];
+        load8(dres, dx_dtype, row * D + vi * 8, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      }
+      store8(dx, dx_dtype, row * D + vi * 8, o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- column reductions
+// partial[chunk][c] = sum over the chunk's rows of f(r,c);  WITH_XHAT: also dy*xhat (LN dgamma).
+// block (32, 8): thread owns 2 adjacent columns, warps stride over rows.  grid (ceil(D/64), chunks).
+constexpr int COL_CHUNKS_MAX = 64;
+
+__device__ __forceinline__ float2 load2(const void* base, int dtype, long long off) {
+  if (dtype == VJ_BF16) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(reinterpret_cast<const bf16*>(base) + off);
+    return make_float2(bf16_lo(u), bf16_hi(u));
+  }
+  return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(base) + off);
+}
+
+template <bool WITH_XHAT>
+__global__ void __launch_bounds__(256) colreduce_kernel(const void* __restrict__ dy, int dy_dtype,
+                                                        const void* __restrict__ x, int x_dtype,
+                                                        const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd,
+                                                        float* __restrict__ part_sum,   // [chunks][D]
+                                                        float* __restrict__ part_xh,    // [chunks][D]
+                                                        long long rows, int D, long long rows_per_chunk) {
+  __shared__ float sm[2][8][64];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = blockIdx.x * 64 + tx * 2;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = min(rows, r0 + rows_per_chunk);
+  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+  if (col < D) {
+    for (long long r = r0 + ty; r < r1; r += 8) {
+      const float2 d = load2(dy, dy_dtype, r * D + col);
+      a0 += d.x; a1 += d.y;
+      if (WITH_XHAT) {
+        const float2 xv = load2(x, x_dtype, r * D + col);
+        const float m = mean[r], rs = rstd[r];
+        b0 += d.x * (xv.x - m) * rs;
+        b1 += d.y * (xv.y - m) * rs;
+      }
+    }
+  }
+  sm[0][ty][tx * 2] = a0; sm[0][ty][tx * 2 + 1] = a1;
+  if (WITH_XHAT) { sm[1][ty][tx * 2] = b0; sm[1][ty][tx * 2 + 1] = b1; }
+  __syncthreads();
+  const int t = ty * 32 + tx;
+  if (t < 64) {
+    const int c = blockIdx.x * 64 + t;
+    if (c < D) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += sm[0][w][t];
+      part_sum[(long long)blockIdx.y * D + c] = s;
+    }
+  } else if (WITH_XHAT && t < 128) {
+    const int tt = t - 64;
+    const int c = blockIdx.x * 64 + tt;
+    if (c < D) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += sm[1][w][tt];
+      part_xh[(long long)blockIdx.y * D + c] = s;
+    }
+  }
+}
+
+__global__ void colreduce_final_kernel(const float* __restrict__ part, float* __restrict__ out, int chunks, int D,
+                                       int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D) return;
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += part[(long long)k * D + c];
+  out[c] = accumulate ? out[c] + s : s;
+}
+
+static inline int col_chunks(long long rows) {
+  long long c = (rows + 255) / 256;
+  if (c < 1) c = 1;
+  if (c > COL_CHUNKS_MAX) c = COL_CHUNKS_MAX;
+  return (int)c;
+}
+
+// ---------------------------------------------------------------- RoPE
+__global__ void rope_table_kernel(const long long* __restrict__ ids, long long n, int Hp, int Wp, int half,
+                                  float* __restrict__ cos_t, float* __restrict__ sin_t) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int per_row = 3 * half;
+  if (t >= n * per_row) return;
+  const long long row = t / per_row;
+  const int r = (int)(t - row * per_row);
+  const int axis = r / half, j = r - axis * half;
+  const long long id = ids[row];
+  const long long tpf = (long long)Hp * Wp;
+  const long long f = id / tpf;
+  const long long rem = id - tpf * f;
+  const long long yy = rem / Wp;
+  const long long xx = rem - Wp * yy;
+  const double pos = (double)(axis == 0 ? f : (axis == 1 ? yy : xx));
+  const double omega = 1.0 / pow(10000.0, (double)j / (double)half);
+  double s, c;
+  sincos(pos * omega, &s, &c);
+  cos_t[t] = (float)c;
+  sin_t[t] = (float)s;
+}
+
+// one thread per 8 consecutive features of the q or k part of one row
+__global__ void __launch_bounds__(256) rope_apply_kernel(bf16* __restrict__ qkv, long long rows, int D, int hd,
+                                                         int seg, const float* __restrict__ cos_t,
+                                                         const float* __restrict__ sin_t, int transpose) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int vec_per_row = (2 * D) >> 3;
+  if (t >= rows * vec_per_row) return;
+  const long long row = t / vec_per_row;
+  const int col = (int)(t - row * vec_per_row) * 8;      // in [0, 2D)
+  const int di0 = col % hd;                               // dim inside the head (D % hd == 0)
+  if (di0 >= 3 * seg) return;                             // pass-through tail, nothing to do
+  const int half = seg >> 1;
+  bf16* p = qkv + row * 3 * (long long)D + col;
+  float v[8], o[8];
+  load8(p, VJ_BF16, 0, v);
+  const float* ct = cos_t + row * 3 * half;
+  const float* st = sin_t + row * 3 * half;
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    const int di = di0 + k;
+    if (di >= 3 * seg) { o[k] = v[k]; o[k + 1] = v[k + 1]; continue; }
+    const int axis = di / seg;
+    const int i = di - axis * seg;                 // even local index
+    const int ja = i % half, jb = (i + 1) % half;
+    const float ca = ct[axis * half + ja], sa = st[axis * half + ja];
+    const float cb = ct[axis * half + jb], sb = st[axis * half + jb];
+    if (!transpose) {
+      o[k] = v[k] * ca - v[k + 1] * sa;
+      o[k + 1] = v[k + 1] * cb + v[k] * sb;
+    } else {
+      o[k] = ca * v[k] + sb * v[k + 1];
+      o[k + 1] = -sa * v[k] + cb * v[k + 1];
+    }
+  }
+  store8(p, VJ_BF16, 0, o);
+}
+
+// ---------------------------------------------------------------- gather / scatter
+__global__ void __launch_bounds__(256) gather_rows_kernel(const void* __restrict__ src, int src_dtype,
+                                                          void* __restrict__ dst, int dst_dtype,
+                                                          const long long* __restrict__ index,
+                                                          const float* __restrict__ fill, long long n_out, int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= n_out) return;
+  const long long s = index[r];
+  const int nvec = D >> 3;
+  for (int vi = lane; vi < nvec; vi += 32) {
+    float v[8];
+    if (s >= 0) {
+      load8(src, src_dtype, s * D + vi * 8, v);
+    } else if (fill) {
+      load8(fill, VJ_F32, vi * 8, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    }
+    store8(dst, dst_dtype, r * D + vi * 8, v);
+  }
+}
+
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(const void* __restrict__ src, int src_dtype,
+                                                               float* __restrict__ dst,
+                                                               const long long* __restrict__ index, long long n_src,
+                                                               int D) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= n_src) return;
+  const long long d = index[r];
+  if (d < 0) return;
+  const int nvec = D >> 3;
+  for (int vi = lane; vi < nvec; vi += 32) {
+    float v[8];
+    load8(src, src_dtype, r * D + vi * 8, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(dst + d * D + vi * 8 + j, v[j]);
+  }
+}
+
+__global__ void mask_to_rows_kernel(const long long* __restrict__ masks, long long* __restrict__ out, long long B,
+                                    long long K, long long N) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * K) return;
+  out[t] = (t / K) * N + masks[t];
+}
+
+// ---------------------------------------------------------------- tubelet im2col
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ clips,
+                                                     const long long* __restrict__ ids, bf16* __restrict__ cols,
+                                                     int B, int C, int T, int H, int W, int tub, int p, long long K) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  if (r >= (long long)B * K) return;
+  const int Hp = H / p, Wp = W / p;
+  const long long b = r / K;
+  const long long n = ids ? ids[r] : (r - b * K);
+  const int t = (int)(n / (Hp * Wp));
+  const int rem = (int)(n - (long long)t * Hp * Wp);
+  const int hh = rem / Wp, ww = rem - hh * Wp;
+  const int p8 = p >> 3;
+  const int nvec = C * tub * p * p8;
+  const long long KK = (long long)C * tub * p * p;
+  for (int vi = lane; vi < nvec; vi += 32) {
+    const int kw8 = vi % p8;
+    int q = vi / p8;
+    const int kh = q % p; q /= p;
+    const int kt = q % tub;
+    const int c = q / tub;
+    const float* src = clips + ((((long long)b * C + c) * T + (t * tub + kt)) * H + (hh * p + kh)) * W + ww * p + kw8 * 8;
+    float v[8];
+    load8(src, VJ_F32, 0, v);
+    store8(cols, VJ_BF16, r * KK + (long long)vi * 8, v);
+  }
+}
+
+// ---------------------------------------------------------------- fused gather + L1 loss (+ grad)
+__global__ void __launch_bounds__(256) l1_loss_kernel(const bf16* __restrict__ z, const float* __restrict__ h,
+                                                      const long long* __restrict__ idx, bf16* __restrict__ dz,
+                                                      float grad_scale, float* __restrict__ partial, long long B,
+                                                      long long K, long long N, int D) {
+  __shared__ float wsum[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + warp;
+  float acc = 0.f;
+  if (r < B * K) {
+    const long long b = r / K;
+    const long long hrow = b * N + idx[r];
+    const int nvec = D >> 3;
+    for (int vi = lane; vi < nvec; vi += 32) {
+      float zv[8], hv[8], g[8];
+      load8(z, VJ_BF16, r * D + vi * 8, zv);
+      load8(h, VJ_F32, hrow * D + vi * 8, hv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = zv[j] - hv[j];
+        acc += fabsf(d);
+        g[j] = d > 0.f ? grad_scale : (d < 0.f ? -grad_scale : 0.f);
+      }
+      if (dz) store8(dz, VJ_BF16, r * D + vi * 8, g);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) wsum[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += wsum[w];
+    partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(1024) l1_final_kernel(const float* __restrict__ partial, long long n,
+                                                        float* __restrict__ loss_accum, float loss_scale) {
+  __shared__ double sm[32];
+  double s = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) s += (double)partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+    loss_accum[0] += (float)(t * (double)loss_scale);
+  }
+}
+
+// ---------------------------------------------------------------- predictor token ranks
+__global__ void __launch_bounds__(256) argsort_rank_kernel(const long long* __restrict__ ids, int* __restrict__ rank,
+                                                           long long S) {
+  __shared__ long long tile[256];
+  const long long b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long* row = ids + b * S;
+  const long long mine = i < S ? row[i] : 0;
+  int cnt = 0;
+  for (long long j0 = 0; j0 < S; j0 += 256) {
+    const long long j = j0 + threadIdx.x;
+    tile[threadIdx.x] = j < S ? row[j] : 0x7fffffffffffffffll;
+    __syncthreads();
+    const int lim = (int)min((long long)256, S - j0);
+    for (int k = 0; k < lim; ++k) {
+      const long long o = tile[k];
+      cnt += (o < mine) || (o == mine && (j0 + k) < i);
+    }
+    __syncthreads();
+  }
+  if (i < S) rank[b * S + i] = cnt;
+}
+
+// ---------------------------------------------------------------- flat optimizer kernels
+__global__ void __launch_bounds__(256) ema_kernel(float* __restrict__ tgt, const float* __restrict__ src,
+                                                  bf16* __restrict__ shadow, long long n4, float m, float om) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 t = reinterpret_cast<float4*>(tgt)[i];
+    const float4 s = __ldg(reinterpret_cast<const float4*>(src) + i);
+    t.x = __fmaf_rn(om, s.x, __fmul_rn(t.x, m));
+    t.y = __fmaf_rn(om, s.y, __fmul_rn(t.y, m));
+    t.z = __fmaf_rn(om, s.z, __fmul_rn(t.z, m));
+    t.w = __fmaf_rn(om, s.w, __fmul_rn(t.w, m));
+    reinterpret_cast<float4*>(tgt)[i] = t;
+    if (shadow) {
+      uint2 u;
+      u.x = pack_bf16x2(t.x, t.y);
+      u.y = pack_bf16x2(t.z, t.w);
+      reinterpret_cast<uint2*>(shadow)[i] = u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) grad_check_kernel(const float* __restrict__ g, long long n4,
+                                                         float* __restrict__ found_inf) {
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(g) + i);
+    bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) found_inf[0] = 1.0f;
+}
+
+struct AdamArgs {
+  float lr_decay;      // 1 - lr*wd
+  float one_minus_b1, b2, one_minus_b2;
+  float step_size;     // lr / bias_c1
+  float inv_sqrt_bc2;  // 1 / sqrt(bias_c2)
+  float eps;
+};
+
+// one block per 4 tiles of 1024 elements; thread handles one float4 per tile
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                    float* __restrict__ m, float* __restrict__ v,
+                                                    bf16* __restrict__ shadow, const uint8_t* __restrict__ flags,
+                                                    long long ntiles, AdamArgs a, const float* __restrict__ inv_scale,
+                                                    const float* __restrict__ found_inf) {
+  if (found_inf && found_inf[0] != 0.f) return;
+  const float is = inv_scale ? inv_scale[0] : 1.0f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const long long tile = (long long)blockIdx.x * 4 + t;
+    if (tile >= ntiles) return;
+    const uint8_t f = flags[tile];
+    if (f & 2) continue;  // frozen: parameter never received a gradient (torch skips grad=None)
+    const float decay = (f & 1) ? a.lr_decay : 1.0f;
+    const long long i = tile * 256 + threadIdx.x;
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+#define VJ_ADAM1(c)                                                        \
+    {                                                                      \
+      const float gr = gg.c * is;                                          \
+      pp.c *= decay;                                                       \
+      mm.c = mm.c + a.one_minus_b1 * (gr - mm.c);                          \
+      vv.c = vv.c * a.b2 + a.one_minus_b2 * gr * gr;                       \
+      const float denom = sqrtf(vv.c) * a.inv_sqrt_bc2 + a.eps;            \
+      pp.c -= a.step_size * (mm.c / denom);                                \
+    }
+    VJ_ADAM1(x) VJ_ADAM1(y) VJ_ADAM1(z) VJ_ADAM1(w)
+#undef VJ_ADAM1
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow) {
+      uint2 u;
+      u.x = pack_bf16x2(pp.x, pp.y);
+      u.y = pack_bf16x2(pp.z, pp.w);
+      reinterpret_cast<uint2*>(shadow)[i] = u;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n4,
+                                                   long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 s = __ldg(reinterpret_cast<const float4*>(src) + i);
+    uint2 u;
+    u.x = pack_bf16x2(s.x, s.y);
+    u.y = pack_bf16x2(s.z, s.w);
+    reinterpret_cast<uint2*>(dst)[i] = u;
+  }
+  // tail (n not a multiple of 4)
+  const long long tail0 = n4 * 4;
+  const long long i = tail0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+static inline int flat_grid(long long n4) {
+  long long blocks = (n4 + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace vj
+
+using namespace vj;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+static int check_rowvec(const char* who, int64_t rows, int64_t D) {
+  VJ_CHECK(rows >= 0 && D > 0, "%s: bad shape rows=%lld D=%lld", who, (long long)rows, (long long)D);
+  VJ_CHECK(D % 8 == 0, "%s: D=%lld must be a multiple of 8", who, (long long)D);
+  return 0;
+}
+
+extern "C" int vj_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
+                                int y_dtype, float* mean, float* rstd, int64_t rows, int64_t D, float eps,
+                                void* stream) {
+  if (check_rowvec("vj_layernorm_fwd", rows, D)) return -1;
+  VJ_CHECK(D <= LN_MAXV * 256, "vj_layernorm_fwd: D=%lld exceeds %d", (long long)D, LN_MAXV * 256);
+  VJ_CHECK(x && y, "vj_layernorm_fwd: null pointer");
+  if (rows == 0) return 0;
+  ln_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(x, x_dtype, gamma, beta, y, y_dtype, mean,
+                                                                         rstd, rows, (int)D, eps);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t vj_layernorm_bwd_scratch(int64_t rows, int64_t D) {
+  return (size_t)2 * col_chunks(rows) * (size_t)D * sizeof(float);
+}
+
+extern "C" int vj_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
+                                const float* mean, const float* rstd, const void* dres, void* dx, int dx_dtype,
+                                float* dgamma, float* dbeta, void* scratch, int64_t rows, int64_t D, void* stream) {
+  if (check_rowvec("vj_layernorm_bwd", rows, D)) return -1;
+  VJ_CHECK(D <= LN_MAXV * 256, "vj_layernorm_bwd: D=%lld exceeds %d", (long long)D, LN_MAXV * 256);
+  VJ_CHECK(dy && x && mean && rstd && dx, "vj_layernorm_bwd: null pointer");
+  if (rows == 0) return 0;
+  ln_bwd_dx_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(dy, dy_dtype, x, x_dtype, gamma, mean, rstd,
+                                                                            dres, dx, dx_dtype, rows, (int)D);
+  VJ_LAUNCH_CHECK();
+  if (dgamma || dbeta) {
+    VJ_CHECK(scratch != nullptr, "vj_layernorm_bwd: scratch required for dgamma/dbeta");
+    const int chunks = col_chunks(rows);
+    const long long rpc = (rows + chunks - 1) / chunks;
+    float* ps = reinterpret_cast<float*>(scratch);
+    float* px = ps + (size_t)chunks * D;
+    dim3 grid((unsigned)((D + 63) / 64), (unsigned)chunks), block(32, 8);
+    colreduce_kernel<true><<<grid, block, 0, STREAM(stream)>>>(dy, dy_dtype, x, x_dtype, mean, rstd, ps, px, rows,
+                                                              (int)D, rpc);
+    VJ_LAUNCH_CHECK();
+    if (dbeta) colreduce_final_kernel<<<(unsigned)((D + 255) / 256), 256, 0, STREAM(stream)>>>(ps, dbeta, chunks, (int)D, 1);
+    if (dgamma) colreduce_final_kernel<<<(unsigned)((D + 255) / 256), 256, 0, STREAM(stream)>>>(px, dgamma, chunks, (int)D, 1);
+    VJ_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" size_t vj_colsum_scratch(int64_t rows, int64_t D) { return (size_t)col_chunks(rows) * (size_t)D * sizeof(float); }
+
+extern "C" int vj_colsum(const void* x, int x_dtype, float* out, int accumulate, void* scratch, int64_t rows,
+                         int64_t D, void* stream) {
+  VJ_CHECK(rows > 0 && D > 0 && D % 2 == 0, "vj_colsum: bad shape rows=%lld D=%lld", (long long)rows, (long long)D);
+  VJ_CHECK(x && out && scratch, "vj_colsum: null pointer");
+  const int chunks = col_chunks(rows);
+  const long long rpc = (rows + chunks - 1) / chunks;
+  float* ps = reinterpret_cast<float*>(scratch);
+  dim3 grid((unsigned)((D + 63) / 64), (unsigned)chunks), block(32, 8);
+  colreduce_kernel<false><<<grid, block, 0, STREAM(stream)>>>(x, x_dtype, nullptr, 0, nullptr, nullptr, ps, nullptr,
+                                                             rows, (int)D, rpc);
+  VJ_LAUNCH_CHECK();
+  colreduce_final_kernel<<<(unsigned)((D + 255) / 256), 256, 0, STREAM(stream)>>>(ps, out, chunks, (int)D, accumulate);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+static int rope_seg(int head_dim) { return 2 * ((head_dim / 3) / 2); }
+
+extern "C" int vj_rope_table(const int64_t* ids, int64_t n, int Hp, int Wp, int head_dim, float* cos_t, float* sin_t,
+                             void* stream) {
+  VJ_CHECK(ids && cos_t && sin_t && n > 0 && Hp > 0 && Wp > 0, "vj_rope_table: bad arguments");
+  const int half = rope_seg(head_dim) / 2;
+  VJ_CHECK(half > 0, "vj_rope_table: head_dim %d too small", head_dim);
+  const long long total = (long long)n * 3 * half;
+  rope_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const long long*>(ids), n, Hp, Wp, half, cos_t, sin_t);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_rope_apply(void* qkv, int64_t rows, int64_t D, int heads, int head_dim, const float* cos_t,
+                             const float* sin_t, int transpose, void* stream) {
+  VJ_CHECK(qkv && cos_t && sin_t && rows > 0, "vj_rope_apply: bad arguments");
+  VJ_CHECK((int64_t)heads * head_dim == D && head_dim % 8 == 0, "vj_rope_apply: D=%lld != heads*head_dim (%d*%d)",
+           (long long)D, heads, head_dim);
+  const long long total = rows * ((2 * D) >> 3);
+  rope_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<bf16*>(qkv), rows, (int)D, head_dim, rope_seg(head_dim), cos_t, sin_t, transpose);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_gather_rows(const void* src, int src_dtype, void* dst, int dst_dtype, const int64_t* index,
+                              const float* fill, int64_t n_out, int64_t D, void* stream) {
+  if (check_rowvec("vj_gather_rows", n_out, D)) return -1;
+  VJ_CHECK(dst && index, "vj_gather_rows: null pointer");
+  if (n_out == 0) return 0;
+  gather_rows_kernel<<<(unsigned)((n_out + 7) / 8), 256, 0, STREAM(stream)>>>(
+      src, src_dtype, dst, dst_dtype, reinterpret_cast<const long long*>(index), fill, n_out, (int)D);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_scatter_add_rows(const void* src, int src_dtype, float* dst, const int64_t* index, int64_t n_src,
+                                   int64_t D, void* stream) {
+  if (check_rowvec("vj_scatter_add_rows", n_src, D)) return -1;
+  VJ_CHECK(src && dst && index, "vj_scatter_add_rows: null pointer");
+  if (n_src == 0) return 0;
+  scatter_add_rows_kernel<<<(unsigned)((n_src + 7) / 8), 256, 0, STREAM(stream)>>>(
+      src, src_dtype, dst, reinterpret_cast<const long long*>(index), n_src, (int)D);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_mask_to_rows(const int64_t* masks, int64_t* out, int64_t B, int64_t K, int64_t N, void* stream) {
+  VJ_CHECK(masks && out && B > 0 && K > 0, "vj_mask_to_rows: bad arguments");
+  mask_to_rows_kernel<<<(unsigned)((B * K + 255) / 256), 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const long long*>(masks), reinterpret_cast<long long*>(out), B, K, N);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_im2col_tubelets(const float* clips, const int64_t* ids, void* cols, int B, int C, int T, int H,
+                                  int W, int tubelet, int patch, int64_t K, void* stream) {
+  VJ_CHECK(clips && cols && B > 0 && C > 0, "vj_im2col_tubelets: bad arguments");
+  VJ_CHECK(patch % 8 == 0 && T % tubelet == 0 && H % patch == 0 && W % patch == 0 && W % 4 == 0,
+           "vj_im2col_tubelets: geometry T=%d H=%d W=%d tubelet=%d patch=%d unsupported", T, H, W, tubelet, patch);
+  if (!ids) K = (int64_t)(T / tubelet) * (H / patch) * (W / patch);
+  im2col_kernel<<<(unsigned)(((int64_t)B * K + 7) / 8), 256, 0, STREAM(stream)>>>(
+      clips, reinterpret_cast<const long long*>(ids), reinterpret_cast<bf16*>(cols), B, C, T, H, W, tubelet, patch, K);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t vj_l1_scratch(int64_t B, int64_t K, int64_t D) {
+  (void)D;
+  return (size_t)((B * K + 7) / 8) * sizeof(float);
+}
+
+extern "C" int vj_l1_loss(const void* z, const float* h, const int64_t* idx, float* loss_accum, void* dz,
+                          float loss_scale, float grad_scale, void* scratch, int64_t B, int64_t K, int64_t N,
+                          int64_t D, void* stream) {
+  if (check_rowvec("vj_l1_loss", B * K, D)) return -1;
+  VJ_CHECK(z && h && idx && loss_accum && scratch && B * K > 0, "vj_l1_loss: null pointer / empty");
+  const long long blocks = (B * K + 7) / 8;
+  l1_loss_kernel<<<(unsigned)blocks, 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const bf16*>(z), h, reinterpret_cast<const long long*>(idx), reinterpret_cast<bf16*>(dz),
+      grad_scale, reinterpret_cast<float*>(scratch), B, K, N, (int)D);
+  VJ_LAUNCH_CHECK();
+  l1_final_kernel<<<1, 1024, 0, STREAM(stream)>>>(reinterpret_cast<const float*>(scratch), blocks, loss_accum, loss_scale);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_argsort_rank(const int64_t* ids, int32_t* rank, int64_t B, int64_t S, void* stream) {
+  VJ_CHECK(ids && rank && B > 0 && S > 0, "vj_argsort_rank: bad arguments");
+  dim3 grid((unsigned)((S + 255) / 256), (unsigned)B);
+  argsort_rank_kernel<<<grid, 256, 0, STREAM(stream)>>>(reinterpret_cast<const long long*>(ids), rank, S);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_ema_update(float* tgt, const float* src, void* tgt_bf16, int64_t n, float m, float one_minus_m,
+                             void* stream) {
+  VJ_CHECK(tgt && src && n > 0 && n % 4 == 0, "vj_ema_update: n=%lld must be a positive multiple of 4", (long long)n);
+  ema_kernel<<<flat_grid(n / 4), 256, 0, STREAM(stream)>>>(tgt, src, reinterpret_cast<bf16*>(tgt_bf16), n / 4, m,
+                                                         one_minus_m);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_grad_check(const float* g, int64_t n, float* found_inf, void* stream) {
+  VJ_CHECK(g && found_inf && n > 0 && n % 4 == 0, "vj_grad_check: n=%lld must be a positive multiple of 4", (long long)n);
+  grad_check_kernel<<<flat_grid(n / 4), 256, 0, STREAM(stream)>>>(g, n / 4, found_inf);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* p_bf16,
+                             const uint8_t* tile_flags, int64_t n, float lr, float beta1, float beta2, float eps,
+                             float wd, float bias_c1, float bias_c2, const float* inv_scale, const float* found_inf,
+                             void* stream) {
+  VJ_CHECK(p && g && exp_avg && exp_avg_sq && tile_flags, "vj_adamw_step: null pointer");
+  VJ_CHECK(n > 0 && n % 1024 == 0, "vj_adamw_step: n=%lld must be a positive multiple of 1024", (long long)n);
+  AdamArgs a;
+  a.lr_decay = (float)(1.0 - (double)lr * (double)wd);
+  a.one_minus_b1 = (float)(1.0 - (double)beta1);
+  a.b2 = beta2;
+  a.one_minus_b2 = (float)(1.0 - (double)beta2);
+  a.step_size = (float)((double)lr / (double)bias_c1);
+  a.inv_sqrt_bc2 = (float)(1.0 / sqrt((double)bias_c2));
+  a.eps = eps;
+  const long long ntiles = n / 1024;
+  adamw_kernel<<<(unsigned)((ntiles + 3) / 4), 256, 0, STREAM(stream)>>>(p, g, exp_avg, exp_avg_sq,
+                                                                        reinterpret_cast<bf16*>(p_bf16), tile_flags,
+                                                                        ntiles, a, inv_scale, found_inf);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  VJ_CHECK(src && dst && n > 0, "vj_cast_f32_bf16: bad arguments");
+  cast_kernel<<<flat_grid(n / 4), 256, 0, STREAM(stream)>>>(src, reinterpret_cast<bf16*>(dst), n / 4, n);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,400 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> smem ring -> tcgen05.mma -> TMEM
+// (double-buffered accumulator) -> epilogue warps (tcgen05.ld, fused bias / GELU / dGELU / residual).
+//
+//   warp 0   TMA producer (one elected lane)
+//   warp 1   MMA issuer   (one elected lane issues tcgen05.mma / tcgen05.commit)
+//   warp 2   TMEM allocate / free
+//   warp 3   idle
+//   warps 4-7 epilogue: warp (4+q) owns TMEM lanes [32q, 32q+32) == output rows m0+32q..+31
+//
+// Tile: 128 (M) x BN (N) x 64 (K) per stage.  Operands may be K-major or MN-major (transposed
+// storage), which covers forward (x W^T), dgrad (dy W) and wgrad (dy^T x) without any transpose pass.
+#include "common.cuh"
+#include "host_common.h"
+#include "../../include/vjepa2_b200.h"
+
+namespace vj {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmEpi {
+  void* out;
+  const float* bias;
+  const void* residual;
+  void* aux_out;
+  const void* aux_in;
+  long long ldo, ldr, ld_aux;
+  int flags;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;   // TMEM columns between the two accumulator stages
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(BN <= 256 && BN % 16 == 0, "UMMA N must be a multiple of 16 and <= 256");
+  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-B alignment");
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& mb, int& nb) {
+  // bands of 16 m-blocks; inside a band m varies fastest so co-resident CTAs share the same B tile
+  constexpr int GROUP_M = 16;
+  const int per_band = GROUP_M * num_n;
+  const int band = tile / per_band;
+  const int first_m = band * GROUP_M;
+  const int gm = min(GROUP_M, num_m - first_m);
+  const int r = tile - band * per_band;
+  nb = r / gm;
+  mb = first_m + (r - nb * gm);
+}
+
+template <int BN>
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t (&acc)[32], long long row, int col0,
+                                               int N) {
+  // 32 consecutive columns of one output row
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+  const int flags = e.flags;
+  if (flags & VJ_EPI_BIAS) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      if (col0 + i < N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + i));
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    }
+  }
+  if (flags & VJ_EPI_AUX_OUT) {
+    bf16* ap = reinterpret_cast<bf16*>(e.aux_out) + row * e.ld_aux + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      if (col0 + i < N) {
+        uint4 u;
+        u.x = pack_bf16x2(v[i], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
+        u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+        *reinterpret_cast<uint4*>(ap + i) = u;
+      }
+    }
+  }
+  if (flags & VJ_EPI_ROUND_BF16) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = bf16_round(v[i]);
+  }
+  if (flags & VJ_EPI_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (flags & VJ_EPI_DGELU) {
+    const bf16* ap = reinterpret_cast<const bf16*>(e.aux_in) + row * e.ld_aux + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      if (col0 + i < N) {
+        const uint4 u = *reinterpret_cast<const uint4*>(ap + i);
+        v[i] *= dgelu_erf(bf16_lo(u.x)); v[i + 1] *= dgelu_erf(bf16_hi(u.x));
+        v[i + 2] *= dgelu_erf(bf16_lo(u.y)); v[i + 3] *= dgelu_erf(bf16_hi(u.y));
+        v[i + 4] *= dgelu_erf(bf16_lo(u.z)); v[i + 5] *= dgelu_erf(bf16_hi(u.z));
+        v[i + 6] *= dgelu_erf(bf16_lo(u.w)); v[i + 7] *= dgelu_erf(bf16_hi(u.w));
+      }
+    }
+  }
+  if (flags & VJ_EPI_RESIDUAL) {
+    if (flags & VJ_EPI_RES_F32) {
+      const float* rp = reinterpret_cast<const float*>(e.residual) + row * e.ldr + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        if (col0 + i < N) {
+          const float4 r = *reinterpret_cast<const float4*>(rp + i);
+          v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
+        }
+      }
+    } else {
+      const bf16* rp = reinterpret_cast<const bf16*>(e.residual) + row * e.ldr + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (col0 + i < N) {
+          const uint4 u = *reinterpret_cast<const uint4*>(rp + i);
+          v[i] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x); v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
+          v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z); v[i + 6] += bf16_lo(u.w); v[i + 7] += bf16_hi(u.w);
+        }
+      }
+    }
+  }
+  if (flags & VJ_EPI_OUT_F32) {
+    float* op = reinterpret_cast<float*>(e.out) + row * e.ldo + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      if (col0 + i < N) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  } else {
+    bf16* op = reinterpret_cast<bf16*>(e.out) + row * e.ldo + col0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      if (col0 + i < N) {
+        uint4 u;
+        u.x = pack_bf16x2(v[i], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
+        u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+        *reinterpret_cast<uint4*>(op + i) = u;
+      }
+    }
+  }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpi epi, int M,
+            int N, int K) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_m = (M + GEMM_BM - 1) / GEMM_BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int mb, nb;
+        tile_coords(tile, num_m, num_n, mb, nb);
+        const int m0 = mb * GEMM_BM, n0 = nb * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          if (!A_MN) {
+            tma_load_2d(sa, &tmA, &full[stage], kb * GEMM_BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < GEMM_BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, &full[stage], m0 + c * 64, kb * GEMM_BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmB, &full[stage], kb * GEMM_BK, n0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, &full[stage], n0 + c * 64, kb * GEMM_BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc(GEMM_BM, BN, A_MN, B_MN);
+    int stage = 0;
+    uint32_t phase = 0;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint64_t ad = A_MN ? desc_mnmajor<128>(sa, 8192) : desc_kmajor<128>(sa);
+          const uint64_t bd = B_MN ? desc_mnmajor<128>(sb, 8192) : desc_kmajor<128>(sb);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t adk = desc_advance(ad, A_MN ? k * 2048 : k * 32);
+            const uint64_t bdk = desc_advance(bd, B_MN ? k * 2048 : k * 32);
+            umma_bf16(d_tmem, adk, bdk, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (kb == num_kb - 1) umma_commit(&tfull[as]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue
+    const int q = warp & 3;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      int mb, nb;
+      tile_coords(tile, num_m, num_n, mb, nb);
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const long long row = (long long)mb * GEMM_BM + q * 32 + lane;
+      const int n0 = nb * BN;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
+      const int nlim = min(N, n0 + BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        if (n0 + c * 32 >= N) break;   // warp-uniform
+        uint32_t acc[32];
+        tmem_ld32(taddr + c * 32, acc);
+        tmem_ld_wait();
+        if (row < M) epilogue_chunk<BN>(epi, acc, row, n0 + c * 32, nlim);
+      }
+      if constexpr (BN % 32 != 0) {   // 16-column tail of the N tile (BN = 176)
+        constexpr int c = BN / 32;
+        if (n0 + c * 32 < N) {
+          uint32_t lo[16];
+          uint32_t acc[32];
+          tmem_ld16(taddr + c * 32, lo);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { acc[i] = lo[i]; acc[16 + i] = 0u; }
+          if (row < M) epilogue_chunk<BN>(epi, acc, row, n0 + c * 32, nlim);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_gemm(const vj_gemm_args* g, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dimsK[2] = {(uint64_t)g->K, (uint64_t)g->M};
+    const uint64_t dimsM[2] = {(uint64_t)g->M, (uint64_t)g->K};
+    const uint64_t str[1] = {(uint64_t)g->lda * 2};
+    const uint32_t boxK[2] = {64, GEMM_BM};
+    const uint32_t boxM[2] = {64, GEMM_BK};
+    int r = make_tmap_bf16(&tmA, g->a, 2, A_MN ? dimsM : dimsK, str, A_MN ? boxM : boxK, 128);
+    if (r) return r;
+  }
+  {
+    const uint64_t dimsK[2] = {(uint64_t)g->K, (uint64_t)g->N};
+    const uint64_t dimsN[2] = {(uint64_t)g->N, (uint64_t)g->K};
+    const uint64_t str[1] = {(uint64_t)g->ldb * 2};
+    const uint32_t boxK[2] = {64, (uint32_t)BN};
+    const uint32_t boxN[2] = {64, GEMM_BK};
+    int r = make_tmap_bf16(&tmB, g->b, 2, B_MN ? dimsN : dimsK, str, B_MN ? boxN : boxK, 128);
+    if (r) return r;
+  }
+  GemmEpi e;
+  e.out = g->out; e.bias = g->bias; e.residual = g->residual; e.aux_out = g->aux_out; e.aux_in = g->aux_in;
+  e.ldo = g->ldo; e.ldr = g->ldr; e.ld_aux = g->ld_aux; e.flags = g->flags;
+
+  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int num_m = (int)((g->M + GEMM_BM - 1) / GEMM_BM);
+  const int num_n = (int)((g->N + BN - 1) / BN);
+  const int tiles = num_m * num_n;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, e, (int)g->M, (int)g->N, (int)g->K);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+// pick the N tile that wastes the fewest MMA columns; MN-major B needs a multiple of 64
+static int pick_bn(long long N, bool b_mn, long long M) {
+  const int cands_k[] = {256, 176, 128};
+  const int cands_mn[] = {256, 192, 128};
+  const int* c = b_mn ? cands_mn : cands_k;
+  int best = 128;
+  double best_cost = 1e30;
+  const long long num_m = (M + 127) / 128;
+  for (int i = 0; i < 3; ++i) {
+    const int bn = c[i];
+    const long long tiles_n = (N + bn - 1) / bn;
+    // cost ~ issued MMA columns, with a mild penalty for narrow tiles (smem bandwidth) and for
+    // grids that cannot fill the machine
+    double cost = (double)tiles_n * bn * (bn <= 128 ? 1.12 : 1.0);
+    const long long tiles = tiles_n * num_m;
+    if (tiles < 148) cost *= 1.0 + 0.5 * (148 - tiles) / 148.0 * (bn > 128 ? 1.0 : 0.0);
+    if (cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+}  // namespace vj
+
+extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
+  using namespace vj;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  VJ_CHECK(g != nullptr, "vj_gemm: null args");
+  VJ_CHECK(g->M > 0 && g->N > 0 && g->K > 0, "vj_gemm: empty problem M=%lld N=%lld K=%lld", (long long)g->M,
+           (long long)g->N, (long long)g->K);
+  VJ_CHECK(g->M < (1ll << 31) && g->N < (1ll << 31) && g->K < (1ll << 31), "vj_gemm: dimension too large");
+  VJ_CHECK(g->N % 8 == 0, "vj_gemm: N=%lld must be a multiple of 8", (long long)g->N);
+  VJ_CHECK(g->lda % 8 == 0 && g->ldb % 8 == 0, "vj_gemm: lda/ldb must be multiples of 8 elements (TMA 16-B pitch)");
+  VJ_CHECK(g->ldo % 8 == 0, "vj_gemm: ldo must be a multiple of 8");
+  VJ_CHECK(g->a && g->b && g->out, "vj_gemm: null operand");
+  if (g->flags & VJ_EPI_BIAS) VJ_CHECK(g->bias != nullptr, "vj_gemm: bias flag without pointer");
+  if (g->flags & VJ_EPI_RESIDUAL) VJ_CHECK(g->residual != nullptr && g->ldr % 8 == 0, "vj_gemm: bad residual");
+  if (g->flags & VJ_EPI_AUX_OUT) VJ_CHECK(g->aux_out != nullptr && g->ld_aux % 8 == 0, "vj_gemm: bad aux_out");
+  if (g->flags & VJ_EPI_DGELU) VJ_CHECK(g->aux_in != nullptr && g->ld_aux % 8 == 0, "vj_gemm: bad aux_in");
+  const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
+  VJ_CHECK(!(amn && !bmn), "vj_gemm: (A MN-major, B K-major) is not instantiated");
+  const int bn = pick_bn(g->N, bmn, g->M);
+#define VJ_GEMM_CASE(BN_, A_, B_) \
+  if (bn == BN_ && amn == A_ && bmn == B_) return launch_gemm<BN_, A_, B_>(g, stream);
+  VJ_GEMM_CASE(256, false, false)
+  VJ_GEMM_CASE(176, false, false)
+  VJ_GEMM_CASE(128, false, false)
+  VJ_GEMM_CASE(256, false, true)
+  VJ_GEMM_CASE(192, false, true)
+  VJ_GEMM_CASE(128, false, true)
+  VJ_GEMM_CASE(256, true, true)
+  VJ_GEMM_CASE(192, true, true)
+  VJ_GEMM_CASE(128, true, true)
+#undef VJ_GEMM_CASE
+  set_error("vj_gemm: no kernel for BN=%d a_mn=%d b_mn=%d", bn, (int)amn, (int)bmn);
+  return -1;
+}
