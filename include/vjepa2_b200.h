@@ -89,11 +89,12 @@ int vj_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, c
  * rotate_queries_or_keys + separate_positions (modules.py:26-50, 311-365).
  * vj_rope_table: token ids (int64, as produced by MaskCollator) -> cos/sin tables
  *   [n][3*(seg/2)] fp32 with seg = 2*((head_dim/3)/2); axis order frame, height, width.
+ *   ids == NULL means the unmasked sequence: id(row) = row % period (torch.arange, modules.py:337-341).
  * vj_rope_apply: in place on the q and k thirds of qkv [rows][3*D] (bf16); transpose!=0 applies the
  *   adjoint map (backward).  The per-pair map is [[cos a, -sin a],[sin b, cos b]] with the TILED
  *   angle layout of the reference (not a rotation). */
-int vj_rope_table(const int64_t* ids, int64_t n, int Hp, int Wp, int head_dim, float* cos_t, float* sin_t,
-                  void* stream);
+int vj_rope_table(const int64_t* ids, int64_t n, int64_t period, int Hp, int Wp, int head_dim, float* cos_t,
+                  float* sin_t, void* stream);
 int vj_rope_apply(void* qkv, int64_t rows, int64_t D, int heads, int head_dim, const float* cos_t,
                   const float* sin_t, int transpose, void* stream);
 
@@ -123,10 +124,12 @@ int vj_mask_to_rows(const int64_t* masks, int64_t* out, int64_t B, int64_t K, in
 
 /* ------------------------------------------------------------------ patch embed im2col
  * PatchEmbed3D (patch_embed.py:49-52): Conv3d k=s=(tub,p,p) as im2col (+ vj_gemm).
- * clips fp32 [B][C][T][H][W]; ids int64 [B][K] token ids to keep (NULL = all T/tub*H/p*W/p tokens,
- * K ignored); cols bf16 [B*K][C*tub*p*p], K order (c,kt,kh,kw). */
+ * clips fp32 [B][C][T][H][W]; ids int64 [B*reps][K] token ids to keep, row block j*B..(j+1)*B-1 being
+ * mask j of apply_masks(concat=True) (NULL = all T/tub*H/p*W/p tokens, K and reps ignored);
+ * cols bf16 [B*reps*K][C*tub*p*p], K order (c,kt,kh,kw).  Gathering BEFORE the GEMM computes only
+ * the kept tubelets (the reference embeds all tokens, then gathers: vision_transformer.py:188-192). */
 int vj_im2col_tubelets(const float* clips, const int64_t* ids, void* cols, int B, int C, int T, int H, int W,
-                       int tubelet, int patch, int64_t K, void* stream);
+                       int tubelet, int patch, int64_t K, int reps, void* stream);
 
 /* ------------------------------------------------------------------ reductions / loss
  * out[D] (+)= sum_r x[r,:]   (bias gradients).  scratch >= vj_colsum_scratch bytes. */
@@ -135,15 +138,26 @@ int vj_colsum(const void* x, int x_dtype, float* out, int accumulate, void* scra
               void* stream);
 /* loss_fn (train.py:425-435) for one mask: loss_accum += loss_scale * sum |z - h[idx]|,
  * dz = grad_scale * sign(z - h[idx]) (bf16; NULL to skip).  z bf16 [B][K][D]; h fp32 [B][N][D];
- * idx int64 [B][K].  scratch >= vj_l1_scratch bytes.  Deterministic two-stage reduction. */
+ * idx int64 [B][K].  grad_scale_mul: optional device scalar multiplied into grad_scale (the
+ * GradScaler loss scale, train.py:445).  scratch >= vj_l1_scratch bytes.  Deterministic two-stage
+ * reduction. */
 size_t vj_l1_scratch(int64_t B, int64_t K, int64_t D);
 int vj_l1_loss(const void* z, const float* h, const int64_t* idx, float* loss_accum, void* dz, float loss_scale,
-               float grad_scale, void* scratch, int64_t B, int64_t K, int64_t N, int64_t D, void* stream);
+               float grad_scale, const float* grad_scale_mul, void* scratch, int64_t B, int64_t K, int64_t N,
+               int64_t D, void* stream);
 
 /* ------------------------------------------------------------------ predictor token order
  * predictor.py:210-217,240-241: rank[b][i] = position of element i in the ascending (stable) order
  * of ids[b][:]  (== argsort(argsort(ids))). */
 int vj_argsort_rank(const int64_t* ids, int32_t* rank, int64_t B, int64_t S, void* stream);
+/* All index tensors of VisionTransformerPredictor.forward in one pass (predictor.py:206-217,240-242).
+ * S = Kc + Kp; element i of cat(masks_x, masks_y)[b] has stable ascending rank r:
+ *   ids_sorted[b*S + r] = id            asm_idx[b*S + r]    = b*Kc + i (context) or -1 (mask token)
+ *   ctx_pos[b*Kc + i]   = b*S + r       tgt_pos[b*Kp + k]   = b*S + r  (i = Kc + k)
+ *   seq_to_tgt[b*S + r] = b*Kp + k (target) or -1 */
+int vj_pred_indices(const int64_t* masks_x, const int64_t* masks_y, int64_t B, int64_t Kc, int64_t Kp,
+                    int64_t* ids_sorted, int64_t* asm_idx, int64_t* tgt_pos, int64_t* ctx_pos,
+                    int64_t* seq_to_tgt, void* stream);
 
 /* ------------------------------------------------------------------ flat optimizer kernels
  * EMA (train.py:457-465): tgt = fma(1-m, src, tgt*m) over a flat fp32 buffer (the rounding order of
@@ -160,6 +174,10 @@ int vj_grad_check(const float* g, int64_t n, float* found_inf, void* stream);
 int vj_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* p_bf16,
                   const uint8_t* tile_flags, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
                   float bias_c1, float bias_c2, const float* inv_scale, const float* found_inf, void* stream);
+/* GradScaler.update() on device scalars (train.py:451): scale *= backoff if *found_inf else grows by
+ * `growth` every `interval` clean steps; writes inv_scale = 1/(scale*world), clears found_inf. */
+int vj_scaler_update(float* scale, float* inv_scale, int32_t* growth_tracker, float* found_inf, float growth,
+                     float backoff, int interval, float world, void* stream);
 /* fp32 -> bf16 flat cast (weight shadow refresh) */
 int vj_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 

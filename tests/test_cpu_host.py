@@ -1,0 +1,148 @@
+"""CPU tests (no GPU needed): the C-ABI library loads and exports every symbol the header declares, host
+logic (schedules, mask generator, flat layout rules, bucketed all-reduce under gloo with world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "vjepa2_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(vj_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from vjepa2_b200 import _cabi
+    lib = _cabi.load()                       # raises if the .so is missing
+    syms = _header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/vjepa2_b200.h but not exported"
+        assert s in _cabi.SIGNATURES, f"{s} has no ctypes prototype"
+    assert set(_cabi.SIGNATURES) == set(syms)
+    assert lib.vj_abi_version() == 1
+
+
+def test_product_path_has_no_cpu_fallback():
+    """A CPU tensor must raise, not silently run something else; and nothing in the package imports the oracle."""
+    from vjepa2_b200.masks import apply_masks
+    with pytest.raises(RuntimeError):
+        apply_masks(torch.zeros(1, 8, 8), [torch.zeros(1, 2, dtype=torch.int64)])
+    pkg = os.path.join(ROOT, "vjepa2_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "vjepa_oracle" not in src and "import oracle" not in src, fn
+    from functools import partial
+    import torch.nn as nn
+    from vjepa2_b200.vision_transformer import VisionTransformer
+    m = VisionTransformer(img_size=32, patch_size=16, num_frames=4, embed_dim=64, depth=1, num_heads=1,
+                          norm_layer=partial(nn.LayerNorm, eps=1e-6), use_rope=True)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 4, 32, 32))     # parameters on CPU -> loud failure
+
+
+def test_module_tree_and_param_names_match_reference_layout():
+    from functools import partial
+    import torch.nn as nn
+    import vjepa_oracle as O
+    from vjepa2_b200.predictor import vit_predictor
+    from vjepa2_b200.vision_transformer import VisionTransformer
+    enc = VisionTransformer(img_size=96, patch_size=16, num_frames=8, embed_dim=128, depth=2, num_heads=2,
+                            norm_layer=partial(nn.LayerNorm, eps=1e-6), use_rope=True)
+    w = O.init_encoder_weights(128, 2, 4.0)
+    assert list(enc.state_dict().keys()) == list(w.keys())
+    assert all(enc.state_dict()[k].shape == v.shape for k, v in w.items())
+    pred = vit_predictor(img_size=96, patch_size=16, num_frames=8, embed_dim=128, predictor_embed_dim=64, depth=2,
+                         num_heads=2, use_mask_tokens=True, num_mask_tokens=2, use_rope=True)
+    wp = O.init_predictor_weights(128, 64, 2, 2)
+    assert list(pred.state_dict().keys()) == list(wp.keys())
+    # reference init statistics (vision_transformer.py:130-153): LN = (1, 0), biases 0, proj/fc2 rescaled
+    assert float(enc.blocks[1].attn.proj.weight.std()) < float(enc.blocks[1].attn.qkv.weight.std())
+    assert float(pred.mask_tokens[0].abs().max()) == 0.0
+    for name in ("vit_large", "vit_giant_xformers"):
+        from vjepa2_b200 import vision_transformer as V
+        assert callable(getattr(V, name))
+
+
+def test_schedules_match_reference(golden):
+    from vjepa2_b200.schedulers import CosineWDSchedule, WarmupCosineSchedule, momentum_schedule
+    s = WarmupCosineSchedule(warmup_steps=4, start_lr=1e-4, ref_lr=5.25e-4, T_max=20, final_lr=1e-5)
+    w = CosineWDSchedule(ref_wd=0.04, T_max=20, final_wd=0.4)
+    lr = torch.tensor([s.step() for _ in range(24)], dtype=torch.float64)
+    wd = torch.tensor([w.step() for _ in range(24)], dtype=torch.float64)
+    torch.testing.assert_close(lr, golden["sched.lr"], rtol=1e-12, atol=0)
+    torch.testing.assert_close(wd, golden["sched.wd"], rtol=1e-12, atol=0)
+    m = list(momentum_schedule((0.99, 1.0), 10, 2, 1.25))
+    assert len(m) == 26 and m[0] == 0.99 and abs(m[-1] - 1.0) < 1e-12
+
+
+def test_mask_collator_bit_exact(golden):
+    """Same torch CPU RNG state in -> bit-identical indices out."""
+    import vjepa_oracle as O
+    from vjepa2_b200.masks import MaskCollator
+    cfgs = [dict(m) for m in O.DEFAULT_MASK_CFG]
+    coll = MaskCollator(cfgs_mask=cfgs, dataset_fpcs=[16], crop_size=(256, 256), patch_size=(16, 16), tubelet_size=2)
+    torch.manual_seed(239)
+    for it in range(3):
+        batch = [(torch.zeros(1), 0, [list(range(16))]) for _ in range(6)]
+        _, enc, pred = coll(batch)[0]
+        for j in range(2):
+            assert enc[j].dtype == torch.int64
+            assert torch.equal(enc[j], golden[f"mask.it{it}.enc{j}"])
+            assert torch.equal(pred[j], golden[f"mask.it{it}.pred{j}"])
+            # structural invariants: ascending, disjoint, in range
+            assert bool((enc[j][:, 1:] > enc[j][:, :-1]).all()) and bool((pred[j][:, 1:] > pred[j][:, :-1]).all())
+            for b in range(6):
+                assert not set(enc[j][b].tolist()) & set(pred[j][b].tolist())
+            assert int(pred[j].max()) < 2048 and enc[j].shape[1] % 8 == 0
+    coll2 = MaskCollator(cfgs_mask=cfgs, dataset_fpcs=[64], crop_size=(384, 384), patch_size=(16, 16), tubelet_size=2)
+    torch.manual_seed(7)
+    enc, pred = coll2.draw(64, 2)
+    for j in range(2):
+        assert torch.equal(enc[j], golden[f"mask384.enc{j}"]) and torch.equal(pred[j], golden[f"mask384.pred{j}"])
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from vjepa2_b200.train import GradBucketer
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+g = torch.Generator().manual_seed(100 + rank)          # rank-local "gradients" (bench: seed = base + rank)
+flat = torch.randn(10 * 1024, generator=g)
+mine = flat.clone()
+b = GradBucketer()
+assert b.world == world
+for start in range(9 * 1024, -1, -1024 * 3):          # reverse order, like backward
+    b.submit(flat, start, min(start + 3 * 1024, flat.numel()))
+b.wait()
+ref = sum(torch.randn(10 * 1024, generator=torch.Generator().manual_seed(100 + r)) for r in range(world))
+assert torch.allclose(flat, ref, atol=1e-6), float((flat - ref).abs().max())
+# data-parallel averaging is folded into inv_scale = 1/(scale*world)
+avg = flat * (1.0 / world)
+assert torch.allclose(avg, ref / world)
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_bucketed_allreduce_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out.decode()
+        assert b"ok" in out

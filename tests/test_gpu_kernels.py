@@ -1,0 +1,337 @@
+"""GPU parity tests, kernel level: every C-ABI entry point against a plain fp32 PyTorch / oracle
+restatement of the same op on the same seeded inputs.  Integer / copy work is bit-exact; floating point
+uses the bf16 tolerances stated inline (north_star: rel. err <= 1e-2 on activations)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from vjepa2_b200 import _cabi
+    _cabi.load()
+    return torch.device("cuda:0")
+
+
+def relerr(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def randn(*shape, seed=0, dtype=F32, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype)
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 264, 200), (515, 1408, 1408), (64, 4224, 1408), (2049, 384, 1536)])
+def test_gemm_forward(dev, M, N, K):
+    from vjepa2_b200 import ops
+    a = randn(M, K, seed=1, dtype=BF16).to(dev)
+    w = randn(N, K, seed=2, dtype=BF16, scale=0.05).to(dev)
+    bias = randn(N, seed=3).to(dev)
+    out = torch.empty(M, N, dtype=BF16, device=dev)
+    ops.gemm(a, w, out, M, N, K, bias=bias)
+    ref = a.float() @ w.float().t() + bias
+    assert relerr(out, ref) < 4e-3          # one bf16 rounding of the output
+
+
+def test_gemm_epilogues(dev):
+    from vjepa2_b200 import ops
+    M, N, K = 777, 1536, 384
+    a = randn(M, K, seed=1, dtype=BF16).to(dev)
+    w = randn(N, K, seed=2, dtype=BF16, scale=0.05).to(dev)
+    bias = randn(N, seed=3).to(dev)
+    res = randn(M, N, seed=4, dtype=BF16).to(dev)
+    pre = a.float() @ w.float().t() + bias
+    # bias + gelu + aux (fc1)
+    act = torch.empty(M, N, dtype=BF16, device=dev)
+    hpre = torch.empty(M, N, dtype=BF16, device=dev)
+    ops.gemm(a, w, act, M, N, K, bias=bias, gelu=True, round_bf16=True, aux_out=hpre)
+    assert relerr(hpre, pre) < 4e-3
+    assert relerr(act, torch.nn.functional.gelu(pre.bfloat16().float())) < 6e-3
+    # bias + residual (proj / fc2), bf16 and fp32 residual streams
+    out = torch.empty(M, N, dtype=BF16, device=dev)
+    ops.gemm(a, w, out, M, N, K, bias=bias, residual=res, round_bf16=True)
+    assert relerr(out, pre.bfloat16().float() + res.float()) < 4e-3
+    res32 = res.float()
+    out32 = torch.empty(M, N, dtype=F32, device=dev)
+    ops.gemm(a, w, out32, M, N, K, bias=bias, residual=res32, round_bf16=True)
+    assert relerr(out32, pre.bfloat16().float() + res32) < 3e-3
+    # dgelu (backward through the activation)
+    aux = randn(M, N, seed=5, dtype=BF16, scale=2.0).to(dev)
+    dg = torch.empty(M, N, dtype=BF16, device=dev)
+    ops.gemm(a, w, dg, M, N, K, dgelu_aux=aux)
+    x = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    assert relerr(dg, (a.float() @ w.float().t()) * x.grad) < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 1408, 4224), (999, 384, 1152), (128, 128, 64)])
+def test_gemm_dgrad(dev, M, N, K):
+    """dx[M,N] = dy[M,K] @ W[K,N]: B operand consumed MN-major, no transpose copy."""
+    from vjepa2_b200 import ops
+    dy = randn(M, K, seed=1, dtype=BF16).to(dev)
+    w = randn(K, N, seed=2, dtype=BF16, scale=0.05).to(dev)
+    out = torch.empty(M, N, dtype=BF16, device=dev)
+    ops.gemm(dy, w, out, M, N, K, b_mn=True)
+    assert relerr(out, dy.float() @ w.float()) < 4e-3
+
+
+@pytest.mark.parametrize("Nw,Kw,tok", [(1408, 384, 1000), (4224, 1408, 3000), (384, 1536, 72), (128, 128, 64)])
+def test_gemm_wgrad_accumulate(dev, Nw, Kw, tok):
+    """dW[Nw,Kw] += dy[tok,Nw]^T @ x[tok,Kw]: both operands MN-major, fp32 accumulate in place."""
+    from vjepa2_b200 import ops
+    dy = randn(tok, Nw, seed=1, dtype=BF16).to(dev)
+    x = randn(tok, Kw, seed=2, dtype=BF16).to(dev)
+    g0 = randn(Nw, Kw, seed=3).to(dev)
+    g = g0.clone()
+    ops.gemm(dy, x, g, Nw, Kw, tok, a_mn=True, b_mn=True, residual=g)
+    ref = g0 + dy.float().t() @ x.float()
+    assert relerr(g, ref) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def _sdpa_ref(qkv, B, S, H, hd):
+    D = H * hd
+    q, k, v = qkv.float().view(B, S, 3, H, hd).permute(2, 0, 3, 1, 4)
+    att = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    return (att.softmax(-1) @ v).transpose(1, 2).reshape(B * S, D)
+
+
+@pytest.mark.parametrize("B,S,H,hd", [(2, 200, 3, 64), (1, 1000, 2, 64), (2, 72, 2, 32), (1, 700, 3, 32), (3, 8, 2, 64)])
+def test_attention_fwd_bwd(dev, B, S, H, hd):
+    from vjepa2_b200 import ops
+    D = H * hd
+    qkv = randn(B * S, 3 * D, seed=7, dtype=BF16).to(dev)
+    out = torch.empty(B * S, D, dtype=BF16, device=dev)
+    lse = torch.empty(B * H * S, dtype=F32, device=dev)
+    ops.attn_fwd(qkv, out, lse, B, S, H, hd)
+    x = qkv.float().requires_grad_(True)
+    ref = _sdpa_ref(x, B, S, H, hd)
+    assert relerr(out, ref) < 6e-3
+    dout = randn(B * S, D, seed=9, dtype=BF16).to(dev)
+    ref.backward(dout.float())
+    dqkv = torch.empty_like(qkv)
+    ops.attn_bwd(qkv, out, dout, lse, dqkv, B, S, H, hd)
+    for w, name in enumerate("qkv"):
+        e = relerr(dqkv[:, w * D:(w + 1) * D], x.grad[:, w * D:(w + 1) * D])
+        assert e < 1.5e-2, (name, e)
+
+
+def test_attention_rows_sum_to_one_full_size(dev):
+    """Size-independent property at the ViT-g target-encoder shape: V = 1 -> output = 1 exactly-ish."""
+    from vjepa2_b200 import ops
+    B, S, H, hd = 2, 2048, 22, 64
+    D = H * hd
+    qkv = randn(B * S, 3 * D, seed=3, dtype=BF16).to(dev)
+    qkv[:, 2 * D:] = 1.0
+    out = torch.empty(B * S, D, dtype=BF16, device=dev)
+    lse = torch.empty(B * H * S, dtype=F32, device=dev)
+    ops.attn_fwd(qkv, out, lse, B, S, H, hd)
+    assert float((out.float() - 1.0).abs().max()) < 1e-2
+
+
+# ----------------------------------------------------------------------------------------------- LayerNorm
+@pytest.mark.parametrize("rows,D,xd,yd", [(1000, 1408, BF16, BF16), (77, 384, F32, BF16), (513, 128, BF16, F32), (9, 64, F32, F32)])
+def test_layernorm_fwd_bwd(dev, rows, D, xd, yd):
+    from vjepa2_b200 import ops
+    x = randn(rows, D, seed=1, dtype=xd).to(dev)
+    gamma = (1 + 0.1 * randn(D, seed=2)).to(dev)
+    beta = (0.1 * randn(D, seed=3)).to(dev)
+    y = torch.empty(rows, D, dtype=yd, device=dev)
+    mean = torch.empty(rows, dtype=F32, device=dev)
+    rstd = torch.empty(rows, dtype=F32, device=dev)
+    ops.layernorm_fwd(x, gamma, beta, y, mean, rstd, 1e-6)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-6)
+    assert relerr(y, ref) < (4e-3 if yd == BF16 else 1e-5)
+    dy = randn(rows, D, seed=4, dtype=BF16).to(dev)
+    dres = randn(rows, D, seed=5, dtype=xd).to(dev)
+    ref.backward(dy.float())
+    dx = torch.empty(rows, D, dtype=xd, device=dev)
+    dg = torch.ones(D, device=dev)
+    db = torch.ones(D, device=dev)
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres=dres, dgamma=dg, dbeta=db)
+    assert relerr(dx, xr.grad + dres.float()) < (5e-3 if xd == BF16 else 1e-4)
+    assert relerr(dg - 1, gr.grad) < 1e-4 and relerr(db - 1, br.grad) < 1e-4
+    # non-affine variant (train.py:417), in place
+    h = x.float().clone()
+    ops.layernorm_fwd(h, None, None, h, None, None, 1e-5)
+    assert relerr(h, torch.nn.functional.layer_norm(x.float(), (D,), None, None, 1e-5)) < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------- RoPE
+@pytest.mark.parametrize("hd,H", [(64, 2), (32, 3)])
+def test_rope_matches_oracle(dev, hd, H):
+    import vjepa_oracle as O
+    from vjepa2_b200 import ops
+    B, S, Hp, Wp = 2, 50, 6, 5
+    D = H * hd
+    g = torch.Generator().manual_seed(3)
+    ids = torch.randint(0, 4 * Hp * Wp, (B, S), generator=g)
+    qkv = randn(B * S, 3 * D, seed=4, dtype=BF16)
+    cos, sin = ops.rope_table(ids.to(dev), B * S, S, Hp, Wp, hd, dev)
+    x = qkv.to(dev).clone()
+    ops.rope_apply(x, D, H, hd, cos, sin, False)
+    q = qkv.float().view(B, S, 3, H, hd).permute(2, 0, 3, 1, 4)
+    ref_q = O.rope_qk(q[0].double(), ids, Hp, Wp).float()
+    ref_k = O.rope_qk(q[1].double(), ids, Hp, Wp).float()
+    got = x.float().view(B, S, 3, H, hd).permute(2, 0, 3, 1, 4).cpu()
+    assert relerr(got[0], ref_q) < 4e-3 and relerr(got[1], ref_k) < 4e-3
+    assert torch.equal(got[2], q[2])                          # v untouched
+    # adjoint: <R x, y> == <x, R^T y>
+    y = randn(B * S, 3 * D, seed=5, dtype=BF16).to(dev)
+    yt = y.clone()
+    ops.rope_apply(yt, D, H, hd, cos, sin, True)
+    lhs = (x.float()[:, :2 * D] * y.float()[:, :2 * D]).sum()
+    rhs = (qkv.to(dev).float()[:, :2 * D] * yt.float()[:, :2 * D]).sum()
+    assert abs(float(lhs - rhs)) < 2e-2 * abs(float(lhs)) + 1.0
+    # unmasked sequence: ids == None means arange
+    cos2, sin2 = ops.rope_table(None, 2 * S, S, Hp, Wp, hd, dev)
+    cos3, sin3 = ops.rope_table(torch.arange(S).repeat(2).to(dev), 2 * S, S, Hp, Wp, hd, dev)
+    assert torch.equal(cos2, cos3) and torch.equal(sin2, sin3)
+
+
+# ----------------------------------------------------------------------------------------------- gather / im2col / indices
+def test_apply_masks_bit_exact(dev, golden):
+    from vjepa2_b200.masks import apply_masks
+    x, m1, m2 = golden["am.x"].to(dev), golden["am.m1"].to(dev), golden["am.m2"].to(dev)
+    assert torch.equal(apply_masks(x, [m1, m1.flip(1)]).cpu(), golden["am.cat"])
+    assert torch.equal(apply_masks(x, [m2], concat=False)[0].cpu(), golden["am.list1"])
+    xb = x.bfloat16()
+    assert torch.equal(apply_masks(xb, [m2])[..., :].cpu(), golden["am.list1"].bfloat16())
+    # backward with duplicate indices == torch.gather's backward
+    xr = x.clone().requires_grad_(True)
+    out = apply_masks(xr, [m1])
+    dy = randn(*out.shape, seed=2).to(dev)
+    out.backward(dy)
+    xt = x.clone().requires_grad_(True)
+    torch.gather(xt, 1, m1.unsqueeze(-1).expand(-1, -1, x.shape[-1])).backward(dy)
+    assert relerr(xr.grad, xt.grad) < 1e-6
+
+
+def test_apply_masks_full_size_roundtrip(dev):
+    """ViT-g sizes: gather with a permutation then with its inverse is the identity (bit-exact)."""
+    from vjepa2_b200.masks import apply_masks
+    B, N, D = 4, 2048, 1408
+    x = randn(B, N, D, seed=1, dtype=BF16).to(dev)
+    g = torch.Generator().manual_seed(0)
+    perm = torch.stack([torch.randperm(N, generator=g) for _ in range(B)]).to(dev)
+    inv = torch.argsort(perm, dim=1)
+    y = apply_masks(apply_masks(x, [perm]), [inv])
+    assert torch.equal(y, x)
+
+
+def test_im2col_and_patch_embed(dev):
+    import vjepa_oracle as O
+    from vjepa2_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    clips = torch.randn(2, 3, 8, 96, 64, generator=g)
+    cols = ops.im2col_tubelets(clips.to(dev), None, 2, 16)
+    ref = O.im2col_tubelets(clips).reshape(-1, 1536)
+    assert torch.equal(cols.cpu(), ref.bfloat16())             # pure data movement + one rounding
+    N = 4 * 6 * 4
+    ids = torch.stack([torch.randperm(N, generator=g)[:40] for _ in range(4)])   # reps = 2
+    cols2 = ops.im2col_tubelets(clips.to(dev), ids.to(dev), 2, 16)
+    full = O.im2col_tubelets(clips)
+    ref2 = torch.cat([torch.gather(full, 1, ids[j * 2:(j + 1) * 2, :, None].expand(-1, -1, 1536)) for j in range(2)])
+    assert torch.equal(cols2.cpu().view(4, 40, 1536), ref2.bfloat16())
+
+
+def test_pred_indices_match_argsort(dev):
+    from vjepa2_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    B, N, Kc, Kp = 5, 300, 70, 130
+    perm = torch.stack([torch.randperm(N, generator=g) for _ in range(B)])
+    mx, my = perm[:, :Kc].sort(1).values, perm[:, Kc:Kc + Kp].sort(1).values
+    ids_sorted, asm, tgt, ctx, s2t = [t.cpu() for t in ops.pred_indices(mx.to(dev), my.to(dev))]
+    masks = torch.cat([mx, my], 1)
+    argsort = torch.argsort(masks, dim=1)
+    assert torch.equal(ids_sorted, torch.gather(masks, 1, argsort))
+    rev = torch.argsort(argsort, dim=1)
+    S = Kc + Kp
+    base = (torch.arange(B) * S)[:, None]
+    assert torch.equal(ctx.view(B, Kc), rev[:, :Kc] + base)
+    assert torch.equal(tgt.view(B, Kp), rev[:, Kc:] + base)
+    src = argsort                                              # sorted pos -> source element
+    exp_asm = torch.where(src < Kc, src + (torch.arange(B) * Kc)[:, None], torch.full_like(src, -1))
+    exp_s2t = torch.where(src >= Kc, src - Kc + (torch.arange(B) * Kp)[:, None], torch.full_like(src, -1))
+    assert torch.equal(asm.view(B, S), exp_asm) and torch.equal(s2t.view(B, S), exp_s2t)
+    rank = ops.argsort_rank(masks.to(dev)).cpu().long()
+    assert torch.equal(rank, rev)
+
+
+# ----------------------------------------------------------------------------------------------- reductions / loss / optimizer
+def test_colsum_and_l1(dev):
+    from vjepa2_b200 import ops
+    x = randn(3000, 384, seed=1, dtype=BF16).to(dev)
+    out = torch.ones(384, device=dev)
+    ops.colsum(x, out, True)
+    assert relerr(out - 1, x.float().sum(0)) < 1e-5
+    B, K, N, D = 3, 50, 200, 128
+    z = randn(B, K, D, seed=2, dtype=BF16).to(dev)
+    h = randn(B, N, D, seed=3).to(dev)
+    g = torch.Generator().manual_seed(4)
+    idx = torch.stack([torch.randperm(N, generator=g)[:K] for _ in range(B)]).to(dev)
+    acc = torch.zeros(1, device=dev)
+    dz = torch.empty_like(z)
+    mul = torch.full((1,), 4.0, device=dev)
+    ops.l1_loss(z, h, idx, acc, dz, 0.5 / z.numel(), 0.5 / z.numel(), mul)
+    hg = torch.gather(h, 1, idx[..., None].expand(-1, -1, D))
+    ref = 0.5 * (z.float() - hg).abs().mean()
+    assert abs(float(acc) - float(ref)) < 1e-5 * float(ref) + 1e-7
+    assert torch.equal(dz.float(), (torch.sign(z.float() - hg) * (4.0 * 0.5 / z.numel())).bfloat16().float())
+
+
+def test_flat_optimizer_kernels(dev):
+    import vjepa_oracle as O
+    from vjepa2_b200 import ops
+    n = 8 * 1024
+    p = randn(n, seed=1).to(dev)
+    g = randn(n, seed=2, scale=1e-2).to(dev)
+    m = torch.zeros(n, device=dev)
+    v = torch.zeros(n, device=dev)
+    flags = torch.tensor([1, 1, 0, 0, 1, 3, 2, 0], dtype=torch.uint8, device=dev)
+    sh = torch.empty(n, dtype=BF16, device=dev)
+    ops.cast_f32_bf16(p, sh)
+    assert torch.equal(sh, p.bfloat16())
+    pr = {f"w{i}": p[i * 1024:(i + 1) * 1024].cpu().clone().view(32, 32) for i in range(8)}
+    gr = {k: g[i * 1024:(i + 1) * 1024].cpu().clone().view(32, 32) * 0.5 for i, k in enumerate(pr)}
+    names = ["w0", "w1", "b2.bias", "b3.bias", "w4", "w5", "b6.bias", "b7.bias"]
+    pr = {names[i]: t for i, t in enumerate(pr.values())}
+    gr = {names[i]: (t if i not in (5, 6) else None) for i, t in enumerate(gr.values())}
+    st = {k: (torch.zeros_like(t), torch.zeros_like(t)) for k, t in pr.items()}
+    inv_scale = torch.full((1,), 0.5, device=dev)
+    found = torch.zeros(1, device=dev)
+    for step in (1, 2):
+        ops.adamw_step(p, g, m, v, sh, flags, 1e-3, 0.9, 0.999, 1e-8, 0.05, step, inv_scale, found)
+        O.adamw_step(pr, gr, st, step, 1e-3, 0.05)
+    ref = torch.cat([t.reshape(-1) for t in pr.values()])
+    assert relerr(p.cpu(), ref) < 1e-6
+    assert torch.equal(sh, p.bfloat16())
+    # inf -> step skipped, scale backs off
+    g2 = g.clone()
+    g2[5] = float("inf")
+    ops.grad_check(g2, found)
+    assert float(found) == 1.0
+    before = p.clone()
+    ops.adamw_step(p, g2, m, v, sh, flags, 1e-3, 0.9, 0.999, 1e-8, 0.05, 3, inv_scale, found)
+    assert torch.equal(p, before)
+    scale = torch.full((1,), 65536.0, device=dev)
+    tracker = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.scaler_update(scale, inv_scale, tracker, found, world=2.0)
+    assert float(scale) == 32768.0 and float(found) == 0.0 and abs(float(inv_scale) - 1 / 65536.0) < 1e-12
+    # EMA
+    t = randn(n, seed=5).to(dev)
+    t0 = t.clone()
+    ops.ema_update(t, p, sh, 0.99)
+    assert relerr(t, 0.99 * t0 + 0.01 * p) < 1e-6 and torch.equal(sh, t.bfloat16())
+    ops.ema_update(t, p, None, 0.0)
+    assert torch.equal(t, p)

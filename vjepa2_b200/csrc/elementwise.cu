@@ -222,15 +222,15 @@ static inline int col_chunks(long long rows) {
 }
 
 // ---------------------------------------------------------------- RoPE
-__global__ void rope_table_kernel(const long long* __restrict__ ids, long long n, int Hp, int Wp, int half,
-                                  float* __restrict__ cos_t, float* __restrict__ sin_t) {
+__global__ void rope_table_kernel(const long long* __restrict__ ids, long long n, long long period, int Hp, int Wp,
+                                  int half, float* __restrict__ cos_t, float* __restrict__ sin_t) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int per_row = 3 * half;
   if (t >= n * per_row) return;
   const long long row = t / per_row;
   const int r = (int)(t - row * per_row);
   const int axis = r / half, j = r - axis * half;
-  const long long id = ids[row];
+  const long long id = ids ? ids[row] : (row % period);
   const long long tpf = (long long)Hp * Wp;
   const long long f = id / tpf;
   const long long rem = id - tpf * f;
@@ -333,13 +333,15 @@ __global__ void mask_to_rows_kernel(const long long* __restrict__ masks, long lo
 // ---------------------------------------------------------------- tubelet im2col
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ clips,
                                                      const long long* __restrict__ ids, bf16* __restrict__ cols,
-                                                     int B, int C, int T, int H, int W, int tub, int p, long long K) {
+                                                     int B, int C, int T, int H, int W, int tub, int p, long long K,
+                                                     int reps) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + warp;
-  if (r >= (long long)B * K) return;
+  if (r >= (long long)B * reps * K) return;
   const int Hp = H / p, Wp = W / p;
-  const long long b = r / K;
-  const long long n = ids ? ids[r] : (r - b * K);
+  const long long bp = r / K;
+  const long long b = bp % B;             // apply_masks(concat=True) stacks the masks along the batch
+  const long long n = ids ? ids[r] : (r - bp * K);
   const int t = (int)(n / (Hp * Wp));
   const int rem = (int)(n - (long long)t * Hp * Wp);
   const int hh = rem / Wp, ww = rem - hh * Wp;
@@ -362,9 +364,11 @@ __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ c
 // ---------------------------------------------------------------- fused gather + L1 loss (+ grad)
 __global__ void __launch_bounds__(256) l1_loss_kernel(const bf16* __restrict__ z, const float* __restrict__ h,
                                                       const long long* __restrict__ idx, bf16* __restrict__ dz,
-                                                      float grad_scale, float* __restrict__ partial, long long B,
-                                                      long long K, long long N, int D) {
+                                                      float grad_scale, const float* __restrict__ grad_scale_mul,
+                                                      float* __restrict__ partial, long long B, long long K,
+                                                      long long N, int D) {
   __shared__ float wsum[8];
+  if (grad_scale_mul) grad_scale *= grad_scale_mul[0];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * 8 + warp;
   float acc = 0.f;
@@ -433,6 +437,66 @@ __global__ void __launch_bounds__(256) argsort_rank_kernel(const long long* __re
     __syncthreads();
   }
   if (i < S) rank[b * S + i] = cnt;
+}
+
+// predictor.py:206-217,240-242 in one pass: element i of cat(masks_x, masks_y)[b] gets its stable
+// ascending rank; emits every index the assemble / extract steps (and their adjoints) need.
+__global__ void __launch_bounds__(256) pred_indices_kernel(const long long* __restrict__ mx,
+                                                           const long long* __restrict__ my, long long Kc,
+                                                           long long Kp, long long* __restrict__ ids_sorted,
+                                                           long long* __restrict__ asm_idx,
+                                                           long long* __restrict__ tgt_pos,
+                                                           long long* __restrict__ ctx_pos,
+                                                           long long* __restrict__ seq_to_tgt) {
+  __shared__ long long tile[256];
+  const long long S = Kc + Kp;
+  const long long b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long* rx = mx + b * Kc;
+  const long long* ry = my + b * Kp;
+  const long long mine = i < S ? (i < Kc ? rx[i] : ry[i - Kc]) : 0;
+  int cnt = 0;
+  for (long long j0 = 0; j0 < S; j0 += 256) {
+    const long long j = j0 + threadIdx.x;
+    tile[threadIdx.x] = j < S ? (j < Kc ? rx[j] : ry[j - Kc]) : 0x7fffffffffffffffll;
+    __syncthreads();
+    const int lim = (int)min((long long)256, S - j0);
+    for (int k = 0; k < lim; ++k) {
+      const long long o = tile[k];
+      cnt += (o < mine) || (o == mine && (j0 + k) < i);
+    }
+    __syncthreads();
+  }
+  if (i >= S) return;
+  const long long pos = b * S + cnt;
+  ids_sorted[pos] = mine;
+  if (i < Kc) {
+    asm_idx[pos] = b * Kc + i;
+    seq_to_tgt[pos] = -1;
+    ctx_pos[b * Kc + i] = pos;
+  } else {
+    asm_idx[pos] = -1;
+    seq_to_tgt[pos] = b * Kp + (i - Kc);
+    tgt_pos[b * Kp + (i - Kc)] = pos;
+  }
+}
+
+// torch.cuda.amp.GradScaler.update() on device scalars (train.py:451): backoff on inf, growth every
+// `interval` clean steps; refreshes inv_scale = 1/(scale*world) and clears found_inf.
+__global__ void scaler_update_kernel(float* scale, float* inv_scale, int* growth_tracker, float* found_inf,
+                                     float growth, float backoff, int interval, float world) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float s = scale[0];
+  if (found_inf[0] != 0.f) {
+    s *= backoff;
+    growth_tracker[0] = 0;
+  } else {
+    const int t = growth_tracker[0] + 1;
+    if (t >= interval) { s *= growth; growth_tracker[0] = 0; } else growth_tracker[0] = t;
+  }
+  scale[0] = s;
+  inv_scale[0] = 1.0f / (s * world);
+  found_inf[0] = 0.f;
 }
 
 // ---------------------------------------------------------------- flat optimizer kernels
@@ -614,14 +678,15 @@ extern "C" int vj_colsum(const void* x, int x_dtype, float* out, int accumulate,
 
 static int rope_seg(int head_dim) { return 2 * ((head_dim / 3) / 2); }
 
-extern "C" int vj_rope_table(const int64_t* ids, int64_t n, int Hp, int Wp, int head_dim, float* cos_t, float* sin_t,
-                             void* stream) {
-  VJ_CHECK(ids && cos_t && sin_t && n > 0 && Hp > 0 && Wp > 0, "vj_rope_table: bad arguments");
+extern "C" int vj_rope_table(const int64_t* ids, int64_t n, int64_t period, int Hp, int Wp, int head_dim, float* cos_t,
+                             float* sin_t, void* stream) {
+  VJ_CHECK(cos_t && sin_t && n > 0 && Hp > 0 && Wp > 0, "vj_rope_table: bad arguments");
+  VJ_CHECK(ids != nullptr || period > 0, "vj_rope_table: ids == NULL needs period > 0");
   const int half = rope_seg(head_dim) / 2;
   VJ_CHECK(half > 0, "vj_rope_table: head_dim %d too small", head_dim);
   const long long total = (long long)n * 3 * half;
   rope_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<const long long*>(ids), n, Hp, Wp, half, cos_t, sin_t);
+      reinterpret_cast<const long long*>(ids), n, period, Hp, Wp, half, cos_t, sin_t);
   VJ_LAUNCH_CHECK();
   return 0;
 }
@@ -669,13 +734,15 @@ extern "C" int vj_mask_to_rows(const int64_t* masks, int64_t* out, int64_t B, in
 }
 
 extern "C" int vj_im2col_tubelets(const float* clips, const int64_t* ids, void* cols, int B, int C, int T, int H,
-                                  int W, int tubelet, int patch, int64_t K, void* stream) {
+                                  int W, int tubelet, int patch, int64_t K, int reps, void* stream) {
   VJ_CHECK(clips && cols && B > 0 && C > 0, "vj_im2col_tubelets: bad arguments");
   VJ_CHECK(patch % 8 == 0 && T % tubelet == 0 && H % patch == 0 && W % patch == 0 && W % 4 == 0,
            "vj_im2col_tubelets: geometry T=%d H=%d W=%d tubelet=%d patch=%d unsupported", T, H, W, tubelet, patch);
-  if (!ids) K = (int64_t)(T / tubelet) * (H / patch) * (W / patch);
-  im2col_kernel<<<(unsigned)(((int64_t)B * K + 7) / 8), 256, 0, STREAM(stream)>>>(
-      clips, reinterpret_cast<const long long*>(ids), reinterpret_cast<bf16*>(cols), B, C, T, H, W, tubelet, patch, K);
+  if (!ids) { K = (int64_t)(T / tubelet) * (H / patch) * (W / patch); reps = 1; }
+  VJ_CHECK(reps >= 1, "vj_im2col_tubelets: reps must be >= 1");
+  im2col_kernel<<<(unsigned)(((int64_t)B * reps * K + 7) / 8), 256, 0, STREAM(stream)>>>(
+      clips, reinterpret_cast<const long long*>(ids), reinterpret_cast<bf16*>(cols), B, C, T, H, W, tubelet, patch, K,
+      reps);
   VJ_LAUNCH_CHECK();
   return 0;
 }
@@ -686,14 +753,14 @@ extern "C" size_t vj_l1_scratch(int64_t B, int64_t K, int64_t D) {
 }
 
 extern "C" int vj_l1_loss(const void* z, const float* h, const int64_t* idx, float* loss_accum, void* dz,
-                          float loss_scale, float grad_scale, void* scratch, int64_t B, int64_t K, int64_t N,
-                          int64_t D, void* stream) {
+                          float loss_scale, float grad_scale, const float* grad_scale_mul, void* scratch, int64_t B,
+                          int64_t K, int64_t N, int64_t D, void* stream) {
   if (check_rowvec("vj_l1_loss", B * K, D)) return -1;
   VJ_CHECK(z && h && idx && loss_accum && scratch && B * K > 0, "vj_l1_loss: null pointer / empty");
   const long long blocks = (B * K + 7) / 8;
   l1_loss_kernel<<<(unsigned)blocks, 256, 0, STREAM(stream)>>>(
       reinterpret_cast<const bf16*>(z), h, reinterpret_cast<const long long*>(idx), reinterpret_cast<bf16*>(dz),
-      grad_scale, reinterpret_cast<float*>(scratch), B, K, N, (int)D);
+      grad_scale, grad_scale_mul, reinterpret_cast<float*>(scratch), B, K, N, (int)D);
   VJ_LAUNCH_CHECK();
   l1_final_kernel<<<1, 1024, 0, STREAM(stream)>>>(reinterpret_cast<const float*>(scratch), blocks, loss_accum, loss_scale);
   VJ_LAUNCH_CHECK();
@@ -749,6 +816,31 @@ extern "C" int vj_adamw_step(float* p, const float* g, float* exp_avg, float* ex
 extern "C" int vj_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
   VJ_CHECK(src && dst && n > 0, "vj_cast_f32_bf16: bad arguments");
   cast_kernel<<<flat_grid(n / 4), 256, 0, STREAM(stream)>>>(src, reinterpret_cast<bf16*>(dst), n / 4, n);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_pred_indices(const int64_t* masks_x, const int64_t* masks_y, int64_t B, int64_t Kc, int64_t Kp,
+                               int64_t* ids_sorted, int64_t* asm_idx, int64_t* tgt_pos, int64_t* ctx_pos,
+                               int64_t* seq_to_tgt, void* stream) {
+  VJ_CHECK(masks_x && masks_y && ids_sorted && asm_idx && tgt_pos && ctx_pos && seq_to_tgt, "vj_pred_indices: null pointer");
+  VJ_CHECK(B > 0 && Kc > 0 && Kp > 0 && B <= 65535, "vj_pred_indices: bad shape B=%lld Kc=%lld Kp=%lld", (long long)B,
+           (long long)Kc, (long long)Kp);
+  dim3 grid((unsigned)((Kc + Kp + 255) / 256), (unsigned)B);
+  pred_indices_kernel<<<grid, 256, 0, STREAM(stream)>>>(
+      reinterpret_cast<const long long*>(masks_x), reinterpret_cast<const long long*>(masks_y), Kc, Kp,
+      reinterpret_cast<long long*>(ids_sorted), reinterpret_cast<long long*>(asm_idx),
+      reinterpret_cast<long long*>(tgt_pos), reinterpret_cast<long long*>(ctx_pos),
+      reinterpret_cast<long long*>(seq_to_tgt));
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_scaler_update(float* scale, float* inv_scale, int32_t* growth_tracker, float* found_inf,
+                                float growth, float backoff, int interval, float world, void* stream) {
+  VJ_CHECK(scale && inv_scale && growth_tracker && found_inf, "vj_scaler_update: null pointer");
+  scaler_update_kernel<<<1, 32, 0, STREAM(stream)>>>(scale, inv_scale, growth_tracker, found_inf, growth, backoff,
+                                                    interval, world);
   VJ_LAUNCH_CHECK();
   return 0;
 }

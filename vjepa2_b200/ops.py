@@ -1,0 +1,255 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch supplies device memory and streams only; every
+function here enqueues hand-written sm_100a kernels on the current CUDA stream."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _cabi as C
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == BF16:
+        return C.VJ_BF16
+    if t.dtype == F32:
+        return C.VJ_F32
+    raise TypeError(f"vjepa2_b200: unsupported dtype {t.dtype}")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vjepa2_b200: expected CUDA tensors (there is no CPU path)")
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------------------ GEMM
+_gemm_args = C.GemmArgs()
+
+
+def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, bias=None, gelu=False, dgelu_aux=None, residual=None,
+         aux_out=None, round_bf16=False, st=None):
+    """out[M,N] = epi(A[M,K] @ B[N,K]^T).  a/b: 2-D bf16 views whose last dim is contiguous
+    (a: [M,K] or, if a_mn, [K,M]; b likewise).  out: bf16 or fp32 [M,N]."""
+    g = _gemm_args
+    flags = 0
+    if bias is not None:
+        flags |= C.EPI_BIAS
+    if gelu:
+        flags |= C.EPI_GELU
+    if dgelu_aux is not None:
+        flags |= C.EPI_DGELU
+    if residual is not None:
+        flags |= C.EPI_RESIDUAL
+        if residual.dtype == F32:
+            flags |= C.EPI_RES_F32
+    if out.dtype == F32:
+        flags |= C.EPI_OUT_F32
+    if round_bf16:
+        flags |= C.EPI_ROUND_BF16
+    if aux_out is not None:
+        flags |= C.EPI_AUX_OUT
+    g.a, g.b, g.out = a.data_ptr(), b.data_ptr(), out.data_ptr()
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb, g.ldo = a.stride(0), b.stride(0), out.stride(0)
+    g.a_mn_major, g.b_mn_major, g.flags = int(a_mn), int(b_mn), flags
+    g.bias = _p(bias)
+    g.residual = _p(residual)
+    g.ldr = residual.stride(0) if residual is not None else 0
+    aux = aux_out if aux_out is not None else dgelu_aux
+    g.aux_out = _p(aux_out)
+    g.aux_in = _p(dgelu_aux)
+    g.ld_aux = aux.stride(0) if aux is not None else 0
+    C.check(C.load().vj_gemm(ctypes.byref(g), st if st is not None else stream()), "vj_gemm")
+    return out
+
+
+# ------------------------------------------------------------------------------ LayerNorm
+def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-6, st=None):
+    rows, D = x.shape
+    C.check(C.load().vj_layernorm_fwd(x.data_ptr(), _dt(x), _p(gamma), _p(beta), y.data_ptr(), _dt(y), _p(mean),
+                                      _p(rstd), rows, D, eps, st if st is not None else stream()),
+            "vj_layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres=None, dgamma=None, dbeta=None, st=None):
+    rows, D = x.shape
+    scratch = None
+    if dgamma is not None or dbeta is not None:
+        nbytes = C.load().vj_layernorm_bwd_scratch(rows, D)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    if dres is not None and dres.dtype != dx.dtype:
+        raise TypeError("layernorm_bwd: dres must have dx's dtype")
+    C.check(C.load().vj_layernorm_bwd(dy.data_ptr(), _dt(dy), x.data_ptr(), _dt(x), _p(gamma), mean.data_ptr(),
+                                      rstd.data_ptr(), _p(dres), dx.data_ptr(), _dt(dx), _p(dgamma), _p(dbeta),
+                                      _p(scratch), rows, D, st if st is not None else stream()),
+            "vj_layernorm_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------ RoPE
+def rope_seg(head_dim: int) -> int:
+    return 2 * ((head_dim // 3) // 2)
+
+
+def rope_table(ids, n, period, Hp, Wp, head_dim, device, st=None):
+    """ids: int64 [n] flattened token ids, or None for id(row) = row % period -> (cos, sin) fp32 [n, 3*seg/2]."""
+    half = rope_seg(head_dim) // 2
+    cos = torch.empty(n, 3 * half, dtype=F32, device=device)
+    sin = torch.empty_like(cos)
+    C.check(C.load().vj_rope_table(_p(ids), n, period, Hp, Wp, head_dim, cos.data_ptr(), sin.data_ptr(),
+                                   st if st is not None else stream()), "vj_rope_table")
+    return cos, sin
+
+
+def rope_apply(qkv, D, heads, head_dim, cos, sin, transpose=False, st=None):
+    rows = qkv.shape[0]
+    C.check(C.load().vj_rope_apply(qkv.data_ptr(), rows, D, heads, head_dim, cos.data_ptr(), sin.data_ptr(),
+                                   int(transpose), st if st is not None else stream()), "vj_rope_apply")
+    return qkv
+
+
+# ------------------------------------------------------------------------------ attention
+def attn_fwd(qkv, out, lse, B, S, H, head_dim, st=None):
+    C.check(C.load().vj_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, S, H, head_dim,
+                                 st if st is not None else stream()), "vj_attn_fwd")
+    return out
+
+
+def attn_bwd(qkv, out, dout, lse, dqkv, B, S, H, head_dim, st=None):
+    nbytes = C.load().vj_attn_bwd_scratch(B, S, H, head_dim)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
+    C.check(C.load().vj_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                 scratch.data_ptr(), B, S, H, head_dim, st if st is not None else stream()),
+            "vj_attn_bwd")
+    return dqkv
+
+
+# ------------------------------------------------------------------------------ gather / scatter / im2col
+def gather_rows(src, dst, index, fill=None, st=None):
+    n_out, D = dst.shape
+    C.check(C.load().vj_gather_rows(_p(src), _dt(src) if src is not None else C.VJ_F32, dst.data_ptr(), _dt(dst),
+                                    index.data_ptr(), _p(fill), n_out, D, st if st is not None else stream()),
+            "vj_gather_rows")
+    return dst
+
+
+def scatter_add_rows(src, dst, index, st=None):
+    n_src, D = src.shape
+    C.check(C.load().vj_scatter_add_rows(src.data_ptr(), _dt(src), dst.data_ptr(), index.data_ptr(), n_src, D,
+                                         st if st is not None else stream()), "vj_scatter_add_rows")
+    return dst
+
+
+def mask_to_rows(masks, N, st=None):
+    B, K = masks.shape
+    out = torch.empty(B * K, dtype=torch.int64, device=masks.device)
+    C.check(C.load().vj_mask_to_rows(masks.data_ptr(), out.data_ptr(), B, K, N, st if st is not None else stream()),
+            "vj_mask_to_rows")
+    return out
+
+
+def im2col_tubelets(clips, ids, tubelet, patch, st=None):
+    """clips fp32 [B,C,T,H,W]; ids int64 [B,K] or None -> bf16 [B*K, C*tubelet*patch*patch]."""
+    B, Cc, T, H, W = clips.shape
+    if ids is not None:
+        reps, K = ids.shape[0] // B, ids.shape[1]
+    else:
+        reps, K = 1, (T // tubelet) * (H // patch) * (W // patch)
+    cols = torch.empty(B * reps * K, Cc * tubelet * patch * patch, dtype=BF16, device=clips.device)
+    C.check(C.load().vj_im2col_tubelets(clips.data_ptr(), _p(ids), cols.data_ptr(), B, Cc, T, H, W, tubelet, patch, K,
+                                        reps, st if st is not None else stream()), "vj_im2col_tubelets")
+    return cols
+
+
+# ------------------------------------------------------------------------------ reductions / loss
+def colsum(x, out, accumulate=True, st=None):
+    rows, D = x.shape
+    nbytes = C.load().vj_colsum_scratch(rows, D)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    C.check(C.load().vj_colsum(x.data_ptr(), _dt(x), out.data_ptr(), int(accumulate), scratch.data_ptr(), rows, D,
+                               st if st is not None else stream()), "vj_colsum")
+    return out
+
+
+def l1_loss(z, h, idx, loss_accum, dz, loss_scale, grad_scale, grad_scale_mul=None, st=None):
+    """z bf16 [B,K,D]; h fp32 [B,N,D]; idx int64 [B,K].  loss_accum (fp32 [1]) += loss_scale*sum|z-h[idx]|."""
+    B, K, D = z.shape
+    N = h.shape[1]
+    nbytes = C.load().vj_l1_scratch(B, K, D)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+    C.check(C.load().vj_l1_loss(z.data_ptr(), h.data_ptr(), idx.data_ptr(), loss_accum.data_ptr(), _p(dz),
+                                loss_scale, grad_scale, _p(grad_scale_mul), scratch.data_ptr(), B, K, N, D,
+                                st if st is not None else stream()), "vj_l1_loss")
+    return loss_accum
+
+
+def argsort_rank(ids, st=None):
+    B, S = ids.shape
+    rank = torch.empty(B, S, dtype=torch.int32, device=ids.device)
+    C.check(C.load().vj_argsort_rank(ids.data_ptr(), rank.data_ptr(), B, S, st if st is not None else stream()),
+            "vj_argsort_rank")
+    return rank
+
+
+def pred_indices(masks_x, masks_y, st=None):
+    B, Kc = masks_x.shape
+    Kp = masks_y.shape[1]
+    S = Kc + Kp
+    dev = masks_x.device
+    i64 = torch.int64
+    ids_sorted = torch.empty(B, S, dtype=i64, device=dev)
+    asm_idx = torch.empty(B * S, dtype=i64, device=dev)
+    tgt_pos = torch.empty(B * Kp, dtype=i64, device=dev)
+    ctx_pos = torch.empty(B * Kc, dtype=i64, device=dev)
+    seq_to_tgt = torch.empty(B * S, dtype=i64, device=dev)
+    C.check(C.load().vj_pred_indices(masks_x.data_ptr(), masks_y.data_ptr(), B, Kc, Kp, ids_sorted.data_ptr(),
+                                     asm_idx.data_ptr(), tgt_pos.data_ptr(), ctx_pos.data_ptr(),
+                                     seq_to_tgt.data_ptr(), st if st is not None else stream()), "vj_pred_indices")
+    return ids_sorted, asm_idx, tgt_pos, ctx_pos, seq_to_tgt
+
+
+# ------------------------------------------------------------------------------ flat optimizer kernels
+def ema_update(tgt, src, tgt_bf16, m, st=None):
+    n = tgt.numel()
+    C.check(C.load().vj_ema_update(tgt.data_ptr(), src.data_ptr(), _p(tgt_bf16), n, float(m), float(1.0 - m),
+                                   st if st is not None else stream()), "vj_ema_update")
+
+
+def grad_check(g, found_inf, st=None):
+    C.check(C.load().vj_grad_check(g.data_ptr(), g.numel(), found_inf.data_ptr(),
+                                   st if st is not None else stream()), "vj_grad_check")
+
+
+def adamw_step(p, g, m, v, p_bf16, tile_flags, lr, beta1, beta2, eps, wd, step, inv_scale=None, found_inf=None,
+               st=None):
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    C.check(C.load().vj_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(p_bf16),
+                                   tile_flags.data_ptr(), p.numel(), lr, beta1, beta2, eps, wd, bc1, bc2,
+                                   _p(inv_scale), _p(found_inf), st if st is not None else stream()),
+            "vj_adamw_step")
+
+
+def scaler_update(scale, inv_scale, growth_tracker, found_inf, world=1.0, growth=2.0, backoff=0.5, interval=2000,
+                  st=None):
+    C.check(C.load().vj_scaler_update(scale.data_ptr(), inv_scale.data_ptr(), growth_tracker.data_ptr(),
+                                      found_inf.data_ptr(), growth, backoff, interval, float(world),
+                                      st if st is not None else stream()), "vj_scaler_update")
+
+
+def cast_f32_bf16(src, dst, st=None):
+    C.check(C.load().vj_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(),
+                                      st if st is not None else stream()), "vj_cast_f32_bf16")
+    return dst

@@ -1,0 +1,208 @@
+"""The V-JEPA 2 pre-training step (app/vjepa/train.py:409-471) as one fused, autograd-free pipeline.
+
+    h   = LN(target_encoder(clips))                         (no grad, :414-418)
+    z   = predictor(encoder(clips, masks_enc), masks_enc, masks_pred)   (:420-423)
+    L   = mean_j mean |z_j - h[masks_pred_j]|               (:425-435)
+    GradScaler-scaled backward, unscale, inf-skip AdamW step (:444-454)
+    target <- m * target + (1 - m) * encoder                (:456-465)
+
+Differences in *mechanism* (not in result): each (fpc group, mask) pair runs forward and backward back
+to back so only one pair's activations are alive; parameter gradients accumulate in a flat fp32 buffer
+written directly by the wgrad GEMM epilogues; the optimizer, the inf check, the GradScaler update and the
+EMA are flat kernels over that buffer; nothing synchronises with the host (the reference's
+`float(loss)` is left to the caller).  Data parallelism: per-block gradient ranges are all-reduced with
+NCCL as soon as the last backward pass has produced them (DDP semantics, train.py:279-281).
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.distributed as dist
+
+from . import engine, ops
+from .predictor import vit_predictor
+from .schedulers import CosineWDSchedule, WarmupCosineSchedule, momentum_schedule
+from .wrappers import MultiSeqWrapper, PredictorMultiSeqWrapper
+from . import vision_transformer as video_vit
+
+
+def init_video_model(device, patch_size=16, max_num_frames=16, tubelet_size=2, model_name="vit_base", crop_size=224,
+                     pred_depth=6, pred_num_heads=None, pred_embed_dim=384, uniform_power=False,
+                     use_mask_tokens=False, num_mask_tokens=2, zero_init_mask_tokens=True, use_sdpa=False,
+                     use_rope=False, use_silu=False, use_pred_silu=False, wide_silu=False,
+                     use_activation_checkpointing=False):
+    """app/vjepa/utils.py:138-204 (same arguments; same name lookup seam)."""
+    encoder = video_vit.__dict__[model_name](
+        img_size=crop_size, patch_size=patch_size, num_frames=max_num_frames, tubelet_size=tubelet_size,
+        uniform_power=uniform_power, use_sdpa=use_sdpa, use_silu=use_silu, wide_silu=wide_silu,
+        use_activation_checkpointing=use_activation_checkpointing, use_rope=use_rope)
+    encoder = MultiSeqWrapper(encoder)
+    predictor = vit_predictor(
+        img_size=crop_size, use_mask_tokens=use_mask_tokens, patch_size=patch_size, num_frames=max_num_frames,
+        tubelet_size=tubelet_size, embed_dim=encoder.backbone.embed_dim, predictor_embed_dim=pred_embed_dim,
+        depth=pred_depth, num_heads=encoder.backbone.num_heads if pred_num_heads is None else pred_num_heads,
+        uniform_power=uniform_power, num_mask_tokens=num_mask_tokens, zero_init_mask_tokens=zero_init_mask_tokens,
+        use_rope=use_rope, use_sdpa=use_sdpa, use_silu=use_pred_silu, wide_silu=wide_silu,
+        use_activation_checkpointing=use_activation_checkpointing)
+    predictor = PredictorMultiSeqWrapper(predictor)
+    encoder.to(device)
+    predictor.to(device)
+    return encoder, predictor
+
+
+class GradBucketer:
+    """Bucketed, asynchronous all-reduce over ranges of a flat gradient buffer (device agnostic, so the
+    N>1 logic is testable on CPU with gloo).  Ranges are reduced in the order they are submitted."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self._works = []
+
+    def submit(self, flat, start, end):
+        if self.world == 1 or end <= start:
+            return
+        self._works.append(dist.all_reduce(flat[start:end], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def wait(self):
+        for w in self._works:
+            w.wait()
+        self._works = []
+
+
+def _unwrap(m):
+    return m.backbone if hasattr(m, "backbone") else m
+
+
+class JepaTrainStep:
+    """Owns the optimizer state and runs train_step().  Construct once; call step() per iteration."""
+
+    def __init__(self, encoder, predictor, target_encoder=None, *, ipe=300, epochs=800, ipe_scale=1.25, warmup=40,
+                 start_lr=1e-4, lr=5.25e-4, final_lr=5.25e-4, weight_decay=0.04, final_weight_decay=0.04,
+                 ema=(0.99925, 0.99925), betas=(0.9, 0.999), eps=1e-8, loss_exp=1.0, mixed_precision=True,
+                 process_group=None):
+        if loss_exp != 1.0:
+            raise NotImplementedError("vjepa2_b200: loss_exp must be 1.0 (L1), as in every shipped config")
+        self.encoder = _unwrap(encoder)
+        self.predictor = _unwrap(predictor)
+        if target_encoder is None:
+            target_encoder = copy.deepcopy(self.encoder)          # train.py:210
+        self.target_encoder = _unwrap(target_encoder)
+        for p in self.target_encoder.parameters():
+            p.requires_grad = False                                # train.py:282-283
+        self.betas, self.eps = betas, eps
+        T_max = int(ipe_scale * epochs * ipe)
+        self.scheduler = WarmupCosineSchedule(int(warmup * ipe), start_lr, lr, T_max, final_lr)
+        self.wd_scheduler = CosineWDSchedule(weight_decay, T_max, final_weight_decay)
+        self.momentum = momentum_schedule(ema, ipe, epochs, ipe_scale)
+        self.bucketer = GradBucketer(process_group)
+        self.world = self.bucketer.world
+        self._step = 0
+        # the step manages bf16 shadows itself (AdamW / EMA kernels rewrite them)
+        for m in (self.encoder, self.predictor, self.target_encoder):
+            m._manual_shadows = False
+        self.enc_rt = self.encoder.runtime()
+        self.pred_rt = self.predictor.runtime()
+        self.tgt_rt = self.target_encoder.runtime()
+        for m in (self.encoder, self.predictor, self.target_encoder):
+            m._manual_shadows = True
+        dev = self.enc_rt.fs.device
+        self.enc_rt.fs.ensure_grads()
+        self.pred_rt.fs.ensure_grads()
+        self.enc_rt.fs.ensure_adam()
+        self.pred_rt.fs.ensure_adam()
+        if self.enc_rt.fs.total != self.tgt_rt.fs.total:
+            raise RuntimeError("target encoder layout differs from the encoder's")
+        f32 = torch.float32
+        self.loss_accum = torch.zeros(1, dtype=f32, device=dev)
+        init_scale = 65536.0 if mixed_precision else 1.0            # torch.cuda.amp.GradScaler() default
+        self.mixed_precision = mixed_precision
+        self.scale = torch.full((1,), init_scale, dtype=f32, device=dev)
+        self.inv_scale = torch.full((1,), 1.0 / (init_scale * self.world), dtype=f32, device=dev)
+        self.found_inf = torch.zeros(1, dtype=f32, device=dev)
+        self.growth_tracker = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._frozen_key = None
+        # flat ranges of the per-block buckets (reverse order of completion in backward)
+        fs = self.enc_rt.fs
+        self._enc_ranges = {i: fs.range_of(h.params) for i, h in enumerate(self.enc_rt.blocks)}
+        self._enc_ranges[len(self.enc_rt.blocks)] = fs.range_of(self.enc_rt.norm_params)
+        self._enc_ranges[-1] = fs.range_of(self.enc_rt.pe_params)
+
+    # ------------------------------------------------------------------------------------------
+    def _set_frozen_mask_tokens(self, n_groups):
+        toks = list(self.predictor.mask_tokens)
+        used = {i % len(toks) for i in range(n_groups)}
+        key = tuple(sorted(used))
+        if key != self._frozen_key:
+            fs = self.pred_rt.fs
+            fs.set_frozen(toks, False)
+            fs.set_frozen([t for k, t in enumerate(toks) if k not in used], True)
+            self._frozen_key = key
+
+    def step(self, clips, masks_enc, masks_pred):
+        """clips: list (one fp32 [B,3,T,H,W] tensor per fpc group); masks_enc / masks_pred: list over
+        groups of lists over masks of int64 [B, K].  Returns (loss [1] fp32 device tensor, lr, wd)."""
+        self._step += 1
+        new_lr = self.scheduler.step()
+        new_wd = self.wd_scheduler.step()
+        st = ops.stream()
+        enc_rt, pred_rt, tgt_rt = self.enc_rt, self.pred_rt, self.tgt_rt
+        efs, pfs, tfs = enc_rt.fs, pred_rt.fs, tgt_rt.fs
+        enc = self.encoder
+        self._set_frozen_mask_tokens(len(clips))
+        efs.g32.zero_()                                           # optimizer.zero_grad() (train.py:454)
+        pfs.g32.zero_()
+        self.loss_accum.zero_()
+        n_pairs = sum(len(m) for m in masks_enc)
+        p = enc.patch_size
+
+        pair_no = 0
+        for i, c in enumerate(clips):
+            c = c.contiguous()
+            _, _, T, H, W = c.shape
+            grid = (H // p, W // p) if enc.handle_nonsquare_inputs else (enc.grid_size, enc.grid_size)
+            # ---- target (train.py:414-418): no-grad encoder + non-affine LayerNorm, eps 1e-5
+            h, _ = engine.encoder_forward(tgt_rt, c, None, grid, save=False)
+            Bq, N, D = h.shape
+            h2 = h.view(Bq * N, D)
+            ops.layernorm_fwd(h2, None, None, h2, None, None, 1e-5, st)     # in place (row-local)
+            for j, (me, mp) in enumerate(zip(masks_enc[i], masks_pred[i])):
+                pair_no += 1
+                last = pair_no == n_pairs
+                me = me.contiguous()
+                mp = mp.contiguous()
+                # ---- context + predictor forward (train.py:420-423)
+                z, sv_e = engine.encoder_forward(enc_rt, c, me, grid, save=True)
+                pred, sv_p = engine.predictor_forward(pred_rt, z, me, mp, i, save=True)
+                # ---- loss (train.py:425-435) and its gradient, GradScaler-scaled (train.py:445)
+                dz = torch.empty_like(pred)
+                inv = 1.0 / (n_pairs * pred.numel())
+                ops.l1_loss(pred, h, mp, self.loss_accum, dz, inv, inv, self.scale, st)
+                # ---- backward
+                dzenc = engine.predictor_backward(pred_rt, sv_p, dz, pfs.g32)
+                del sv_p
+                if last and self.world > 1:
+                    self.bucketer.submit(pfs.g32, 0, pfs.total)
+                    hook = lambda b, efs=efs: self.bucketer.submit(efs.g32, *self._enc_ranges[b])  # noqa: E731
+                else:
+                    hook = None
+                engine.encoder_backward(enc_rt, sv_e, dzenc, efs.g32, on_block_done=hook)
+                del sv_e
+        self.bucketer.wait()
+
+        # ---- unscale + inf check + AdamW (train.py:446-451; app/vjepa/utils.py:239), flat kernels
+        ops.grad_check(efs.g32, self.found_inf, st)
+        ops.grad_check(pfs.g32, self.found_inf, st)
+        b1, b2 = self.betas
+        for fs in (efs, pfs):
+            ops.adamw_step(fs.p32, fs.g32, fs.exp_avg, fs.exp_avg_sq, fs.p16, fs.flags, new_lr, b1, b2, self.eps,
+                           new_wd, self._step, self.inv_scale, self.found_inf, st)
+        if self.mixed_precision:
+            ops.scaler_update(self.scale, self.inv_scale, self.growth_tracker, self.found_inf, float(self.world), st=st)
+        else:
+            self.found_inf.zero_()
+        # ---- EMA of the target encoder (train.py:456-465) + its bf16 shadow
+        m = next(self.momentum)
+        ops.ema_update(tfs.p32, efs.p32, tfs.p16, m, st)
+        return self.loss_accum, new_lr, new_wd

@@ -1,0 +1,215 @@
+"""Drop-in for src/models/vision_transformer.py of the reference: same constructor arguments, same
+module tree / parameter names, same forward(x, masks=None) signature -- executed on sm_100a kernels.
+
+Scope: video inputs (num_frames > 1) with use_rope=True, exact-GELU MLP, zero
+dropout / drop-path, i.e. every shipped pre-training config.  Anything else raises
+NotImplementedError at construction rather than silently running a different code path.
+"""
+from __future__ import annotations
+
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from . import engine
+from .flat import FlatStore
+from .modules import Block, PatchEmbed3D, init_weights_, rescale_blocks_
+
+
+class _FlatModule(nn.Module):
+    """Shared plumbing: lazily (re)build the flat parameter store and the kernel handles."""
+
+    _RT = None  # set by subclasses: engine.EncoderRT / engine.PredictorRT
+
+    def _init_flat_state(self):
+        self._fs = None
+        self._rt = None
+        self._manual_shadows = False  # the fused train step refreshes the bf16 shadows itself
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._mark_dirty())
+
+    def _mark_dirty(self):
+        if self._fs is not None:
+            self._fs._versions = None
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse) if recurse else super()._apply(fn)
+        self._fs = None
+        self._rt = None
+        return out
+
+    def flat(self) -> FlatStore:
+        fs = self._fs
+        if fs is None or not fs.valid():
+            p0 = next(self.parameters())
+            if not p0.is_cuda:
+                raise RuntimeError("vjepa2_b200: the model must be on a CUDA device (there is no CPU path); "
+                                   "call .cuda() / .to('cuda') first")
+            for p in self.parameters():
+                if p.dtype != torch.float32:
+                    raise RuntimeError("vjepa2_b200: parameters must stay fp32 (master weights); bf16 operands are "
+                                       "kept internally, like autocast in the reference")
+            fs = FlatStore(self, p0.device)
+            self._fs = fs
+            self._rt = None
+        elif not self._manual_shadows and (fs._versions is None or fs.shadows_stale()):
+            fs.refresh_shadows()
+        return fs
+
+    def runtime(self):
+        fs = self.flat()
+        if self._rt is None or self._rt.fs is not fs:
+            self._rt = type(self)._RT(self, fs)
+        return self._rt
+
+
+class _EncoderFn(torch.autograd.Function):
+    """Autograd bridge for drop-in use: one graph node for the whole encoder call."""
+
+    @staticmethod
+    def forward(ctx, model, clips, ids, grid_hw, *params):
+        rt = model.runtime()
+        out, saved = engine.encoder_forward(rt, clips, ids, grid_hw, save=True)
+        ctx.rt, ctx.saved, ctx.nparams = rt, saved, len(params)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rt = ctx.rt
+        fs = rt.fs
+        gbuf = torch.zeros(fs.total, dtype=torch.float32, device=dout.device)
+        engine.encoder_backward(rt, ctx.saved, dout.contiguous(), gbuf)
+        ctx.saved = None
+        grads = tuple(fs.grad_view(gbuf, p) if p.requires_grad else None for p in fs.params)
+        return (None, None, None, None) + grads
+
+
+class VisionTransformer(_FlatModule):
+    """Vision Transformer (video, 3D-RoPE).  Mirrors vision_transformer.py:19-272."""
+
+    _RT = engine.EncoderRT
+
+    def __init__(self, img_size=(224, 224), patch_size=16, num_frames=1, tubelet_size=2, in_chans=3, embed_dim=768,
+                 depth=12, num_heads=12, mlp_ratio=4.0, qkv_bias=True, qk_scale=None, drop_rate=0.0,
+                 attn_drop_rate=0.0, drop_path_rate=0.0, norm_layer=nn.LayerNorm, init_std=0.02, out_layers=None,
+                 uniform_power=False, use_silu=False, wide_silu=True, use_sdpa=True,
+                 use_activation_checkpointing=False, use_rope=False, handle_nonsquare_inputs=True, **kwargs):
+        super().__init__()
+        if num_frames <= 1:
+            raise NotImplementedError("vjepa2_b200: image inputs (PatchEmbed 2-D) are out of scope; num_frames > 1")
+        if not use_rope:
+            raise NotImplementedError("vjepa2_b200: sincos position embeddings are out of scope; use_rope=True")
+        if use_silu:
+            raise NotImplementedError("vjepa2_b200: SwiGLU MLP is out of scope (use_silu=False in the train configs)")
+        if drop_rate or attn_drop_rate or drop_path_rate:
+            raise NotImplementedError("vjepa2_b200: dropout / drop-path > 0 are not implemented")
+        self.num_features = self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.out_layers = out_layers
+        self.handle_nonsquare_inputs = handle_nonsquare_inputs
+        if type(img_size) is int:
+            img_size = (img_size, img_size)
+        self.img_height, self.img_width = img_size
+        self.patch_size = patch_size
+        self.num_frames = num_frames
+        self.tubelet_size = tubelet_size
+        self.is_video = True
+        # kept for API parity; the engine stores what backward needs and never re-runs the forward
+        self.use_activation_checkpointing = use_activation_checkpointing
+        self.patch_embed = PatchEmbed3D(patch_size=patch_size, tubelet_size=tubelet_size, in_chans=in_chans,
+                                        embed_dim=embed_dim)
+        self.num_patches = (num_frames // tubelet_size) * (img_size[0] // patch_size) * (img_size[1] // patch_size)
+        self.uniform_power = uniform_power
+        self.use_rope = use_rope
+        self.pos_embed = None
+        self.grid_size = img_size[0] // patch_size
+        self.blocks = nn.ModuleList([
+            Block(use_rope=use_rope, grid_size=img_size[0] // patch_size, grid_depth=num_frames // tubelet_size,
+                  dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, use_sdpa=use_sdpa, qkv_bias=qkv_bias,
+                  qk_scale=qk_scale, drop=drop_rate, act_layer=nn.GELU, wide_silu=wide_silu, attn_drop=attn_drop_rate,
+                  drop_path=0.0, norm_layer=norm_layer)
+            for _ in range(depth)])
+        self.norm = norm_layer(embed_dim)
+        if not isinstance(self.norm, nn.LayerNorm) or abs(self.norm.eps - 1e-6) > 1e-12:
+            raise NotImplementedError("vjepa2_b200: norm_layer must be partial(nn.LayerNorm, eps=1e-6)")
+        self.init_std = init_std
+        init_weights_(self, init_std)
+        rescale_blocks_(self.blocks)
+        self._init_flat_state()
+
+    def get_num_layers(self):
+        return len(self.blocks)
+
+    def no_weight_decay(self):
+        return {}
+
+    def forward(self, x, masks=None):
+        """x: fp32 clip [B, C, T, H, W]; masks: None | int64 [B, K] | list of such (kept-token ids).
+        Returns fp32 [B * len(masks), K, D] (or [B, N, D]) like the reference under bf16 autocast."""
+        if x.ndim != 5:
+            raise NotImplementedError("vjepa2_b200: expected a video tensor [B, C, T, H, W]")
+        if masks is not None and not isinstance(masks, list):
+            masks = [masks]
+        _, _, T, H, W = x.shape
+        if self.handle_nonsquare_inputs:
+            grid_hw = (H // self.patch_size, W // self.patch_size)
+        else:
+            grid_hw = (self.grid_size, self.grid_size)   # separate_positions falls back to grid_size (modules.py:312)
+        ids = None
+        if masks is not None:
+            ids = torch.cat([m.to(device=x.device, dtype=torch.int64) for m in masks], dim=0).contiguous()
+        x = x.contiguous().float()
+        rt = self.runtime()
+        if self.out_layers is not None:
+            outs, _ = engine.encoder_forward(rt, x, ids, grid_hw, save=False, out_layers=self.out_layers)
+            return outs
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in rt.fs.params)
+        if not needs_grad:
+            out, _ = engine.encoder_forward(rt, x, ids, grid_hw, save=False)
+            return out
+        return _EncoderFn.apply(self, x, ids, grid_hw, *rt.fs.params)
+
+
+def _vit(embed_dim, depth, num_heads, mlp_ratio, patch_size=16, **kwargs):
+    return VisionTransformer(patch_size=patch_size, embed_dim=embed_dim, depth=depth, num_heads=num_heads,
+                             mlp_ratio=mlp_ratio, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
+
+
+# factories with the reference's names (vision_transformer.py:275-475); head_dim must be 32 or 64 for now
+def vit_large(patch_size=16, **kwargs):
+    return _vit(1024, 24, 16, 4, patch_size, **kwargs)
+
+
+def vit_giant_xformers(patch_size=16, **kwargs):
+    return _vit(1408, 40, 22, 48 / 11, patch_size, **kwargs)
+
+
+def vit_huge(patch_size=16, **kwargs):
+    # head_dim 80: rejected by RoPEAttention until the 64+16 split-K attention tile lands
+    return _vit(1280, 32, 16, 4, patch_size, **kwargs)
+
+
+def vit_base(patch_size=16, **kwargs):
+    return _vit(768, 12, 12, 4, patch_size, **kwargs)
+
+
+def vit_small(patch_size=16, **kwargs):
+    return _vit(384, 12, 6, 4, patch_size, **kwargs)
+
+
+def vit_tiny(patch_size=16, **kwargs):
+    return _vit(192, 12, 3, 4, patch_size, **kwargs)
+
+
+def vit_large_rope(patch_size=16, **kwargs):
+    return _vit(1024, 24, 16, 4, patch_size, use_rope=True, **kwargs)
+
+
+def vit_giant_xformers_rope(patch_size=16, **kwargs):
+    return _vit(1408, 40, 22, 48 / 11, patch_size, use_rope=True, **kwargs)
+
+
+VIT_EMBED_DIMS = {
+    "vit_tiny": 192, "vit_small": 384, "vit_base": 768, "vit_large": 1024, "vit_huge": 1280,
+    "vit_giant_xformers": 1408,
+}
