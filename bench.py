@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the V-JEPA 2 pre-training step (BASELINE.json: clips/s & tokens/s per GPU, ViT-g/16,
+16x256x256 clips, batch 24 per GPU, bf16 tensor-core operands; % of bf16 tensor-core peak).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model vit_giant_xformers]
+
+One "step" = one full train step (target fwd, 2x masked context fwd+bwd, 2x predictor fwd+bwd, L1 loss,
+GradScaler check, AdamW, EMA) on one synthetic batch with a fresh multiblock-3D mask draw.  Prints ONE JSON
+line (rank 0).  `value` is timed with inputs resident in HBM; `e2e` goes through the public API with pinned
+host buffers (H2D of clips + masks and D2H of the loss inside the timed region).  `--impl reference` times
+the CPU restatement of the reference step (oracle/, kind "port") on the host cores.
+"""
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODELS = {  # name: (embed_dim, depth, heads, mlp_hidden)
+    "vit_large": (1024, 24, 16, 4096),
+    "vit_giant_xformers": (1408, 40, 22, 6144),
+}
+PRED = dict(dim=384, depth=12, heads=12, hidden=1536)
+# configs/train/vitg16/pretrain-256px-16f.yaml
+OPT = dict(ipe=300, epochs=800, ipe_scale=1.25, warmup=40, start_lr=1e-4, lr=5.25e-4, final_lr=5.25e-4,
+           weight_decay=0.04, final_weight_decay=0.04, ema=(0.99925, 0.99925))
+MASK_CFG = [
+    dict(aspect_ratio=(0.75, 1.5), num_blocks=8, spatial_scale=(0.15, 0.15), temporal_scale=(1.0, 1.0),
+         max_temporal_keep=1.0, max_keep=None, full_complement=False),
+    dict(aspect_ratio=(0.75, 1.5), num_blocks=2, spatial_scale=(0.7, 0.7), temporal_scale=(1.0, 1.0),
+         max_temporal_keep=1.0, max_keep=None, full_complement=False),
+]
+FRAMES, CROP, PATCH, TUB = 16, 256, 16, 2
+NTOK = (FRAMES // TUB) * (CROP // PATCH) ** 2
+
+
+def block_flops(S, D, Hm):
+    """forward FLOPs of one transformer block for one sample of S tokens."""
+    return 8 * S * D * D + 4 * S * D * Hm + 4 * S * S * D
+
+
+def step_flops(model, B, k_enc, k_pred):
+    """Algorithmic FLOPs of one train step for B clips (backward = 2x forward, no recompute counted)."""
+    D, depth, _, Hm = MODELS[model]
+    pe = 2 * 1536 * D
+    f = depth * block_flops(NTOK, D, Hm) + NTOK * pe                       # target forward
+    for ke, kp in zip(k_enc, k_pred):
+        f += 3 * depth * block_flops(ke, D, Hm) + 2 * ke * pe                # context fwd+bwd (+patch embed fwd, wgrad)
+        S = ke + kp
+        f += 3 * (PRED["depth"] * block_flops(S, PRED["dim"], PRED["hidden"]) + 2 * ke * D * PRED["dim"]
+                  + 2 * kp * PRED["dim"] * D)
+    return B * f
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], burst=d["bf16_tflops"], sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                pass
+        busy = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+        return dict(sm_mhz=statistics.median(busy) if busy else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def make_masks(collator, B, steps):
+    out = []
+    for _ in range(steps):
+        enc, pred = collator.draw(FRAMES, B)
+        out.append((enc, pred))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step_time(model, max_seconds=240.0, steps=1, warmup=0, batch=1, log=None):
+    """Times the oracle's restatement of the reference step (fp32, torch CPU, all host threads)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import vjepa_oracle as O
+    D, depth, heads, Hm = MODELS[model]
+    torch.manual_seed(0)
+    w_enc = O.init_encoder_weights(D, depth, Hm / D, seed=0)
+    w_pred = O.init_predictor_weights(D, PRED["dim"], PRED["depth"], 6, seed=1)
+    st = O.StepState(w_enc, w_pred, dict(depth=depth, heads=heads),
+                     dict(depth=PRED["depth"], heads=PRED["heads"], grid_size=CROP // PATCH, num_patches=NTOK,
+                          num_mask_tokens=6), dict(OPT, loss_exp=1.0))
+    del w_enc, w_pred
+    gens = O.make_mask_generators(O.DEFAULT_MASK_CFG, (CROP, CROP), FRAMES)
+    torch.manual_seed(239)
+    g = torch.Generator().manual_seed(0)
+    times, flops = [], []
+    t_begin = time.time()
+    for it in range(warmup + steps):
+        clips = torch.randn(batch, 3, FRAMES, CROP, CROP, generator=g)
+        masks = [gen(batch) for gen in gens]
+        me, mp = [m[0] for m in masks], [m[1] for m in masks]
+        t0 = time.time()
+        loss = O.train_step(st, clips, me, mp)
+        dt = time.time() - t0
+        if log:
+            log(f"cpu reference step {it}: {dt:.1f}s loss {loss:.4f}")
+        if it >= warmup:
+            times.append(dt)
+            flops.append(step_flops(model, batch, [m.shape[1] for m in me], [m.shape[1] for m in mp]))
+        if time.time() - t_begin > max_seconds and times:
+            break
+    return times, flops, batch
+
+
+# ---------------------------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="vit_giant_xformers", choices=list(MODELS))
+    ap.add_argument("--batch", type=int, default=24)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = f"clips/sec ({'ViT-g/16' if args.model == 'vit_giant_xformers' else 'ViT-L/16'} V-JEPA 2 pretrain step, " \
+             f"16x256x256 clips, fwd+bwd+AdamW+EMA)"
+    config = dict(workload=f"{args.model} pretrain step (configs/train/vitg16/pretrain-256px-16f.yaml shapes), "
+                           f"batch {args.batch}/GPU, multiblock3d masks (8x0.15 + 2x0.7), predictor depth 12 / 384",
+                  global_batch=args.batch * world, tokens_per_clip=NTOK, parallelism=f"dp{world}",
+                  l2_policy="working set (>= 2 GB of bf16 weights + activations per step) exceeds the 126 MB L2; no flush")
+
+    def log(msg):
+        print(f"[bench r{rank}] {msg}", file=sys.stderr, flush=True)
+
+    # ------------------------------------------------------------------ reference arm (CPU port)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import torch
+        cores = torch.get_num_threads()
+        times, flops, b = cpu_reference_step_time(args.model, max_seconds=200.0, steps=max(1, args.steps),
+                                                  warmup=min(1, args.warmup), batch=1, log=log)
+        ms = 1e3 * sum(times) / len(times)
+        val = b / (ms / 1e3)
+        line = dict(metric=metric, value=val, unit="clips/s", impl="reference", n_gpus=args.gpus, device="cpu",
+                    steps=len(times),
+                    steps_requested=args.steps, warmup=min(1, args.warmup), ms_per_step=ms, higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config,
+                    tokens_per_s=val * NTOK, tflops=sum(flops) / sum(times) / 1e12,
+                    cpu_baseline=dict(value=val, unit="clips/s", cores=cores, kind="port",
+                                      sample=f"{len(times)} step(s) of 1 clip (same model, masks and optimizer; "
+                                             f"reference batch is {args.batch}), oracle/vjepa_oracle.py on torch CPU fp32"),
+                    e2e=dict(value=val, unit="clips/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    from vjepa2_b200 import ops
+    from vjepa2_b200 import train as T
+    from vjepa2_b200.masks import MaskCollator
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = read_peaks()
+
+    t0 = time.time()
+    torch.manual_seed(0)                               # identical init on every rank (DDP broadcasts rank 0's)
+    with torch.device(dev):
+        encoder, predictor = T.init_video_model(
+            device=dev, patch_size=PATCH, max_num_frames=FRAMES, tubelet_size=TUB, model_name=args.model,
+            crop_size=CROP, pred_depth=PRED["depth"], pred_num_heads=PRED["heads"], pred_embed_dim=PRED["dim"],
+            uniform_power=True, use_mask_tokens=True, num_mask_tokens=6, zero_init_mask_tokens=True, use_sdpa=True,
+            use_rope=True, use_activation_checkpointing=True)
+    step = T.JepaTrainStep(encoder, predictor, **OPT)
+    if world > 1:                                      # DDP's construction-time parameter broadcast
+        for fs in (step.enc_rt.fs, step.pred_rt.fs, step.tgt_rt.fs):
+            dist.broadcast(fs.p32, 0)
+            fs.refresh_shadows()
+    log(f"models built in {time.time() - t0:.1f}s; encoder params "
+        f"{sum(p.numel() for p in step.encoder.parameters()) / 1e6:.1f}M")
+
+    B = args.batch
+    n_e2e = 0 if args.no_e2e else max(2, min(args.steps, 5))
+    total = args.warmup + args.steps + n_e2e + 1
+    collator = MaskCollator(cfgs_mask=MASK_CFG, dataset_fpcs=[FRAMES], crop_size=(CROP, CROP), patch_size=(PATCH, PATCH),
+                            tubelet_size=TUB)
+    torch.manual_seed(239 + rank)                      # config seed 239; rank-local mask / clip streams
+    masks_host = make_masks(collator, B, total)
+    gclip = torch.Generator().manual_seed(1000 + rank)
+    clips_host = torch.randn(B, 3, FRAMES, CROP, CROP, generator=gclip).pin_memory()
+    clips_dev = clips_host.to(dev, non_blocking=True)
+    masks_dev = [([m.to(dev) for m in e], [m.to(dev) for m in p]) for e, p in masks_host]
+    torch.cuda.synchronize()
+
+    def run_step(i, clips):
+        e, p = masks_dev[i]
+        return step.step([clips], [e], [p])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        run_step(i, clips_dev)
+    barrier()
+
+    # ---- timed region: device-resident inputs, CUDA events on the launching stream
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ops.LAUNCHES
+    ev0.record()
+    for i in range(args.warmup, args.warmup + args.steps):
+        loss, _, _ = run_step(i, clips_dev)
+    ev1.record()
+    torch.cuda.synchronize()
+    launches = ops.LAUNCHES - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    barrier()
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    loss_val = float(loss.item())
+    flops_timed = sum(step_flops(args.model, B, [m.shape[1] for m in masks_host[i][0]],
+                                 [m.shape[1] for m in masks_host[i][1]])
+                      for i in range(args.warmup, args.warmup + args.steps))
+    clips_s = world * B * args.steps / (ms_total / 1e3)
+    tflops_gpu = flops_timed / (ms_total / 1e3) / 1e12          # per GPU (each rank does B clips)
+
+    # ---- e2e: public API with pinned host inputs; H2D + D2H inside the timed region (wall clock)
+    e2e = None
+    if n_e2e:
+        base = args.warmup + args.steps
+        h2d = clips_host.numel() * 4 + sum(m.numel() * 8 for m in masks_host[base][0] + masks_host[base][1])
+        pinned_masks = [([m.pin_memory() for m in e], [m.pin_memory() for m in p]) for e, p in masks_host]
+        barrier()
+        t_start = time.perf_counter()
+        for i in range(base, base + n_e2e):
+            c = clips_host.to(dev, non_blocking=True)
+            e = [m.to(dev, non_blocking=True) for m in pinned_masks[i][0]]
+            p = [m.to(dev, non_blocking=True) for m in pinned_masks[i][1]]
+            l, _, _ = step.step([c], [e], [p])
+            _ = float(l.item())                                 # train.py:468 host read of the loss
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t_start
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = dict(value=world * B * n_e2e / float(tt.item()), unit="clips/s", h2d_bytes_per_step=h2d,
+                   d2h_bytes_per_step=4, steps=n_e2e)
+
+    # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA events, one instrumented step
+    #      (every rank runs the step -- it contains the gradient all-reduce -- rank 0 instruments it)
+    import vjepa2_b200.engine as eng
+    recs = []
+    real_gemm = ops.gemm
+
+    def timed_gemm(a, b, out, M, N, K, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = real_gemm(a, b, out, M, N, K, **kw)
+        e.record()
+        recs.append((s, e, 2.0 * M * N * K))
+        return r
+
+    if rank == 0:
+        eng.ops.gemm = timed_gemm
+    barrier()
+    evs, eve = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evs.record()
+    run_step(total - 1, clips_dev)
+    eve.record()
+    torch.cuda.synchronize()
+    eng.ops.gemm = real_gemm
+    roof = None
+    if rank == 0:
+        g_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+        g_fl = sum(f for _, _, f in recs)
+        achieved = g_fl / (g_ms / 1e3) / 1e12
+        roof = dict(bound="tensor", kernel="vj::gemm_kernel (tcgen05 GEMM, all fwd/dgrad/wgrad launches of one step)",
+                    achieved=achieved, peak=peaks["sustained"], unit="TFLOP/s", frac=achieved / peaks["sustained"],
+                    peak_source=f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)",
+                    traffic=None, launches=len(recs), gemm_ms_per_step=g_ms, step_ms_instrumented=evs.elapsed_time(eve),
+                    gemm_share_of_step=g_ms / evs.elapsed_time(eve))
+    barrier()
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same step on the host cores
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del step, encoder, predictor
+        torch.cuda.empty_cache()
+        try:
+            times, _, b = cpu_reference_step_time(args.model, max_seconds=120.0, steps=1, warmup=0, batch=1, log=log)
+            cpu = dict(value=b / (sum(times) / len(times)), unit="clips/s", cores=torch.get_num_threads(), kind="port",
+                       sample=f"1 step of 1 clip (same model / masks / optimizer; the GPU arm runs batch {B}), "
+                              f"oracle/vjepa_oracle.py on torch CPU fp32")
+        except Exception as ex:  # the CPU leg must never take the GPU numbers down with it
+            cpu = dict(value=None, unit="clips/s", cores=torch.get_num_threads(), kind="port", sample=f"failed: {ex}")
+
+    if rank == 0:
+        line = dict(metric=metric, value=clips_s, unit="clips/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                    data="synthetic", config=config, tokens_per_s=clips_s * NTOK, clips_per_s_per_gpu=clips_s / world,
+                    tflops_per_gpu=tflops_gpu, frac_of_nominal_2250=tflops_gpu / 2250.0,
+                    frac_of_measured_sustained=tflops_gpu / peaks["sustained"],
+                    frac_of_measured_burst=tflops_gpu / peaks["burst"], loss=loss_val, clocks=clocks,
+                    gpu_launches=launches, e2e=e2e, roofline=roof, cpu_baseline=cpu)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

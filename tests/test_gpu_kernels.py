@@ -19,7 +19,7 @@ def dev():
 
 
 def relerr(a, b):
-    a, b = a.float(), b.float()
+    a, b = a.detach().float(), b.detach().float()
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 

@@ -33,6 +33,23 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# kernels launched per C-ABI call (bench.py reports the total as `gpu_launches`)
+KERNELS_PER_CALL = {
+    "vj_gemm": 1, "vj_layernorm_fwd": 1, "vj_layernorm_bwd": 4, "vj_rope_table": 1, "vj_rope_apply": 1,
+    "vj_attn_fwd": 1, "vj_attn_bwd": 3, "vj_gather_rows": 1, "vj_scatter_add_rows": 1, "vj_mask_to_rows": 1,
+    "vj_im2col_tubelets": 1, "vj_colsum": 2, "vj_l1_loss": 2, "vj_argsort_rank": 1, "vj_pred_indices": 1,
+    "vj_ema_update": 1, "vj_grad_check": 1, "vj_adamw_step": 1, "vj_scaler_update": 1, "vj_cast_f32_bf16": 1,
+}
+LAUNCHES = 0
+_real_check = C.check
+
+
+def _counting_check(rc, what=""):
+    global LAUNCHES
+    LAUNCHES += KERNELS_PER_CALL.get(what, 1)
+    _real_check(rc, what)
+
+
 # ------------------------------------------------------------------------------ GEMM
 _gemm_args = C.GemmArgs()
 
@@ -70,14 +87,14 @@ def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, bias=None, gelu=False, d
     g.aux_out = _p(aux_out)
     g.aux_in = _p(dgelu_aux)
     g.ld_aux = aux.stride(0) if aux is not None else 0
-    C.check(C.load().vj_gemm(ctypes.byref(g), st if st is not None else stream()), "vj_gemm")
+    _counting_check(C.load().vj_gemm(ctypes.byref(g), st if st is not None else stream()), "vj_gemm")
     return out
 
 
 # ------------------------------------------------------------------------------ LayerNorm
 def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-6, st=None):
     rows, D = x.shape
-    C.check(C.load().vj_layernorm_fwd(x.data_ptr(), _dt(x), _p(gamma), _p(beta), y.data_ptr(), _dt(y), _p(mean),
+    _counting_check(C.load().vj_layernorm_fwd(x.data_ptr(), _dt(x), _p(gamma), _p(beta), y.data_ptr(), _dt(y), _p(mean),
                                       _p(rstd), rows, D, eps, st if st is not None else stream()),
             "vj_layernorm_fwd")
     return y
@@ -91,7 +108,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres=None, dgamma=None, dbeta=No
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     if dres is not None and dres.dtype != dx.dtype:
         raise TypeError("layernorm_bwd: dres must have dx's dtype")
-    C.check(C.load().vj_layernorm_bwd(dy.data_ptr(), _dt(dy), x.data_ptr(), _dt(x), _p(gamma), mean.data_ptr(),
+    _counting_check(C.load().vj_layernorm_bwd(dy.data_ptr(), _dt(dy), x.data_ptr(), _dt(x), _p(gamma), mean.data_ptr(),
                                       rstd.data_ptr(), _p(dres), dx.data_ptr(), _dt(dx), _p(dgamma), _p(dbeta),
                                       _p(scratch), rows, D, st if st is not None else stream()),
             "vj_layernorm_bwd")
@@ -108,21 +125,21 @@ def rope_table(ids, n, period, Hp, Wp, head_dim, device, st=None):
     half = rope_seg(head_dim) // 2
     cos = torch.empty(n, 3 * half, dtype=F32, device=device)
     sin = torch.empty_like(cos)
-    C.check(C.load().vj_rope_table(_p(ids), n, period, Hp, Wp, head_dim, cos.data_ptr(), sin.data_ptr(),
+    _counting_check(C.load().vj_rope_table(_p(ids), n, period, Hp, Wp, head_dim, cos.data_ptr(), sin.data_ptr(),
                                    st if st is not None else stream()), "vj_rope_table")
     return cos, sin
 
 
 def rope_apply(qkv, D, heads, head_dim, cos, sin, transpose=False, st=None):
     rows = qkv.shape[0]
-    C.check(C.load().vj_rope_apply(qkv.data_ptr(), rows, D, heads, head_dim, cos.data_ptr(), sin.data_ptr(),
+    _counting_check(C.load().vj_rope_apply(qkv.data_ptr(), rows, D, heads, head_dim, cos.data_ptr(), sin.data_ptr(),
                                    int(transpose), st if st is not None else stream()), "vj_rope_apply")
     return qkv
 
 
 # ------------------------------------------------------------------------------ attention
 def attn_fwd(qkv, out, lse, B, S, H, head_dim, st=None):
-    C.check(C.load().vj_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, S, H, head_dim,
+    _counting_check(C.load().vj_attn_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), B, S, H, head_dim,
                                  st if st is not None else stream()), "vj_attn_fwd")
     return out
 
@@ -130,7 +147,7 @@ def attn_fwd(qkv, out, lse, B, S, H, head_dim, st=None):
 def attn_bwd(qkv, out, dout, lse, dqkv, B, S, H, head_dim, st=None):
     nbytes = C.load().vj_attn_bwd_scratch(B, S, H, head_dim)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
-    C.check(C.load().vj_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+    _counting_check(C.load().vj_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
                                  scratch.data_ptr(), B, S, H, head_dim, st if st is not None else stream()),
             "vj_attn_bwd")
     return dqkv
@@ -139,7 +156,7 @@ def attn_bwd(qkv, out, dout, lse, dqkv, B, S, H, head_dim, st=None):
 # ------------------------------------------------------------------------------ gather / scatter / im2col
 def gather_rows(src, dst, index, fill=None, st=None):
     n_out, D = dst.shape
-    C.check(C.load().vj_gather_rows(_p(src), _dt(src) if src is not None else C.VJ_F32, dst.data_ptr(), _dt(dst),
+    _counting_check(C.load().vj_gather_rows(_p(src), _dt(src) if src is not None else C.VJ_F32, dst.data_ptr(), _dt(dst),
                                     index.data_ptr(), _p(fill), n_out, D, st if st is not None else stream()),
             "vj_gather_rows")
     return dst
@@ -147,7 +164,7 @@ def gather_rows(src, dst, index, fill=None, st=None):
 
 def scatter_add_rows(src, dst, index, st=None):
     n_src, D = src.shape
-    C.check(C.load().vj_scatter_add_rows(src.data_ptr(), _dt(src), dst.data_ptr(), index.data_ptr(), n_src, D,
+    _counting_check(C.load().vj_scatter_add_rows(src.data_ptr(), _dt(src), dst.data_ptr(), index.data_ptr(), n_src, D,
                                          st if st is not None else stream()), "vj_scatter_add_rows")
     return dst
 
@@ -155,7 +172,7 @@ def scatter_add_rows(src, dst, index, st=None):
 def mask_to_rows(masks, N, st=None):
     B, K = masks.shape
     out = torch.empty(B * K, dtype=torch.int64, device=masks.device)
-    C.check(C.load().vj_mask_to_rows(masks.data_ptr(), out.data_ptr(), B, K, N, st if st is not None else stream()),
+    _counting_check(C.load().vj_mask_to_rows(masks.data_ptr(), out.data_ptr(), B, K, N, st if st is not None else stream()),
             "vj_mask_to_rows")
     return out
 
@@ -168,7 +185,7 @@ def im2col_tubelets(clips, ids, tubelet, patch, st=None):
     else:
         reps, K = 1, (T // tubelet) * (H // patch) * (W // patch)
     cols = torch.empty(B * reps * K, Cc * tubelet * patch * patch, dtype=BF16, device=clips.device)
-    C.check(C.load().vj_im2col_tubelets(clips.data_ptr(), _p(ids), cols.data_ptr(), B, Cc, T, H, W, tubelet, patch, K,
+    _counting_check(C.load().vj_im2col_tubelets(clips.data_ptr(), _p(ids), cols.data_ptr(), B, Cc, T, H, W, tubelet, patch, K,
                                         reps, st if st is not None else stream()), "vj_im2col_tubelets")
     return cols
 
@@ -178,7 +195,7 @@ def colsum(x, out, accumulate=True, st=None):
     rows, D = x.shape
     nbytes = C.load().vj_colsum_scratch(rows, D)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    C.check(C.load().vj_colsum(x.data_ptr(), _dt(x), out.data_ptr(), int(accumulate), scratch.data_ptr(), rows, D,
+    _counting_check(C.load().vj_colsum(x.data_ptr(), _dt(x), out.data_ptr(), int(accumulate), scratch.data_ptr(), rows, D,
                                st if st is not None else stream()), "vj_colsum")
     return out
 
@@ -189,7 +206,7 @@ def l1_loss(z, h, idx, loss_accum, dz, loss_scale, grad_scale, grad_scale_mul=No
     N = h.shape[1]
     nbytes = C.load().vj_l1_scratch(B, K, D)
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
-    C.check(C.load().vj_l1_loss(z.data_ptr(), h.data_ptr(), idx.data_ptr(), loss_accum.data_ptr(), _p(dz),
+    _counting_check(C.load().vj_l1_loss(z.data_ptr(), h.data_ptr(), idx.data_ptr(), loss_accum.data_ptr(), _p(dz),
                                 loss_scale, grad_scale, _p(grad_scale_mul), scratch.data_ptr(), B, K, N, D,
                                 st if st is not None else stream()), "vj_l1_loss")
     return loss_accum
@@ -198,7 +215,7 @@ def l1_loss(z, h, idx, loss_accum, dz, loss_scale, grad_scale, grad_scale_mul=No
 def argsort_rank(ids, st=None):
     B, S = ids.shape
     rank = torch.empty(B, S, dtype=torch.int32, device=ids.device)
-    C.check(C.load().vj_argsort_rank(ids.data_ptr(), rank.data_ptr(), B, S, st if st is not None else stream()),
+    _counting_check(C.load().vj_argsort_rank(ids.data_ptr(), rank.data_ptr(), B, S, st if st is not None else stream()),
             "vj_argsort_rank")
     return rank
 
@@ -214,7 +231,7 @@ def pred_indices(masks_x, masks_y, st=None):
     tgt_pos = torch.empty(B * Kp, dtype=i64, device=dev)
     ctx_pos = torch.empty(B * Kc, dtype=i64, device=dev)
     seq_to_tgt = torch.empty(B * S, dtype=i64, device=dev)
-    C.check(C.load().vj_pred_indices(masks_x.data_ptr(), masks_y.data_ptr(), B, Kc, Kp, ids_sorted.data_ptr(),
+    _counting_check(C.load().vj_pred_indices(masks_x.data_ptr(), masks_y.data_ptr(), B, Kc, Kp, ids_sorted.data_ptr(),
                                      asm_idx.data_ptr(), tgt_pos.data_ptr(), ctx_pos.data_ptr(),
                                      seq_to_tgt.data_ptr(), st if st is not None else stream()), "vj_pred_indices")
     return ids_sorted, asm_idx, tgt_pos, ctx_pos, seq_to_tgt
@@ -223,12 +240,12 @@ def pred_indices(masks_x, masks_y, st=None):
 # ------------------------------------------------------------------------------ flat optimizer kernels
 def ema_update(tgt, src, tgt_bf16, m, st=None):
     n = tgt.numel()
-    C.check(C.load().vj_ema_update(tgt.data_ptr(), src.data_ptr(), _p(tgt_bf16), n, float(m), float(1.0 - m),
+    _counting_check(C.load().vj_ema_update(tgt.data_ptr(), src.data_ptr(), _p(tgt_bf16), n, float(m), float(1.0 - m),
                                    st if st is not None else stream()), "vj_ema_update")
 
 
 def grad_check(g, found_inf, st=None):
-    C.check(C.load().vj_grad_check(g.data_ptr(), g.numel(), found_inf.data_ptr(),
+    _counting_check(C.load().vj_grad_check(g.data_ptr(), g.numel(), found_inf.data_ptr(),
                                    st if st is not None else stream()), "vj_grad_check")
 
 
@@ -236,7 +253,7 @@ def adamw_step(p, g, m, v, p_bf16, tile_flags, lr, beta1, beta2, eps, wd, step, 
                st=None):
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
-    C.check(C.load().vj_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(p_bf16),
+    _counting_check(C.load().vj_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(p_bf16),
                                    tile_flags.data_ptr(), p.numel(), lr, beta1, beta2, eps, wd, bc1, bc2,
                                    _p(inv_scale), _p(found_inf), st if st is not None else stream()),
             "vj_adamw_step")
@@ -244,12 +261,12 @@ def adamw_step(p, g, m, v, p_bf16, tile_flags, lr, beta1, beta2, eps, wd, step, 
 
 def scaler_update(scale, inv_scale, growth_tracker, found_inf, world=1.0, growth=2.0, backoff=0.5, interval=2000,
                   st=None):
-    C.check(C.load().vj_scaler_update(scale.data_ptr(), inv_scale.data_ptr(), growth_tracker.data_ptr(),
+    _counting_check(C.load().vj_scaler_update(scale.data_ptr(), inv_scale.data_ptr(), growth_tracker.data_ptr(),
                                       found_inf.data_ptr(), growth, backoff, interval, float(world),
                                       st if st is not None else stream()), "vj_scaler_update")
 
 
 def cast_f32_bf16(src, dst, st=None):
-    C.check(C.load().vj_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(),
+    _counting_check(C.load().vj_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(),
                                       st if st is not None else stream()), "vj_cast_f32_bf16")
     return dst
