@@ -5,7 +5,9 @@
 //   warp 1   MMA issuer   (one elected lane issues tcgen05.mma / tcgen05.commit)
 //   warp 2   TMEM allocate / free
 //   warp 3   idle
-//   warps 4-7 epilogue: warp (4+q) owns TMEM lanes [32q, 32q+32) == output rows m0+32q..+31
+//   warps 4-11 epilogue, two warpgroups: warp (4+q) / (8+q) owns TMEM lanes [32q, 32q+32) == output rows
+//              m0+32q..+31; group 0 takes the even 32-column chunks of the tile, group 1 the odd ones.
+//              Residual / dGELU operands of the next chunk are prefetched while the current one is computed.
 //
 // Tile: 128 (M) x BN (N) x 64 (K) per stage.  Operands may be K-major or MN-major (transposed
 // storage), which covers forward (x W^T), dgrad (dy W) and wgrad (dy^T x) without any transpose pass.
@@ -17,7 +19,7 @@ namespace vj {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
 
 struct GemmEpi {
   void* out;
@@ -54,9 +56,61 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int&
   mb = first_m + (r - nb * gm);
 }
 
+// Side inputs of one 32-column chunk of one output row, fetched ahead of the accumulator:
+//   bf16 residual -> v[0..3];  fp32 residual -> v[0..7];  bf16 dGELU operand -> v[4..7]
+struct EpiSide {
+  uint4 v[8];
+};
+
+__device__ __forceinline__ void epilogue_prefetch(const GemmEpi& e, EpiSide& s, long long row, int col0, int N) {
+  const int flags = e.flags;
+  if (flags & VJ_EPI_RESIDUAL) {
+    if (flags & VJ_EPI_RES_F32) {
+      const float* rp = reinterpret_cast<const float*>(e.residual) + row * e.ldr + col0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (col0 + i * 4 < N) s.v[i] = *reinterpret_cast<const uint4*>(rp + i * 4);
+    } else {
+      const bf16* rp = reinterpret_cast<const bf16*>(e.residual) + row * e.ldr + col0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (col0 + i * 8 < N) s.v[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
+    }
+  }
+  if (flags & VJ_EPI_DGELU) {
+    const bf16* ap = reinterpret_cast<const bf16*>(e.aux_in) + row * e.ld_aux + col0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (col0 + i * 8 < N) s.v[4 + i] = *reinterpret_cast<const uint4*>(ap + i * 8);
+  }
+}
+
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): one rcp + one ex2 instead of erff's two branches.
+// Returns erf(z) and e = exp(-z*z) (reused for the Gaussian pdf in gelu').
+__device__ __forceinline__ float erf_as(float z, float& e) {
+  const float az = fabsf(z);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
+  e = exp2f(-az * az * 1.4426950408889634f);
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float r = 1.0f - p * t * e;
+  return copysignf(r, z);
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float e;
+  return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f, e));
+}
+__device__ __forceinline__ float dgelu_fast(float x) {
+  float e;
+  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f, e));
+  return fmaf(x * 0.39894228040143268f, e, cdf);
+}
+
 template <int BN>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t (&acc)[32], long long row, int col0,
-                                               int N) {
+__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t (&acc)[32], const EpiSide& s,
+                                               long long row, int col0, int N) {
   // 32 consecutive columns of one output row
   float v[32];
 #pragma unroll
@@ -89,40 +143,32 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t 
   }
   if (flags & VJ_EPI_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
   }
   if (flags & VJ_EPI_DGELU) {
-    const bf16* ap = reinterpret_cast<const bf16*>(e.aux_in) + row * e.ld_aux + col0;
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      if (col0 + i < N) {
-        const uint4 u = *reinterpret_cast<const uint4*>(ap + i);
-        v[i] *= dgelu_erf(bf16_lo(u.x)); v[i + 1] *= dgelu_erf(bf16_hi(u.x));
-        v[i + 2] *= dgelu_erf(bf16_lo(u.y)); v[i + 3] *= dgelu_erf(bf16_hi(u.y));
-        v[i + 4] *= dgelu_erf(bf16_lo(u.z)); v[i + 5] *= dgelu_erf(bf16_hi(u.z));
-        v[i + 6] *= dgelu_erf(bf16_lo(u.w)); v[i + 7] *= dgelu_erf(bf16_hi(u.w));
-      }
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = s.v[4 + i];
+      v[i * 8] *= dgelu_fast(bf16_lo(u.x)); v[i * 8 + 1] *= dgelu_fast(bf16_hi(u.x));
+      v[i * 8 + 2] *= dgelu_fast(bf16_lo(u.y)); v[i * 8 + 3] *= dgelu_fast(bf16_hi(u.y));
+      v[i * 8 + 4] *= dgelu_fast(bf16_lo(u.z)); v[i * 8 + 5] *= dgelu_fast(bf16_hi(u.z));
+      v[i * 8 + 6] *= dgelu_fast(bf16_lo(u.w)); v[i * 8 + 7] *= dgelu_fast(bf16_hi(u.w));
     }
   }
   if (flags & VJ_EPI_RESIDUAL) {
     if (flags & VJ_EPI_RES_F32) {
-      const float* rp = reinterpret_cast<const float*>(e.residual) + row * e.ldr + col0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        if (col0 + i < N) {
-          const float4 r = *reinterpret_cast<const float4*>(rp + i);
-          v[i] += r.x; v[i + 1] += r.y; v[i + 2] += r.z; v[i + 3] += r.w;
-        }
+      for (int i = 0; i < 8; ++i) {
+        const uint4 u = s.v[i];
+        v[i * 4] += __uint_as_float(u.x); v[i * 4 + 1] += __uint_as_float(u.y);
+        v[i * 4 + 2] += __uint_as_float(u.z); v[i * 4 + 3] += __uint_as_float(u.w);
       }
     } else {
-      const bf16* rp = reinterpret_cast<const bf16*>(e.residual) + row * e.ldr + col0;
 #pragma unroll
-      for (int i = 0; i < 32; i += 8) {
-        if (col0 + i < N) {
-          const uint4 u = *reinterpret_cast<const uint4*>(rp + i);
-          v[i] += bf16_lo(u.x); v[i + 1] += bf16_hi(u.x); v[i + 2] += bf16_lo(u.y); v[i + 3] += bf16_hi(u.y);
-          v[i + 4] += bf16_lo(u.z); v[i + 5] += bf16_hi(u.z); v[i + 6] += bf16_lo(u.w); v[i + 7] += bf16_hi(u.w);
-        }
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = s.v[i];
+        v[i * 8] += bf16_lo(u.x); v[i * 8 + 1] += bf16_hi(u.x); v[i * 8 + 2] += bf16_lo(u.y); v[i * 8 + 3] += bf16_hi(u.y);
+        v[i * 8 + 4] += bf16_lo(u.z); v[i * 8 + 5] += bf16_hi(u.z); v[i * 8 + 6] += bf16_lo(u.w); v[i * 8 + 7] += bf16_hi(u.w);
       }
     }
   }
@@ -179,7 +225,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 4);
+      mbar_init(&tempty[s], 8);
     }
     mbar_fence_init();
   }
@@ -258,37 +304,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue
     const int q = warp & 3;
+    const int eg = (warp - 4) >> 2;                 // warpgroup 0: even chunks, 1: odd chunks
+    constexpr int NCH = (BN + 31) / 32;
     int local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       int mb, nb;
       tile_coords(tile, num_m, num_n, mb, nb);
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
+      const long long row = (long long)mb * GEMM_BM + q * 32 + lane;
+      const bool row_ok = row < M;
+      const int n0 = nb * BN;
+      const int nlim = min(N, n0 + BN);
+      EpiSide side;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) side.v[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok && n0 + eg * 32 < nlim) epilogue_prefetch(epi, side, row, n0 + eg * 32, nlim);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
-      const long long row = (long long)mb * GEMM_BM + q * 32 + lane;
-      const int n0 = nb * BN;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
-      const int nlim = min(N, n0 + BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        if (n0 + c * 32 >= N) break;   // warp-uniform
+      for (int c = eg; c < NCH; c += 2) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= N) break;                       // warp-uniform
         uint32_t acc[32];
-        tmem_ld32(taddr + c * 32, acc);
-        tmem_ld_wait();
-        if (row < M) epilogue_chunk<BN>(epi, acc, row, n0 + c * 32, nlim);
-      }
-      if constexpr (BN % 32 != 0) {   // 16-column tail of the N tile (BN = 176)
-        constexpr int c = BN / 32;
-        if (n0 + c * 32 < N) {
+        if (BN % 32 != 0 && c == NCH - 1) {         // 16-column tail of the N tile (BN = 176)
           uint32_t lo[16];
-          uint32_t acc[32];
           tmem_ld16(taddr + c * 32, lo);
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; ++i) { acc[i] = lo[i]; acc[16 + i] = 0u; }
-          if (row < M) epilogue_chunk<BN>(epi, acc, row, n0 + c * 32, nlim);
+        } else {
+          tmem_ld32(taddr + c * 32, acc);
+          tmem_ld_wait();
         }
+        const EpiSide cur = side;
+        if (row_ok && col0 + 64 < nlim && c + 2 < NCH) epilogue_prefetch(epi, side, row, col0 + 64, nlim);
+        if (row_ok) epilogue_chunk<BN>(epi, acc, cur, row, col0, nlim);
       }
       tc_fence_before();
       __syncwarp();
@@ -380,6 +432,7 @@ extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
   if (g->flags & VJ_EPI_RESIDUAL) VJ_CHECK(g->residual != nullptr && g->ldr % 8 == 0, "vj_gemm: bad residual");
   if (g->flags & VJ_EPI_AUX_OUT) VJ_CHECK(g->aux_out != nullptr && g->ld_aux % 8 == 0, "vj_gemm: bad aux_out");
   if (g->flags & VJ_EPI_DGELU) VJ_CHECK(g->aux_in != nullptr && g->ld_aux % 8 == 0, "vj_gemm: bad aux_in");
+  VJ_CHECK(!((g->flags & VJ_EPI_DGELU) && (g->flags & VJ_EPI_RES_F32)), "vj_gemm: DGELU with an fp32 residual is not supported");
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
   VJ_CHECK(!(amn && !bmn), "vj_gemm: (A MN-major, B K-major) is not instantiated");
   const int bn = pick_bn(g->N, bmn, g->M);

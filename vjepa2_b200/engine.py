@@ -16,6 +16,7 @@ from __future__ import annotations
 import torch
 
 from . import ops
+from .workspace import TorchAlloc
 
 BF16, F32 = torch.bfloat16, torch.float32
 
@@ -56,79 +57,105 @@ class BlockG:
 # ------------------------------------------------------------------------------------------------
 # one transformer block
 # ------------------------------------------------------------------------------------------------
-def block_forward(h: BlockH, x, B, S, heads, hd, cos, sin, save, st):
-    """x: residual stream [B*S, D] (bf16 encoder / fp32 predictor).  Returns (x_out, saved)."""
+def block_forward(h: BlockH, x, x_out, B, S, heads, hd, cos, sin, save, st, ws):
+    """x: residual stream [B*S, D] (bf16 encoder / fp32 predictor); x_out: where the block output goes.
+    save=True keeps everything backward needs in ws.act; otherwise temporaries live in ws.tmp (caller
+    brackets the call with mark/release).  Returns saved tuple or None."""
     M, D = x.shape
-    dev = x.device
     Hm = h.hidden
+    A = ws.act if save else ws.tmp
     mean1 = rstd1 = mean2 = rstd2 = hpre = None
     if save:
-        stats = torch.empty(4, M, dtype=F32, device=dev)
+        stats = A((4, M), F32)
         mean1, rstd1, mean2, rstd2 = stats[0], stats[1], stats[2], stats[3]
-        hpre = torch.empty(M, Hm, dtype=BF16, device=dev)
-    ln1 = torch.empty(M, D, dtype=BF16, device=dev)
+        hpre = A((M, Hm), BF16)
+    ln1 = A((M, D), BF16)
     ops.layernorm_fwd(x, h.n1w, h.n1b, ln1, mean1, rstd1, 1e-6, st)
-    qkv = torch.empty(M, 3 * D, dtype=BF16, device=dev)
+    qkv = A((M, 3 * D), BF16)
     ops.gemm(ln1, h.qkv_w, qkv, M, 3 * D, D, bias=h.qkv_b, st=st)
     ops.rope_apply(qkv, D, heads, hd, cos, sin, False, st)
-    att = torch.empty(M, D, dtype=BF16, device=dev)
-    lse = torch.empty(B * heads * S, dtype=F32, device=dev)
+    att = A((M, D), BF16)
+    lse = A((B * heads * S,), F32)
     ops.attn_fwd(qkv, att, lse, B, S, heads, hd, st)
-    x1 = torch.empty_like(x)
+    x1 = A((M, D), x.dtype)
     ops.gemm(att, h.proj_w, x1, M, D, D, bias=h.proj_b, residual=x, round_bf16=True, st=st)
-    ln2 = torch.empty(M, D, dtype=BF16, device=dev)
+    ln2 = A((M, D), BF16)
     ops.layernorm_fwd(x1, h.n2w, h.n2b, ln2, mean2, rstd2, 1e-6, st)
-    act = torch.empty(M, Hm, dtype=BF16, device=dev)
+    act = A((M, Hm), BF16)
     ops.gemm(ln2, h.fc1_w, act, M, Hm, D, bias=h.fc1_b, gelu=True, round_bf16=True, aux_out=hpre, st=st)
-    x2 = torch.empty_like(x)
-    ops.gemm(act, h.fc2_w, x2, M, D, Hm, bias=h.fc2_b, residual=x1, round_bf16=True, st=st)
-    saved = (x, mean1, rstd1, ln1, qkv, att, lse, x1, mean2, rstd2, ln2, hpre, act) if save else None
-    return x2, saved
+    ops.gemm(act, h.fc2_w, x_out, M, D, Hm, bias=h.fc2_b, residual=x1, round_bf16=True, st=st)
+    return (x, mean1, rstd1, ln1, qkv, att, lse, x1, mean2, rstd2, ln2, hpre, act) if save else None
 
 
-def _as_bf16(t, st):
+def _as_bf16(t, st, ws):
     if t.dtype == BF16:
         return t
-    out = torch.empty(t.shape, dtype=BF16, device=t.device)
+    out = ws.tmp(tuple(t.shape), BF16)
     ops.cast_f32_bf16(t, out, st)
     return out
 
 
-def block_backward(h: BlockH, g: BlockG, saved, dx2, B, S, heads, hd, cos, sin, st):
-    """dx2: gradient w.r.t. the block output [M, D] (dtype of the residual stream).  Parameter gradients
-    are ACCUMULATED into g (fp32).  Returns the gradient w.r.t. the block input."""
+def block_backward(h: BlockH, g: BlockG, saved, dx2, dx0, B, S, heads, hd, cos, sin, st, ws):
+    """dx2: gradient w.r.t. the block output [M, D] (dtype of the residual stream); dx0: output buffer for
+    the gradient w.r.t. the block input (may not alias dx2).  Parameter gradients are ACCUMULATED into g
+    (fp32).  Temporaries come from ws.tmp and are released before returning."""
     x, mean1, rstd1, ln1, qkv, att, lse, x1, mean2, rstd2, ln2, hpre, act = saved
     M, D = x.shape
-    dev = x.device
     Hm = h.hidden
-    d2 = _as_bf16(dx2, st)
+    T = ws.tmp
+    mk = ws.mark()
+    d2 = _as_bf16(dx2, st, ws)
     # ---- MLP: x2 = x1 + fc2(gelu(fc1(LN2(x1))))
-    dh = torch.empty(M, Hm, dtype=BF16, device=dev)
+    dh = T((M, Hm), BF16)
     ops.gemm(d2, h.fc2_w, dh, M, Hm, D, b_mn=True, dgelu_aux=hpre, st=st)                 # dgrad fc2 * gelu'
     ops.gemm(d2, act, g.fc2_w, D, Hm, M, a_mn=True, b_mn=True, residual=g.fc2_w, st=st)   # wgrad fc2 (+=)
-    ops.colsum(d2, g.fc2_b, True, st)
-    dln2 = torch.empty(M, D, dtype=BF16, device=dev)
+    ops.colsum(d2, g.fc2_b, True, st, T)
+    dln2 = T((M, D), BF16)
     ops.gemm(dh, h.fc1_w, dln2, M, D, Hm, b_mn=True, st=st)                               # dgrad fc1
     ops.gemm(dh, ln2, g.fc1_w, Hm, D, M, a_mn=True, b_mn=True, residual=g.fc1_w, st=st)   # wgrad fc1
-    ops.colsum(dh, g.fc1_b, True, st)
-    dx1 = torch.empty_like(dx2)
-    ops.layernorm_bwd(dln2, x1, h.n2w, mean2, rstd2, dx1, dres=dx2, dgamma=g.n2w, dbeta=g.n2b, st=st)
+    ops.colsum(dh, g.fc1_b, True, st, T)
+    dx1 = T((M, D), dx2.dtype)
+    ops.layernorm_bwd(dln2, x1, h.n2w, mean2, rstd2, dx1, dres=dx2, dgamma=g.n2w, dbeta=g.n2b, st=st, alloc=T)
     # ---- attention: x1 = x + proj(attn(rope(qkv(LN1(x)))))
-    d1 = _as_bf16(dx1, st)
-    datt = torch.empty(M, D, dtype=BF16, device=dev)
+    d1 = _as_bf16(dx1, st, ws)
+    datt = T((M, D), BF16)
     ops.gemm(d1, h.proj_w, datt, M, D, D, b_mn=True, st=st)
     ops.gemm(d1, att, g.proj_w, D, D, M, a_mn=True, b_mn=True, residual=g.proj_w, st=st)
-    ops.colsum(d1, g.proj_b, True, st)
-    dqkv = torch.empty(M, 3 * D, dtype=BF16, device=dev)
-    ops.attn_bwd(qkv, att, datt, lse, dqkv, B, S, heads, hd, st)
+    ops.colsum(d1, g.proj_b, True, st, T)
+    dqkv = T((M, 3 * D), BF16)
+    ops.attn_bwd(qkv, att, datt, lse, dqkv, B, S, heads, hd, st, T)
     ops.rope_apply(dqkv, D, heads, hd, cos, sin, True, st)
-    dln1 = torch.empty(M, D, dtype=BF16, device=dev)
+    dln1 = T((M, D), BF16)
     ops.gemm(dqkv, h.qkv_w, dln1, M, D, 3 * D, b_mn=True, st=st)
     ops.gemm(dqkv, ln1, g.qkv_w, 3 * D, D, M, a_mn=True, b_mn=True, residual=g.qkv_w, st=st)
-    ops.colsum(dqkv, g.qkv_b, True, st)
-    dx0 = torch.empty_like(dx2)
-    ops.layernorm_bwd(dln1, x, h.n1w, mean1, rstd1, dx0, dres=dx1, dgamma=g.n1w, dbeta=g.n1b, st=st)
+    ops.colsum(dqkv, g.qkv_b, True, st, T)
+    ops.layernorm_bwd(dln1, x, h.n1w, mean1, rstd1, dx0, dres=dx1, dgamma=g.n1w, dbeta=g.n1b, st=st, alloc=T)
+    ws.release(mk)
     return dx0
+
+
+def _run_blocks_forward(blocks, x, B, S, heads, hd, cos, sin, save, st, ws, on_block=None):
+    """Runs the block stack.  save=True: every block output is a fresh ws.act tensor (it is the next block's
+    saved input).  save=False: two ping-pong residual buffers, per-block temporaries released immediately."""
+    saved_all = []
+    if save:
+        for i, h in enumerate(blocks):
+            x_out = ws.act(tuple(x.shape), x.dtype)
+            saved_all.append(block_forward(h, x, x_out, B, S, heads, hd, cos, sin, True, st, ws))
+            x = x_out
+            if on_block is not None:
+                on_block(i, x)
+        return x, saved_all
+    pp = (ws.tmp(tuple(x.shape), x.dtype), ws.tmp(tuple(x.shape), x.dtype))
+    for i, h in enumerate(blocks):
+        x_out = pp[i & 1]
+        mk = ws.mark()
+        block_forward(h, x, x_out, B, S, heads, hd, cos, sin, False, st, ws)
+        ws.release(mk)
+        x = x_out
+        if on_block is not None:
+            on_block(i, x)
+    return x, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -172,65 +199,77 @@ class EncoderRT:
         return g
 
 
-def encoder_forward(rt: EncoderRT, clips, ids, grid_hw, save, out_layers=None):
+def encoder_forward(rt: EncoderRT, clips, ids, grid_hw, save, ws=None, out_layers=None):
     """clips fp32 [B,C,T,H,W]; ids None or int64 [B*reps, K] kept-token ids.
-    Returns (out fp32 [B*reps, S, D], saved) -- or the list of normed intermediate outputs if out_layers."""
+    Returns (out fp32 [B*reps, S, D], saved) -- or the list of normed intermediate outputs if out_layers.
+    With an Arena `ws`, the output lives in ws.act (save) / ws.tmp and is only valid until the arena is reset."""
     st = ops.stream()
     B = clips.shape[0]
     dev = clips.device
+    if ws is None:
+        ws = TorchAlloc(dev)
     Hp, Wp = grid_hw
     D, heads, hd = rt.D, rt.heads, rt.hd
-    cols = ops.im2col_tubelets(clips, ids, rt.tubelet, rt.patch, st)
+    A = ws.act if save else ws.tmp
+    cols = ops.im2col_tubelets(clips, ids, rt.tubelet, rt.patch, st, A)
     M = cols.shape[0]
     if ids is not None:
         Bp, S = ids.shape
     else:
         Bp, S = B, M // B
-    x = torch.empty(M, D, dtype=BF16, device=dev)
+    x = A((M, D), BF16)
     ops.gemm(cols, rt.pe_w, x, M, D, rt.pe_k, bias=rt.pe_b, st=st)
-    cos, sin = ops.rope_table(ids, M, S, Hp, Wp, hd, dev, st)
-    blocks_saved = []
+    cos, sin = ops.rope_table(ids, M, S, Hp, Wp, hd, dev, st, A)
     outs = []
-    for i, h in enumerate(rt.blocks):
-        x, sv = block_forward(h, x, Bp, S, heads, hd, cos, sin, save, st)
-        if save:
-            blocks_saved.append(sv)
+
+    def collect(i, xi):
         if out_layers is not None and i in out_layers:
             o = torch.empty(M, D, dtype=F32, device=dev)
-            ops.layernorm_fwd(x, rt.norm_w, rt.norm_b, o, None, None, 1e-6, st)
+            ops.layernorm_fwd(xi, rt.norm_w, rt.norm_b, o, None, None, 1e-6, st)
             outs.append(o.view(Bp, S, D))
+
+    x, blocks_saved = _run_blocks_forward(rt.blocks, x, Bp, S, heads, hd, cos, sin, save, st, ws,
+                                          collect if out_layers is not None else None)
     if out_layers is not None:
         return outs, None
-    out = torch.empty(M, D, dtype=F32, device=dev)
+    out = A((M, D), F32)
     mean = rstd = None
     if save:
-        mean = torch.empty(M, dtype=F32, device=dev)
-        rstd = torch.empty(M, dtype=F32, device=dev)
+        mean = A((M,), F32)
+        rstd = A((M,), F32)
     ops.layernorm_fwd(x, rt.norm_w, rt.norm_b, out, mean, rstd, 1e-6, st)
     saved = (cols, cos, sin, blocks_saved, x, mean, rstd, Bp, S) if save else None
     return out.view(Bp, S, D), saved
 
 
-def encoder_backward(rt: EncoderRT, saved, dout, gbuf, on_block_done=None):
+def encoder_backward(rt: EncoderRT, saved, dout, gbuf, ws=None, on_block_done=None):
     """dout: gradient w.r.t. the encoder output [B', S, D] (bf16 or fp32).  Accumulates parameter
     gradients into gbuf (flat fp32).  The input clip needs no gradient."""
     st = ops.stream()
     cols, cos, sin, blocks_saved, x_last, mean, rstd, Bp, S = saved
     D, heads, hd = rt.D, rt.heads, rt.hd
     M = Bp * S
+    if ws is None:
+        ws = TorchAlloc(dout.device)
     g = rt.grads(gbuf)
     dy = dout.reshape(M, D)
-    dx = torch.empty(M, D, dtype=BF16, device=dy.device)
-    ops.layernorm_bwd(dy, x_last, rt.norm_w, mean, rstd, dx, dres=None, dgamma=g["norm_w"], dbeta=g["norm_b"], st=st)
+    outer = ws.mark()
+    pp = (ws.tmp((M, D), BF16), ws.tmp((M, D), BF16))
+    dx = pp[0]
+    ops.layernorm_bwd(dy, x_last, rt.norm_w, mean, rstd, dx, dres=None, dgamma=g["norm_w"], dbeta=g["norm_b"], st=st,
+                      alloc=ws.tmp)
     if on_block_done is not None:
         on_block_done(len(rt.blocks))           # final norm params are done
+    k = 0
     for i in range(len(rt.blocks) - 1, -1, -1):
-        dx = block_backward(rt.blocks[i], g["blocks"][i], blocks_saved[i], dx, Bp, S, heads, hd, cos, sin, st)
-        blocks_saved[i] = None                  # release activations as we go
+        k ^= 1
+        dx = block_backward(rt.blocks[i], g["blocks"][i], blocks_saved[i], dx, pp[k], Bp, S, heads, hd, cos, sin, st, ws)
+        blocks_saved[i] = None                  # release activations as we go (torch allocator path)
         if on_block_done is not None:
             on_block_done(i)
     ops.gemm(dx, cols, g["pe_w"], D, rt.pe_k, M, a_mn=True, b_mn=True, residual=g["pe_w"], st=st)
-    ops.colsum(dx, g["pe_b"], True, st)
+    ops.colsum(dx, g["pe_b"], True, st, ws.tmp)
+    ws.release(outer)
     if on_block_done is not None:
         on_block_done(-1)                       # patch-embed params are done
 
@@ -274,38 +313,42 @@ class PredictorRT:
         return g
 
 
-def predictor_forward(rt: PredictorRT, z, masks_x, masks_y, mask_index, save):
+def predictor_forward(rt: PredictorRT, z, masks_x, masks_y, mask_index, save, ws=None):
     """z: context-encoder output [B, Kc, D_in] (fp32 or bf16); masks_x [B,Kc], masks_y [B,Kp] int64.
     Returns (pred bf16 [B, Kp, D_in], saved)."""
     st = ops.stream()
     dev = z.device
+    if ws is None:
+        ws = TorchAlloc(dev)
     B, Kc, Din = z.shape
     Kp = masks_y.shape[1]
     S = Kc + Kp
     D, heads, hd = rt.D, rt.heads, rt.hd
-    z16 = _as_bf16(z.reshape(B * Kc, Din), st)
-    emb = torch.empty(B * Kc, D, dtype=BF16, device=dev)
+    A = ws.act if save else ws.tmp
+    z2 = z.reshape(B * Kc, Din)
+    if z2.dtype == BF16:
+        z16 = z2
+    else:
+        z16 = A((B * Kc, Din), BF16)
+        ops.cast_f32_bf16(z2, z16, st)
+    emb = A((B * Kc, D), BF16)
     ops.gemm(z16, rt.embed_w, emb, B * Kc, D, Din, bias=rt.embed_b, st=st)
-    ids_sorted, asm_idx, tgt_pos, ctx_pos, seq_to_tgt = ops.pred_indices(masks_x, masks_y, st)
+    ids_sorted, asm_idx, tgt_pos, ctx_pos, seq_to_tgt = ops.pred_indices(masks_x, masks_y, st, A)
     mi = mask_index % len(rt.mask_tokens)
-    x = torch.empty(B * S, D, dtype=F32, device=dev)
+    x = A((B * S, D), F32)
     ops.gather_rows(emb, x, asm_idx, fill=rt.mask_tokens[mi], st=st)
-    cos, sin = ops.rope_table(ids_sorted, B * S, S, rt.grid, rt.grid, hd, dev, st)
-    blocks_saved = []
-    for h in rt.blocks:
-        x, sv = block_forward(h, x, B, S, heads, hd, cos, sin, save, st)
-        if save:
-            blocks_saved.append(sv)
+    cos, sin = ops.rope_table(ids_sorted, B * S, S, rt.grid, rt.grid, hd, dev, st, A)
+    x, blocks_saved = _run_blocks_forward(rt.blocks, x, B, S, heads, hd, cos, sin, save, st, ws)
     # LayerNorm is row-wise, so norm(x)[targets] == norm(x[targets]) (predictor.py:233,240-242)
-    xg = torch.empty(B * Kp, D, dtype=F32, device=dev)
+    xg = A((B * Kp, D), F32)
     ops.gather_rows(x, xg, tgt_pos, st=st)
-    y16 = torch.empty(B * Kp, D, dtype=BF16, device=dev)
+    y16 = A((B * Kp, D), BF16)
     mean = rstd = None
     if save:
-        mean = torch.empty(B * Kp, dtype=F32, device=dev)
-        rstd = torch.empty(B * Kp, dtype=F32, device=dev)
+        mean = A((B * Kp,), F32)
+        rstd = A((B * Kp,), F32)
     ops.layernorm_fwd(xg, rt.norm_w, rt.norm_b, y16, mean, rstd, 1e-6, st)
-    out = torch.empty(B * Kp, Din, dtype=BF16, device=dev)
+    out = A((B * Kp, Din), BF16)
     ops.gemm(y16, rt.proj_w, out, B * Kp, Din, D, bias=rt.proj_b, st=st)
     saved = None
     if save:
@@ -313,37 +356,47 @@ def predictor_forward(rt: PredictorRT, z, masks_x, masks_y, mask_index, save):
     return out.view(B, Kp, Din), saved
 
 
-def predictor_backward(rt: PredictorRT, saved, dout, gbuf):
-    """dout bf16 [B, Kp, D_in].  Accumulates parameter grads into gbuf; returns d(z) bf16 [B, Kc, D_in]."""
+def predictor_backward(rt: PredictorRT, saved, dout, gbuf, ws=None, dz_out=None):
+    """dout bf16 [B, Kp, D_in].  Accumulates parameter grads into gbuf; returns d(z) bf16 [B, Kc, D_in]
+    (written to dz_out if given, else allocated from ws.act so it outlives this call's temporaries)."""
     st = ops.stream()
     z16, cos, sin, blocks_saved, xg, mean, rstd, y16, tgt_pos, ctx_pos, seq_to_tgt, mi, B, Kc, Kp = saved
     dev = z16.device
+    if ws is None:
+        ws = TorchAlloc(dev)
     S = Kc + Kp
     D, heads, hd, Din = rt.D, rt.heads, rt.hd, rt.D_in
     g = rt.grads(gbuf)
-    do = _as_bf16(dout.reshape(B * Kp, Din), st)
+    dz = dz_out if dz_out is not None else ws.act((B * Kc, Din), BF16)
+    T = ws.tmp
+    outer = ws.mark()
+    do = _as_bf16(dout.reshape(B * Kp, Din), st, ws)
     # predictor_proj
-    dy16 = torch.empty(B * Kp, D, dtype=BF16, device=dev)
+    dy16 = T((B * Kp, D), BF16)
     ops.gemm(do, rt.proj_w, dy16, B * Kp, D, Din, b_mn=True, st=st)
     ops.gemm(do, y16, g["proj_w"], Din, D, B * Kp, a_mn=True, b_mn=True, residual=g["proj_w"], st=st)
-    ops.colsum(do, g["proj_b"], True, st)
+    ops.colsum(do, g["proj_b"], True, st, T)
     # predictor_norm on the target rows, then scatter back into the sorted sequence
-    dxg = torch.empty(B * Kp, D, dtype=F32, device=dev)
-    ops.layernorm_bwd(dy16, xg, rt.norm_w, mean, rstd, dxg, dres=None, dgamma=g["norm_w"], dbeta=g["norm_b"], st=st)
-    dx = torch.empty(B * S, D, dtype=F32, device=dev)
+    dxg = T((B * Kp, D), F32)
+    ops.layernorm_bwd(dy16, xg, rt.norm_w, mean, rstd, dxg, dres=None, dgamma=g["norm_w"], dbeta=g["norm_b"], st=st,
+                      alloc=T)
+    pp = (T((B * S, D), F32), T((B * S, D), F32))
+    dx = pp[0]
     ops.gather_rows(dxg, dx, seq_to_tgt, fill=None, st=st)          # context rows get zeros
+    k = 0
     for i in range(len(rt.blocks) - 1, -1, -1):
-        dx = block_backward(rt.blocks[i], g["blocks"][i], blocks_saved[i], dx, B, S, heads, hd, cos, sin, st)
+        k ^= 1
+        dx = block_backward(rt.blocks[i], g["blocks"][i], blocks_saved[i], dx, pp[k], B, S, heads, hd, cos, sin, st, ws)
         blocks_saved[i] = None
     # mask token: sum of the gradients of every target slot (predictor.py:195-197)
-    dtg = torch.empty(B * Kp, D, dtype=F32, device=dev)
+    dtg = T((B * Kp, D), F32)
     ops.gather_rows(dx, dtg, tgt_pos, st=st)
-    ops.colsum(dtg, g["mask_tokens"][mi], True, st)
+    ops.colsum(dtg, g["mask_tokens"][mi], True, st, T)
     # predictor_embed
-    demb = torch.empty(B * Kc, D, dtype=BF16, device=dev)
+    demb = T((B * Kc, D), BF16)
     ops.gather_rows(dx, demb, ctx_pos, st=st)
-    dz = torch.empty(B * Kc, Din, dtype=BF16, device=dev)
     ops.gemm(demb, rt.embed_w, dz, B * Kc, Din, D, b_mn=True, st=st)
     ops.gemm(demb, z16, g["embed_w"], D, Din, B * Kc, a_mn=True, b_mn=True, residual=g["embed_w"], st=st)
-    ops.colsum(demb, g["embed_b"], True, st)
+    ops.colsum(demb, g["embed_b"], True, st, T)
+    ws.release(outer)
     return dz.view(B, Kc, Din)

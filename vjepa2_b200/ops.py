@@ -100,12 +100,17 @@ def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-6, st=None):
     return y
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres=None, dgamma=None, dbeta=None, st=None):
+def _scratch(nbytes, device, alloc):
+    if alloc is not None:
+        return alloc((nbytes,), torch.uint8)
+    return torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres=None, dgamma=None, dbeta=None, st=None, alloc=None):
     rows, D = x.shape
     scratch = None
     if dgamma is not None or dbeta is not None:
-        nbytes = C.load().vj_layernorm_bwd_scratch(rows, D)
-        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        scratch = _scratch(C.load().vj_layernorm_bwd_scratch(rows, D), x.device, alloc)
     if dres is not None and dres.dtype != dx.dtype:
         raise TypeError("layernorm_bwd: dres must have dx's dtype")
     _counting_check(C.load().vj_layernorm_bwd(dy.data_ptr(), _dt(dy), x.data_ptr(), _dt(x), _p(gamma), mean.data_ptr(),
@@ -120,11 +125,14 @@ def rope_seg(head_dim: int) -> int:
     return 2 * ((head_dim // 3) // 2)
 
 
-def rope_table(ids, n, period, Hp, Wp, head_dim, device, st=None):
+def rope_table(ids, n, period, Hp, Wp, head_dim, device, st=None, alloc=None):
     """ids: int64 [n] flattened token ids, or None for id(row) = row % period -> (cos, sin) fp32 [n, 3*seg/2]."""
     half = rope_seg(head_dim) // 2
-    cos = torch.empty(n, 3 * half, dtype=F32, device=device)
-    sin = torch.empty_like(cos)
+    if alloc is not None:
+        cos, sin = alloc((n, 3 * half), F32), alloc((n, 3 * half), F32)
+    else:
+        cos = torch.empty(n, 3 * half, dtype=F32, device=device)
+        sin = torch.empty_like(cos)
     _counting_check(C.load().vj_rope_table(_p(ids), n, period, Hp, Wp, head_dim, cos.data_ptr(), sin.data_ptr(),
                                    st if st is not None else stream()), "vj_rope_table")
     return cos, sin
@@ -144,9 +152,8 @@ def attn_fwd(qkv, out, lse, B, S, H, head_dim, st=None):
     return out
 
 
-def attn_bwd(qkv, out, dout, lse, dqkv, B, S, H, head_dim, st=None):
-    nbytes = C.load().vj_attn_bwd_scratch(B, S, H, head_dim)
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device=qkv.device)
+def attn_bwd(qkv, out, dout, lse, dqkv, B, S, H, head_dim, st=None, alloc=None):
+    scratch = _scratch(C.load().vj_attn_bwd_scratch(B, S, H, head_dim), qkv.device, alloc)
     _counting_check(C.load().vj_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
                                  scratch.data_ptr(), B, S, H, head_dim, st if st is not None else stream()),
             "vj_attn_bwd")
@@ -177,35 +184,34 @@ def mask_to_rows(masks, N, st=None):
     return out
 
 
-def im2col_tubelets(clips, ids, tubelet, patch, st=None):
+def im2col_tubelets(clips, ids, tubelet, patch, st=None, alloc=None):
     """clips fp32 [B,C,T,H,W]; ids int64 [B,K] or None -> bf16 [B*K, C*tubelet*patch*patch]."""
     B, Cc, T, H, W = clips.shape
     if ids is not None:
         reps, K = ids.shape[0] // B, ids.shape[1]
     else:
         reps, K = 1, (T // tubelet) * (H // patch) * (W // patch)
-    cols = torch.empty(B * reps * K, Cc * tubelet * patch * patch, dtype=BF16, device=clips.device)
+    shape = (B * reps * K, Cc * tubelet * patch * patch)
+    cols = alloc(shape, BF16) if alloc is not None else torch.empty(shape, dtype=BF16, device=clips.device)
     _counting_check(C.load().vj_im2col_tubelets(clips.data_ptr(), _p(ids), cols.data_ptr(), B, Cc, T, H, W, tubelet, patch, K,
                                         reps, st if st is not None else stream()), "vj_im2col_tubelets")
     return cols
 
 
 # ------------------------------------------------------------------------------ reductions / loss
-def colsum(x, out, accumulate=True, st=None):
+def colsum(x, out, accumulate=True, st=None, alloc=None):
     rows, D = x.shape
-    nbytes = C.load().vj_colsum_scratch(rows, D)
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    scratch = _scratch(C.load().vj_colsum_scratch(rows, D), x.device, alloc)
     _counting_check(C.load().vj_colsum(x.data_ptr(), _dt(x), out.data_ptr(), int(accumulate), scratch.data_ptr(), rows, D,
                                st if st is not None else stream()), "vj_colsum")
     return out
 
 
-def l1_loss(z, h, idx, loss_accum, dz, loss_scale, grad_scale, grad_scale_mul=None, st=None):
+def l1_loss(z, h, idx, loss_accum, dz, loss_scale, grad_scale, grad_scale_mul=None, st=None, alloc=None):
     """z bf16 [B,K,D]; h fp32 [B,N,D]; idx int64 [B,K].  loss_accum (fp32 [1]) += loss_scale*sum|z-h[idx]|."""
     B, K, D = z.shape
     N = h.shape[1]
-    nbytes = C.load().vj_l1_scratch(B, K, D)
-    scratch = torch.empty(nbytes, dtype=torch.uint8, device=z.device)
+    scratch = _scratch(C.load().vj_l1_scratch(B, K, D), z.device, alloc)
     _counting_check(C.load().vj_l1_loss(z.data_ptr(), h.data_ptr(), idx.data_ptr(), loss_accum.data_ptr(), _p(dz),
                                 loss_scale, grad_scale, _p(grad_scale_mul), scratch.data_ptr(), B, K, N, D,
                                 st if st is not None else stream()), "vj_l1_loss")
@@ -220,17 +226,19 @@ def argsort_rank(ids, st=None):
     return rank
 
 
-def pred_indices(masks_x, masks_y, st=None):
+def pred_indices(masks_x, masks_y, st=None, alloc=None):
     B, Kc = masks_x.shape
     Kp = masks_y.shape[1]
     S = Kc + Kp
     dev = masks_x.device
     i64 = torch.int64
-    ids_sorted = torch.empty(B, S, dtype=i64, device=dev)
-    asm_idx = torch.empty(B * S, dtype=i64, device=dev)
-    tgt_pos = torch.empty(B * Kp, dtype=i64, device=dev)
-    ctx_pos = torch.empty(B * Kc, dtype=i64, device=dev)
-    seq_to_tgt = torch.empty(B * S, dtype=i64, device=dev)
+    if alloc is None:
+        alloc = lambda shape, dtype: torch.empty(shape, dtype=dtype, device=dev)  # noqa: E731
+    ids_sorted = alloc((B, S), i64)
+    asm_idx = alloc((B * S,), i64)
+    tgt_pos = alloc((B * Kp,), i64)
+    ctx_pos = alloc((B * Kc,), i64)
+    seq_to_tgt = alloc((B * S,), i64)
     _counting_check(C.load().vj_pred_indices(masks_x.data_ptr(), masks_y.data_ptr(), B, Kc, Kp, ids_sorted.data_ptr(),
                                      asm_idx.data_ptr(), tgt_pos.data_ptr(), ctx_pos.data_ptr(),
                                      seq_to_tgt.data_ptr(), st if st is not None else stream()), "vj_pred_indices")

@@ -23,6 +23,7 @@ import torch.distributed as dist
 from . import engine, ops
 from .predictor import vit_predictor
 from .schedulers import CosineWDSchedule, WarmupCosineSchedule, momentum_schedule
+from .workspace import Arena
 from .wrappers import MultiSeqWrapper, PredictorMultiSeqWrapper
 from . import vision_transformer as video_vit
 
@@ -123,6 +124,7 @@ class JepaTrainStep:
         self.found_inf = torch.zeros(1, dtype=f32, device=dev)
         self.growth_tracker = torch.zeros(1, dtype=torch.int32, device=dev)
         self._frozen_key = None
+        self.ws = Arena(dev)                                        # activations / temporaries (no allocator in-step)
         # flat ranges of the per-block buckets (reverse order of completion in backward)
         fs = self.enc_rt.fs
         self._enc_ranges = {i: fs.range_of(h.params) for i, h in enumerate(self.enc_rt.blocks)}
@@ -154,6 +156,8 @@ class JepaTrainStep:
         efs.g32.zero_()                                           # optimizer.zero_grad() (train.py:454)
         pfs.g32.zero_()
         self.loss_accum.zero_()
+        ws = self.ws
+        ws.reset()
         n_pairs = sum(len(m) for m in masks_enc)
         p = enc.patch_size
 
@@ -163,7 +167,7 @@ class JepaTrainStep:
             _, _, T, H, W = c.shape
             grid = (H // p, W // p) if enc.handle_nonsquare_inputs else (enc.grid_size, enc.grid_size)
             # ---- target (train.py:414-418): no-grad encoder + non-affine LayerNorm, eps 1e-5
-            h, _ = engine.encoder_forward(tgt_rt, c, None, grid, save=False)
+            h, _ = engine.encoder_forward(tgt_rt, c, None, grid, save=False, ws=ws)   # stays on the tmp stack
             Bq, N, D = h.shape
             h2 = h.view(Bq * N, D)
             ops.layernorm_fwd(h2, None, None, h2, None, None, 1e-5, st)     # in place (row-local)
@@ -173,22 +177,25 @@ class JepaTrainStep:
                 me = me.contiguous()
                 mp = mp.contiguous()
                 # ---- context + predictor forward (train.py:420-423)
-                z, sv_e = engine.encoder_forward(enc_rt, c, me, grid, save=True)
-                pred, sv_p = engine.predictor_forward(pred_rt, z, me, mp, i, save=True)
+                z, sv_e = engine.encoder_forward(enc_rt, c, me, grid, save=True, ws=ws)
+                pred, sv_p = engine.predictor_forward(pred_rt, z, me, mp, i, save=True, ws=ws)
                 # ---- loss (train.py:425-435) and its gradient, GradScaler-scaled (train.py:445)
-                dz = torch.empty_like(pred)
+                dz = ws.act(tuple(pred.shape), pred.dtype)
                 inv = 1.0 / (n_pairs * pred.numel())
-                ops.l1_loss(pred, h, mp, self.loss_accum, dz, inv, inv, self.scale, st)
+                mk = ws.mark()
+                ops.l1_loss(pred, h, mp, self.loss_accum, dz, inv, inv, self.scale, st, ws.tmp)
+                ws.release(mk)
                 # ---- backward
-                dzenc = engine.predictor_backward(pred_rt, sv_p, dz, pfs.g32)
+                dzenc = engine.predictor_backward(pred_rt, sv_p, dz, pfs.g32, ws=ws)
                 del sv_p
                 if last and self.world > 1:
                     self.bucketer.submit(pfs.g32, 0, pfs.total)
                     hook = lambda b, efs=efs: self.bucketer.submit(efs.g32, *self._enc_ranges[b])  # noqa: E731
                 else:
                     hook = None
-                engine.encoder_backward(enc_rt, sv_e, dzenc, efs.g32, on_block_done=hook)
-                del sv_e
+                engine.encoder_backward(enc_rt, sv_e, dzenc, efs.g32, ws=ws, on_block_done=hook)
+                del sv_e, z, pred, dz, dzenc
+                ws._act.reset()                                   # this pair's activations are dead
         self.bucketer.wait()
 
         # ---- unscale + inf check + AdamW (train.py:446-451; app/vjepa/utils.py:239), flat kernels
