@@ -51,7 +51,9 @@ enum {
   VJ_EPI_OUT_F32 = 16,   /* out is fp32 (else bf16) */
   VJ_EPI_RES_F32 = 32,   /* residual is fp32 (else bf16) */
   VJ_EPI_ROUND_BF16 = 64,/* round v to bf16 before gelu/residual (mirrors autocast's bf16 Linear output) */
-  VJ_EPI_AUX_OUT = 128   /* also write the pre-activation v as bf16 to aux_out */
+  VJ_EPI_AUX_OUT = 128,  /* also write the pre-activation v as bf16 to aux_out */
+  VJ_EPI_ROPE = 256      /* qkv projection: apply the 3-axis RoPE map to columns < 2*rope_D (q and k thirds)
+                            after bias, using rope_table[m] (vj_rope_table layout); v passes through */
 };
 
 typedef struct {
@@ -68,6 +70,9 @@ typedef struct {
   void* aux_out;         /* bf16, ld = ld_aux */
   const void* aux_in;    /* bf16, ld = ld_aux */
   int64_t ld_aux;
+  const void* rope_table; /* fp16 [M][2][rope_hd] (VJ_EPI_ROPE) */
+  int32_t rope_hd;        /* head dim (32 or 64) */
+  int32_t rope_D;         /* model width: N == 3*rope_D */
 } vj_gemm_args;
 
 int vj_gemm(const vj_gemm_args* a, void* stream);
@@ -87,16 +92,18 @@ int vj_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, c
 
 /* ------------------------------------------------------------------ 3-axis RoPE
  * rotate_queries_or_keys + separate_positions (modules.py:26-50, 311-365).
- * vj_rope_table: token ids (int64, as produced by MaskCollator) -> cos/sin tables
- *   [n][3*(seg/2)] fp32 with seg = 2*((head_dim/3)/2); axis order frame, height, width.
- *   ids == NULL means the unmasked sequence: id(row) = row % period (torch.arange, modules.py:337-341).
- * vj_rope_apply: in place on the q and k thirds of qkv [rows][3*D] (bf16); transpose!=0 applies the
- *   adjoint map (backward).  The per-pair map is [[cos a, -sin a],[sin b, cos b]] with the TILED
- *   angle layout of the reference (not a rotation). */
-int vj_rope_table(const int64_t* ids, int64_t n, int64_t period, int Hp, int Wp, int head_dim, float* cos_t,
-                  float* sin_t, void* stream);
-int vj_rope_apply(void* qkv, int64_t rows, int64_t D, int heads, int head_dim, const float* cos_t,
-                  const float* sin_t, int transpose, void* stream);
+ * vj_rope_table: token ids (int64, as produced by MaskCollator; NULL = unmasked sequence, id(row) =
+ *   row % period, the torch.arange of modules.py:337-341) -> fp16 table [n][2][head_dim]: per ELEMENT d of the
+ *   head cos(theta) then sin(theta) with theta = pos_axis(d) * 10000^(-j/(seg/2)), seg = 2*((head_dim/3)/2),
+ *   axis(d) = d/seg (frame, height, width), j = (d mod seg) mod (seg/2) -- the TILED angle layout of the
+ *   reference; dims >= 3*seg pass through (cos 1, sin 0).
+ * vj_rope_apply: in place on the q and k thirds of qkv [rows][3*D] (bf16); transpose != 0 applies the adjoint
+ *   (backward).  The per-pair map [[c(2k), -s(2k)],[s(2k+1), c(2k+1)]] is NOT a rotation (modules.py:40-50).
+ * The same table feeds the fused paths: VJ_EPI_ROPE in vj_gemm (forward) and vj_attn_bwd (adjoint). */
+int vj_rope_table(const int64_t* ids, int64_t n, int64_t period, int Hp, int Wp, int head_dim, void* table,
+                  void* stream);
+int vj_rope_apply(void* qkv, int64_t rows, int64_t D, int heads, int head_dim, const void* table, int transpose,
+                  void* stream);
 
 /* ------------------------------------------------------------------ attention (tcgen05 flash fwd/bwd)
  * F.scaled_dot_product_attention, non-causal, no mask, dropout 0, scale 1/sqrt(d) (modules.py:369).
@@ -105,11 +112,13 @@ int vj_rope_apply(void* qkv, int64_t rows, int64_t D, int heads, int head_dim, c
  * lse: [B][H][S] fp32, log2-domain log-sum-exp (saved for backward).
  * head_dim in {32, 64}.  S arbitrary >= 1. */
 int vj_attn_fwd(const void* qkv, void* out, float* lse, int B, int S, int H, int head_dim, void* stream);
-/* dqkv: [B*S][3*D] bf16 (gradient w.r.t. the rotated q/k and v).
+/* dqkv: [B*S][3*D] bf16: gradient w.r.t. the rotated q/k and v; if rope_table != NULL (vj_rope_table layout,
+ * rows = B*S) the adjoint RoPE map is applied to dq and dk on the way out, giving the gradient w.r.t. the
+ * un-rotated qkv projection output.
  * scratch: vj_attn_bwd_scratch bytes (fp32 dq accumulators + delta). */
 size_t vj_attn_bwd_scratch(int B, int S, int H, int head_dim);
 int vj_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv, void* scratch,
-                int B, int S, int H, int head_dim, void* stream);
+                const void* rope_table, int B, int S, int H, int head_dim, void* stream);
 
 /* ------------------------------------------------------------------ row gather / scatter
  * apply_masks (masks/utils.py:9-21): dst[r,:] = src[index[r],:]; index[r] < 0 -> fill[:] (or 0).

@@ -170,33 +170,59 @@ def test_layernorm_fwd_bwd(dev, rows, D, xd, yd):
 # ----------------------------------------------------------------------------------------------- RoPE
 @pytest.mark.parametrize("hd,H", [(64, 2), (32, 3)])
 def test_rope_matches_oracle(dev, hd, H):
+    """Stand-alone kernel, the fused GEMM epilogue (VJ_EPI_ROPE) and the fused adjoint in attention backward
+    all against the oracle's restatement of rotate_queries_or_keys (modules.py:26-50)."""
     import vjepa_oracle as O
     from vjepa2_b200 import ops
-    B, S, Hp, Wp = 2, 50, 6, 5
+    B, S, Hp, Wp = 2, 56, 6, 5
     D = H * hd
     g = torch.Generator().manual_seed(3)
     ids = torch.randint(0, 4 * Hp * Wp, (B, S), generator=g)
     qkv = randn(B * S, 3 * D, seed=4, dtype=BF16)
-    cos, sin = ops.rope_table(ids.to(dev), B * S, S, Hp, Wp, hd, dev)
+    table = ops.rope_table(ids.to(dev), B * S, S, Hp, Wp, hd, dev)
+    assert table.dtype == torch.float16 and tuple(table.shape) == (B * S, 2, hd)
     x = qkv.to(dev).clone()
-    ops.rope_apply(x, D, H, hd, cos, sin, False)
+    ops.rope_apply(x, D, H, hd, table, False)
     q = qkv.float().view(B, S, 3, H, hd).permute(2, 0, 3, 1, 4)
     ref_q = O.rope_qk(q[0].double(), ids, Hp, Wp).float()
     ref_k = O.rope_qk(q[1].double(), ids, Hp, Wp).float()
     got = x.float().view(B, S, 3, H, hd).permute(2, 0, 3, 1, 4).cpu()
-    assert relerr(got[0], ref_q) < 4e-3 and relerr(got[1], ref_k) < 4e-3
+    assert relerr(got[0], ref_q) < 4e-3 and relerr(got[1], ref_k) < 4e-3      # fp16 table + one bf16 rounding
     assert torch.equal(got[2], q[2])                          # v untouched
     # adjoint: <R x, y> == <x, R^T y>
     y = randn(B * S, 3 * D, seed=5, dtype=BF16).to(dev)
     yt = y.clone()
-    ops.rope_apply(yt, D, H, hd, cos, sin, True)
+    ops.rope_apply(yt, D, H, hd, table, True)
     lhs = (x.float()[:, :2 * D] * y.float()[:, :2 * D]).sum()
     rhs = (qkv.to(dev).float()[:, :2 * D] * yt.float()[:, :2 * D]).sum()
     assert abs(float(lhs - rhs)) < 2e-2 * abs(float(lhs)) + 1.0
     # unmasked sequence: ids == None means arange
-    cos2, sin2 = ops.rope_table(None, 2 * S, S, Hp, Wp, hd, dev)
-    cos3, sin3 = ops.rope_table(torch.arange(S).repeat(2).to(dev), 2 * S, S, Hp, Wp, hd, dev)
-    assert torch.equal(cos2, cos3) and torch.equal(sin2, sin3)
+    t2 = ops.rope_table(None, 2 * S, S, Hp, Wp, hd, dev)
+    t3 = ops.rope_table(torch.arange(S).repeat(2).to(dev), 2 * S, S, Hp, Wp, hd, dev)
+    assert torch.equal(t2, t3)
+    # fused into the qkv GEMM epilogue == GEMM followed by the stand-alone kernel (same roundings)
+    M, K = B * S, 96
+    a = randn(M, K, seed=6, dtype=BF16).to(dev)
+    w = randn(3 * D, K, seed=7, dtype=BF16, scale=0.1).to(dev)
+    bias = randn(3 * D, seed=8).to(dev)
+    fused = torch.empty(M, 3 * D, dtype=BF16, device=dev)
+    ops.gemm(a, w, fused, M, 3 * D, K, bias=bias, rope=(table, hd, D))
+    two = torch.empty(M, 3 * D, dtype=BF16, device=dev)
+    ops.gemm(a, w, two, M, 3 * D, K, bias=bias)
+    ops.rope_apply(two, D, H, hd, table, False)
+    assert torch.equal(fused, two)
+    # fused adjoint in attention backward == attention backward followed by the stand-alone adjoint
+    out = torch.empty(M, D, dtype=BF16, device=dev)
+    lse = torch.empty(B * H * S, dtype=F32, device=dev)
+    ops.attn_fwd(fused, out, lse, B, S, H, hd)
+    dout = randn(M, D, seed=9, dtype=BF16).to(dev)
+    d_fused = torch.empty_like(fused)
+    ops.attn_bwd(fused, out, dout, lse, d_fused, B, S, H, hd, rope=table)
+    d_two = torch.empty_like(fused)
+    ops.attn_bwd(fused, out, dout, lse, d_two, B, S, H, hd)
+    assert torch.equal(d_fused[:, 2 * D:], d_two[:, 2 * D:])                   # dv untouched
+    ops.rope_apply(d_two, D, H, hd, table, True)
+    assert relerr(d_fused[:, :2 * D], d_two[:, :2 * D]) < 6e-3                  # one rounding fewer when fused
 
 
 # ----------------------------------------------------------------------------------------------- gather / im2col / indices

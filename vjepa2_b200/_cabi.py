@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libvjepa2_b200.so")
 
 VJ_BF16, VJ_F32 = 0, 1
 EPI_BIAS, EPI_GELU, EPI_DGELU, EPI_RESIDUAL = 1, 2, 4, 8
-EPI_OUT_F32, EPI_RES_F32, EPI_ROUND_BF16, EPI_AUX_OUT = 16, 32, 64, 128
+EPI_OUT_F32, EPI_RES_F32, EPI_ROUND_BF16, EPI_AUX_OUT, EPI_ROPE = 16, 32, 64, 128, 256
 
 
 class GemmArgs(Structure):
@@ -25,6 +25,7 @@ class GemmArgs(Structure):
         ("a_mn_major", c_int32), ("b_mn_major", c_int32), ("flags", c_int32),
         ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int64),
         ("aux_out", c_void_p), ("aux_in", c_void_p), ("ld_aux", c_int64),
+        ("rope_table", c_void_p), ("rope_hd", c_int32), ("rope_D", c_int32),
     ]
 
 
@@ -39,12 +40,12 @@ SIGNATURES = {
     "vj_layernorm_bwd_scratch": (c_size_t, [c_int64, c_int64]),
     "vj_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
-    "vj_rope_table": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "vj_rope_apply": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "vj_rope_table": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vj_rope_apply": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
     "vj_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vj_attn_bwd_scratch": (c_size_t, [c_int, c_int, c_int, c_int]),
-    "vj_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
-                            c_int, c_void_p]),
+    "vj_attn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                            c_int, c_int, c_void_p]),
     "vj_gather_rows": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "vj_scatter_add_rows": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "vj_mask_to_rows": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),

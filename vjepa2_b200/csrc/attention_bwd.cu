@@ -12,6 +12,8 @@
 //   P^T and dS^T are written to smem as bf16 K-major tiles; the same dS^T buffer is consumed as an
 //   MN-major A operand for dQ (no transpose).  dQ partial tiles are accumulated across key tiles with
 //   fp32 reductions into a scratch buffer and converted to bf16 by a small follow-up kernel.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "host_common.h"
 #include "../../include/vjepa2_b200.h"
@@ -60,9 +62,24 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   delta[(b * H + h) * S + q] = acc;
 }
 
-// dq accumulators fp32 [B*S][D] -> bf16 q-third of dqkv [B*S][3D]
+// adjoint of the RoPE pair map on 8 consecutive head dims (cos/sin: 8 fp16 each, vj_rope_table layout)
+__device__ __forceinline__ void rope_adjoint8(float* g, const uint4 c, const uint4 s) {
+  const __half2* ch = reinterpret_cast<const __half2*>(&c);
+  const __half2* sh = reinterpret_cast<const __half2*>(&s);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 cc = __half22float2(ch[i]);
+    const float2 ss = __half22float2(sh[i]);
+    const float g0 = g[2 * i], g1 = g[2 * i + 1];
+    g[2 * i] = cc.x * g0 + ss.y * g1;
+    g[2 * i + 1] = -ss.x * g0 + cc.y * g1;
+  }
+}
+
+// dq accumulators fp32 [B*S][D] -> bf16 q-third of dqkv [B*S][3D] (+ adjoint RoPE if a table is given)
 __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __restrict__ dq_acc,
-                                                              bf16* __restrict__ dqkv, long long rows, int D) {
+                                                              bf16* __restrict__ dqkv, long long rows, int D, int hd,
+                                                              const __half* __restrict__ rope) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int vec_per_row = D >> 3;
   if (t >= rows * vec_per_row) return;
@@ -70,9 +87,14 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
   const int c = (int)(t - row * vec_per_row) * 8;
   const float4 a = *reinterpret_cast<const float4*>(dq_acc + row * D + c);
   const float4 b = *reinterpret_cast<const float4*>(dq_acc + row * D + c + 4);
+  float g[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (rope) {
+    const __half* tr = rope + row * 2 * hd + (c % hd);
+    rope_adjoint8(g, *reinterpret_cast<const uint4*>(tr), *reinterpret_cast<const uint4*>(tr + hd));
+  }
   uint4 u;
-  u.x = pack_bf16x2(a.x, a.y); u.y = pack_bf16x2(a.z, a.w);
-  u.z = pack_bf16x2(b.x, b.y); u.w = pack_bf16x2(b.z, b.w);
+  u.x = pack_bf16x2(g[0], g[1]); u.y = pack_bf16x2(g[2], g[3]);
+  u.z = pack_bf16x2(g[4], g[5]); u.w = pack_bf16x2(g[6], g[7]);
   *reinterpret_cast<uint4*>(dqkv + row * 3 * (long long)D + c) = u;
 }
 
@@ -80,7 +102,8 @@ template <int HD>
 __global__ void __launch_bounds__(192, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                 const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
-                bf16* __restrict__ dqkv, int S, int H, int D, float scale, float scale_log2) {
+                bf16* __restrict__ dqkv, const __half* __restrict__ rope, int S, int H, int D, float scale,
+                float scale_log2) {
   using Cfg = AttnBwdCfg<HD>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -261,13 +284,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tmem_ld32(lane_addr + Cfg::COL_DV + c0, c);
       tmem_ld_wait();
       if (key_ok) {
+        const __half* tr = rope ? rope + ((long long)b * S + key) * 2 * HD + c0 : nullptr;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           uint4 u, w;
-          u.x = pack_bf16x2(__uint_as_float(a[j]) * scale, __uint_as_float(a[j + 1]) * scale);
-          u.y = pack_bf16x2(__uint_as_float(a[j + 2]) * scale, __uint_as_float(a[j + 3]) * scale);
-          u.z = pack_bf16x2(__uint_as_float(a[j + 4]) * scale, __uint_as_float(a[j + 5]) * scale);
-          u.w = pack_bf16x2(__uint_as_float(a[j + 6]) * scale, __uint_as_float(a[j + 7]) * scale);
+          float gk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gk[e] = __uint_as_float(a[j + e]) * scale;
+          if (rope) rope_adjoint8(gk, *reinterpret_cast<const uint4*>(tr + j), *reinterpret_cast<const uint4*>(tr + HD + j));
+          u.x = pack_bf16x2(gk[0], gk[1]);
+          u.y = pack_bf16x2(gk[2], gk[3]);
+          u.z = pack_bf16x2(gk[4], gk[5]);
+          u.w = pack_bf16x2(gk[6], gk[7]);
           w.x = pack_bf16x2(__uint_as_float(c[j]), __uint_as_float(c[j + 1]));
           w.y = pack_bf16x2(__uint_as_float(c[j + 2]), __uint_as_float(c[j + 3]));
           w.z = pack_bf16x2(__uint_as_float(c[j + 4]), __uint_as_float(c[j + 5]));
@@ -286,7 +314,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
 
 template <int HD>
 static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                           void* scratch, int B, int S, int H, cudaStream_t stream) {
+                           void* scratch, const void* rope, int B, int S, int H, cudaStream_t stream) {
   using Cfg = AttnBwdCfg<HD>;
   const int D = H * HD;
   float* dq_acc = reinterpret_cast<float*>(scratch);
@@ -321,13 +349,14 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
   }
   dim3 grid((S + Cfg::BT - 1) / Cfg::BT, H, B);
   const float scale = 1.0f / sqrtf((float)HD);
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmQKV, tmDO, lse, delta, dq_acc, reinterpret_cast<bf16*>(dqkv), S, H, D,
-                                              scale, scale * 1.4426950408889634f);
+  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmQKV, tmDO, lse, delta, dq_acc, reinterpret_cast<bf16*>(dqkv),
+                                              reinterpret_cast<const __half*>(rope), S, H, D, scale,
+                                              scale * 1.4426950408889634f);
   VJ_LAUNCH_CHECK();
   {
     const long long n = (long long)B * S * (D / 8);
-    attn_dq_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dq_acc, reinterpret_cast<bf16*>(dqkv),
-                                                                          (long long)B * S, D);
+    attn_dq_convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(
+        dq_acc, reinterpret_cast<bf16*>(dqkv), (long long)B * S, D, HD, reinterpret_cast<const __half*>(rope));
     VJ_LAUNCH_CHECK();
   }
   return 0;
@@ -340,14 +369,14 @@ extern "C" size_t vj_attn_bwd_scratch(int B, int S, int H, int head_dim) {
 }
 
 extern "C" int vj_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
-                           void* scratch, int B, int S, int H, int head_dim, void* stream) {
+                           void* scratch, const void* rope_table, int B, int S, int H, int head_dim, void* stream) {
   using namespace vj;
   VJ_CHECK(qkv && out && dout && lse && dqkv && scratch, "vj_attn_bwd: null pointer");
   VJ_CHECK(B > 0 && S > 0 && H > 0, "vj_attn_bwd: bad shape B=%d S=%d H=%d", B, S, H);
   VJ_CHECK(B <= 65535 && H <= 65535, "vj_attn_bwd: B/H exceed grid limits");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (head_dim == 64) return launch_attn_bwd<64>(qkv, out, dout, lse, dqkv, scratch, B, S, H, st);
-  if (head_dim == 32) return launch_attn_bwd<32>(qkv, out, dout, lse, dqkv, scratch, B, S, H, st);
+  if (head_dim == 64) return launch_attn_bwd<64>(qkv, out, dout, lse, dqkv, scratch, rope_table, B, S, H, st);
+  if (head_dim == 32) return launch_attn_bwd<32>(qkv, out, dout, lse, dqkv, scratch, rope_table, B, S, H, st);
   set_error("vj_attn_bwd: head_dim %d not supported (32, 64)", head_dim);
   return -1;
 }

@@ -2,6 +2,8 @@
 // scatter, tubelet im2col, bias-gradient column sums, fused gather+L1 loss, predictor token ranks,
 // flat EMA / AdamW / grad check.  All HBM-bound: 128-bit coalesced accesses, warp-shuffle reductions,
 // deterministic two-stage reductions (no fp32 atomics except the documented scatter-add).
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "host_common.h"
 #include "../../include/vjepa2_b200.h"
@@ -30,6 +32,17 @@ __device__ __forceinline__ void store8(void* base, int dtype, long long elem_off
     float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off);
     p[0] = make_float4(v[0], v[1], v[2], v[3]);
     p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+__device__ __forceinline__ void rope_load8(const __half* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
   }
 }
 
@@ -222,60 +235,60 @@ static inline int col_chunks(long long rows) {
 }
 
 // ---------------------------------------------------------------- RoPE
+// Table layout (fp16): [row][2][hd] -- cos then sin PER ELEMENT d of the head: angle index of element d in
+// its segment is (d mod seg) mod (seg/2) (the reference tiles sin/cos, modules.py:40-41); pass-through
+// dims carry cos = 1, sin = 0.  With it:  out[2k]   = x[2k]  *c[2k]   - x[2k+1]*s[2k]
+//                                         out[2k+1] = x[2k+1]*c[2k+1] + x[2k]  *s[2k+1]
 __global__ void rope_table_kernel(const long long* __restrict__ ids, long long n, long long period, int Hp, int Wp,
-                                  int half, float* __restrict__ cos_t, float* __restrict__ sin_t) {
+                                  int hd, int seg, __half* __restrict__ table) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int per_row = 3 * half;
-  if (t >= n * per_row) return;
-  const long long row = t / per_row;
-  const int r = (int)(t - row * per_row);
-  const int axis = r / half, j = r - axis * half;
-  const long long id = ids ? ids[row] : (row % period);
-  const long long tpf = (long long)Hp * Wp;
-  const long long f = id / tpf;
-  const long long rem = id - tpf * f;
-  const long long yy = rem / Wp;
-  const long long xx = rem - Wp * yy;
-  const double pos = (double)(axis == 0 ? f : (axis == 1 ? yy : xx));
-  const double omega = 1.0 / pow(10000.0, (double)j / (double)half);
-  double s, c;
-  sincos(pos * omega, &s, &c);
-  cos_t[t] = (float)c;
-  sin_t[t] = (float)s;
+  if (t >= n * hd) return;
+  const long long row = t / hd;
+  const int d = (int)(t - row * hd);
+  float c = 1.f, s = 0.f;
+  if (d < 3 * seg) {
+    const int half = seg >> 1;
+    const int axis = d / seg;
+    const int j = (d - axis * seg) % half;
+    const long long id = ids ? ids[row] : (row % period);
+    const long long tpf = (long long)Hp * Wp;
+    const long long f = id / tpf;
+    const long long rem = id - tpf * f;
+    const long long yy = rem / Wp;
+    const long long xx = rem - Wp * yy;
+    const double pos = (double)(axis == 0 ? f : (axis == 1 ? yy : xx));
+    const double omega = 1.0 / pow(10000.0, (double)j / (double)half);
+    double sd, cd;
+    sincos(pos * omega, &sd, &cd);
+    c = (float)cd;
+    s = (float)sd;
+  }
+  table[row * 2 * hd + d] = __float2half_rn(c);
+  table[row * 2 * hd + hd + d] = __float2half_rn(s);
 }
 
 // one thread per 8 consecutive features of the q or k part of one row
 __global__ void __launch_bounds__(256) rope_apply_kernel(bf16* __restrict__ qkv, long long rows, int D, int hd,
-                                                         int seg, const float* __restrict__ cos_t,
-                                                         const float* __restrict__ sin_t, int transpose) {
+                                                         const __half* __restrict__ table, int transpose) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int vec_per_row = (2 * D) >> 3;
   if (t >= rows * vec_per_row) return;
   const long long row = t / vec_per_row;
   const int col = (int)(t - row * vec_per_row) * 8;      // in [0, 2D)
-  const int di0 = col % hd;                               // dim inside the head (D % hd == 0)
-  if (di0 >= 3 * seg) return;                             // pass-through tail, nothing to do
-  const int half = seg >> 1;
+  const int d0 = (col % D) % hd;
   bf16* p = qkv + row * 3 * (long long)D + col;
-  float v[8], o[8];
+  float v[8], o[8], c[8], s[8];
   load8(p, VJ_BF16, 0, v);
-  const float* ct = cos_t + row * 3 * half;
-  const float* st = sin_t + row * 3 * half;
+  rope_load8(table + row * 2 * hd + d0, c);
+  rope_load8(table + row * 2 * hd + hd + d0, s);
 #pragma unroll
   for (int k = 0; k < 8; k += 2) {
-    const int di = di0 + k;
-    if (di >= 3 * seg) { o[k] = v[k]; o[k + 1] = v[k + 1]; continue; }
-    const int axis = di / seg;
-    const int i = di - axis * seg;                 // even local index
-    const int ja = i % half, jb = (i + 1) % half;
-    const float ca = ct[axis * half + ja], sa = st[axis * half + ja];
-    const float cb = ct[axis * half + jb], sb = st[axis * half + jb];
     if (!transpose) {
-      o[k] = v[k] * ca - v[k + 1] * sa;
-      o[k + 1] = v[k + 1] * cb + v[k] * sb;
+      o[k] = v[k] * c[k] - v[k + 1] * s[k];
+      o[k + 1] = v[k + 1] * c[k + 1] + v[k] * s[k + 1];
     } else {
-      o[k] = ca * v[k] + sb * v[k + 1];
-      o[k + 1] = -sa * v[k] + cb * v[k + 1];
+      o[k] = c[k] * v[k] + s[k + 1] * v[k + 1];
+      o[k + 1] = -s[k] * v[k] + c[k + 1] * v[k + 1];
     }
   }
   store8(p, VJ_BF16, 0, o);
@@ -678,27 +691,27 @@ extern "C" int vj_colsum(const void* x, int x_dtype, float* out, int accumulate,
 
 static int rope_seg(int head_dim) { return 2 * ((head_dim / 3) / 2); }
 
-extern "C" int vj_rope_table(const int64_t* ids, int64_t n, int64_t period, int Hp, int Wp, int head_dim, float* cos_t,
-                             float* sin_t, void* stream) {
-  VJ_CHECK(cos_t && sin_t && n > 0 && Hp > 0 && Wp > 0, "vj_rope_table: bad arguments");
+extern "C" int vj_rope_table(const int64_t* ids, int64_t n, int64_t period, int Hp, int Wp, int head_dim, void* table,
+                             void* stream) {
+  VJ_CHECK(table && n > 0 && Hp > 0 && Wp > 0, "vj_rope_table: bad arguments");
   VJ_CHECK(ids != nullptr || period > 0, "vj_rope_table: ids == NULL needs period > 0");
-  const int half = rope_seg(head_dim) / 2;
-  VJ_CHECK(half > 0, "vj_rope_table: head_dim %d too small", head_dim);
-  const long long total = (long long)n * 3 * half;
+  VJ_CHECK(head_dim % 8 == 0 && rope_seg(head_dim) > 0, "vj_rope_table: head_dim %d unsupported", head_dim);
+  const long long total = (long long)n * head_dim;
   rope_table_kernel<<<(unsigned)((total + 255) / 256), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<const long long*>(ids), n, period, Hp, Wp, half, cos_t, sin_t);
+      reinterpret_cast<const long long*>(ids), n, period, Hp, Wp, head_dim, rope_seg(head_dim),
+      reinterpret_cast<__half*>(table));
   VJ_LAUNCH_CHECK();
   return 0;
 }
 
-extern "C" int vj_rope_apply(void* qkv, int64_t rows, int64_t D, int heads, int head_dim, const float* cos_t,
-                             const float* sin_t, int transpose, void* stream) {
-  VJ_CHECK(qkv && cos_t && sin_t && rows > 0, "vj_rope_apply: bad arguments");
+extern "C" int vj_rope_apply(void* qkv, int64_t rows, int64_t D, int heads, int head_dim, const void* table,
+                             int transpose, void* stream) {
+  VJ_CHECK(qkv && table && rows > 0, "vj_rope_apply: bad arguments");
   VJ_CHECK((int64_t)heads * head_dim == D && head_dim % 8 == 0, "vj_rope_apply: D=%lld != heads*head_dim (%d*%d)",
            (long long)D, heads, head_dim);
   const long long total = rows * ((2 * D) >> 3);
   rope_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, STREAM(stream)>>>(
-      reinterpret_cast<bf16*>(qkv), rows, (int)D, head_dim, rope_seg(head_dim), cos_t, sin_t, transpose);
+      reinterpret_cast<bf16*>(qkv), rows, (int)D, head_dim, reinterpret_cast<const __half*>(table), transpose);
   VJ_LAUNCH_CHECK();
   return 0;
 }

@@ -11,6 +11,8 @@
 //
 // Tile: 128 (M) x BN (N) x 64 (K) per stage.  Operands may be K-major or MN-major (transposed
 // storage), which covers forward (x W^T), dgrad (dy W) and wgrad (dy^T x) without any transpose pass.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "host_common.h"
 #include "../../include/vjepa2_b200.h"
@@ -28,6 +30,8 @@ struct GemmEpi {
   void* aux_out;
   const void* aux_in;
   long long ldo, ldr, ld_aux;
+  const __half* rope;
+  int rope_hd, rope_D;
   int flags;
 };
 
@@ -83,6 +87,34 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmEpi& e, EpiSide& s, 
     for (int i = 0; i < 4; ++i)
       if (col0 + i * 8 < N) s.v[4 + i] = *reinterpret_cast<const uint4*>(ap + i * 8);
   }
+  if (flags & VJ_EPI_ROPE) {
+    // two 16-column groups (a group never straddles a head: hd % 16 == 0): cos -> v[2g..2g+1], sin -> v[4+2g..]
+    const __half* tr = e.rope + row * 2 * e.rope_hd;
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int c = col0 + g * 16;
+      if (c < N && c < 2 * e.rope_D) {
+        const int d0 = (c % e.rope_D) % e.rope_hd;
+        s.v[2 * g] = *reinterpret_cast<const uint4*>(tr + d0);
+        s.v[2 * g + 1] = *reinterpret_cast<const uint4*>(tr + d0 + 8);
+        s.v[4 + 2 * g] = *reinterpret_cast<const uint4*>(tr + e.rope_hd + d0);
+        s.v[4 + 2 * g + 1] = *reinterpret_cast<const uint4*>(tr + e.rope_hd + d0 + 8);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void rope_pairs8(float* v, const uint4 c, const uint4 s) {
+  const __half2* ch = reinterpret_cast<const __half2*>(&c);
+  const __half2* sh = reinterpret_cast<const __half2*>(&s);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 cc = __half22float2(ch[i]);
+    const float2 ss = __half22float2(sh[i]);
+    const float x0 = v[2 * i], x1 = v[2 * i + 1];
+    v[2 * i] = x0 * cc.x - x1 * ss.x;
+    v[2 * i + 1] = x1 * cc.y + x0 * ss.y;
+  }
 }
 
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): one rcp + one ex2 instead of erff's two branches.
@@ -122,6 +154,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t 
       if (col0 + i < N) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + i));
         v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    }
+  }
+  if (flags & VJ_EPI_ROPE) {
+    // mirror the reference: the Linear output is rounded to bf16 before the rotation (modules.py:330-365)
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int c = col0 + g * 16;
+      if (c < N && c < 2 * e.rope_D) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[g * 16 + i] = bf16_round(v[g * 16 + i]);
+        rope_pairs8(v + g * 16, s.v[2 * g], s.v[4 + 2 * g]);
+        rope_pairs8(v + g * 16 + 8, s.v[2 * g + 1], s.v[4 + 2 * g + 1]);
       }
     }
   }
@@ -378,6 +423,7 @@ static int launch_gemm(const vj_gemm_args* g, cudaStream_t stream) {
   GemmEpi e;
   e.out = g->out; e.bias = g->bias; e.residual = g->residual; e.aux_out = g->aux_out; e.aux_in = g->aux_in;
   e.ldo = g->ldo; e.ldr = g->ldr; e.ld_aux = g->ld_aux; e.flags = g->flags;
+  e.rope = reinterpret_cast<const __half*>(g->rope_table); e.rope_hd = g->rope_hd; e.rope_D = g->rope_D;
 
   auto kern = gemm_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
@@ -433,6 +479,12 @@ extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
   if (g->flags & VJ_EPI_AUX_OUT) VJ_CHECK(g->aux_out != nullptr && g->ld_aux % 8 == 0, "vj_gemm: bad aux_out");
   if (g->flags & VJ_EPI_DGELU) VJ_CHECK(g->aux_in != nullptr && g->ld_aux % 8 == 0, "vj_gemm: bad aux_in");
   VJ_CHECK(!((g->flags & VJ_EPI_DGELU) && (g->flags & VJ_EPI_RES_F32)), "vj_gemm: DGELU with an fp32 residual is not supported");
+  if (g->flags & VJ_EPI_ROPE) {
+    VJ_CHECK(!(g->flags & (VJ_EPI_RESIDUAL | VJ_EPI_DGELU | VJ_EPI_GELU)), "vj_gemm: ROPE combines with BIAS only");
+    VJ_CHECK(g->rope_table && (g->rope_hd == 32 || g->rope_hd == 64) && g->rope_D > 0 && g->rope_D % g->rope_hd == 0 &&
+                 g->N == 3 * (int64_t)g->rope_D && g->rope_D % 16 == 0,
+             "vj_gemm: bad ROPE arguments (hd=%d D=%d N=%lld)", g->rope_hd, g->rope_D, (long long)g->N);
+  }
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
   VJ_CHECK(!(amn && !bmn), "vj_gemm: (A MN-major, B K-major) is not instantiated");
   const int bn = pick_bn(g->N, bmn, g->M);

@@ -295,7 +295,7 @@ static void test_attn(int B, int S, int H, int hd, bool bwd) {
     const size_t sb = vj_attn_bwd_scratch(B, S, H, hd);
     void* scratch = dalloc<char>(sb);
     CK(cudaMemset(dqkv, 0xFF, nq * 2));
-    VJ(vj_attn_bwd(qkv, out, dout, lse, dqkv, scratch, B, S, H, hd, 0));
+    VJ(vj_attn_bwd(qkv, out, dout, lse, dqkv, scratch, nullptr, B, S, H, hd, 0));
     ref_attn_bwd_kernel<<<grid, 64>>>(qkv, oref, dout, lref, dref, B, S, H, hd);
     CK(cudaDeviceSynchronize());
     std::vector<float> got = d2h_bf16(dqkv, nq), ref = d2h_f32(dref, nq);
@@ -370,10 +370,10 @@ static void bench_attn(int B, int S, int H, int hd, bool bwd) {
   const double fl = 4.0 * B * H * (double)S * S * hd;
   printf("[bench attn fwd] B=%d S=%d H=%d hd=%d  %.3f ms  %.1f TFLOP/s\n", B, S, H, hd, ms, fl / ms * 1e-9);
   if (bwd) {
-    for (int i = 0; i < 2; ++i) VJ(vj_attn_bwd(qkv, out, dout, lse, dqkv, scratch, B, S, H, hd, 0));
+    for (int i = 0; i < 2; ++i) VJ(vj_attn_bwd(qkv, out, dout, lse, dqkv, scratch, nullptr, B, S, H, hd, 0));
     CK(cudaDeviceSynchronize());
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) VJ(vj_attn_bwd(qkv, out, dout, lse, dqkv, scratch, B, S, H, hd, 0));
+    for (int i = 0; i < iters; ++i) VJ(vj_attn_bwd(qkv, out, dout, lse, dqkv, scratch, nullptr, B, S, H, hd, 0));
     cudaEventRecord(e1);
     CK(cudaEventSynchronize(e1));
     cudaEventElapsedTime(&ms, e0, e1);

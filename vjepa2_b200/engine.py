@@ -57,7 +57,7 @@ class BlockG:
 # ------------------------------------------------------------------------------------------------
 # one transformer block
 # ------------------------------------------------------------------------------------------------
-def block_forward(h: BlockH, x, x_out, B, S, heads, hd, cos, sin, save, st, ws):
+def block_forward(h: BlockH, x, x_out, B, S, heads, hd, rope, save, st, ws):
     """x: residual stream [B*S, D] (bf16 encoder / fp32 predictor); x_out: where the block output goes.
     save=True keeps everything backward needs in ws.act; otherwise temporaries live in ws.tmp (caller
     brackets the call with mark/release).  Returns saved tuple or None."""
@@ -72,8 +72,7 @@ def block_forward(h: BlockH, x, x_out, B, S, heads, hd, cos, sin, save, st, ws):
     ln1 = A((M, D), BF16)
     ops.layernorm_fwd(x, h.n1w, h.n1b, ln1, mean1, rstd1, 1e-6, st)
     qkv = A((M, 3 * D), BF16)
-    ops.gemm(ln1, h.qkv_w, qkv, M, 3 * D, D, bias=h.qkv_b, st=st)
-    ops.rope_apply(qkv, D, heads, hd, cos, sin, False, st)
+    ops.gemm(ln1, h.qkv_w, qkv, M, 3 * D, D, bias=h.qkv_b, rope=(rope, hd, D), st=st)     # qkv + fused 3-axis RoPE
     att = A((M, D), BF16)
     lse = A((B * heads * S,), F32)
     ops.attn_fwd(qkv, att, lse, B, S, heads, hd, st)
@@ -95,7 +94,7 @@ def _as_bf16(t, st, ws):
     return out
 
 
-def block_backward(h: BlockH, g: BlockG, saved, dx2, dx0, B, S, heads, hd, cos, sin, st, ws):
+def block_backward(h: BlockH, g: BlockG, saved, dx2, dx0, B, S, heads, hd, rope, st, ws):
     """dx2: gradient w.r.t. the block output [M, D] (dtype of the residual stream); dx0: output buffer for
     the gradient w.r.t. the block input (may not alias dx2).  Parameter gradients are ACCUMULATED into g
     (fp32).  Temporaries come from ws.tmp and are released before returning."""
@@ -123,8 +122,7 @@ def block_backward(h: BlockH, g: BlockG, saved, dx2, dx0, B, S, heads, hd, cos, 
     ops.gemm(d1, att, g.proj_w, D, D, M, a_mn=True, b_mn=True, residual=g.proj_w, st=st)
     ops.colsum(d1, g.proj_b, True, st, T)
     dqkv = T((M, 3 * D), BF16)
-    ops.attn_bwd(qkv, att, datt, lse, dqkv, B, S, heads, hd, st, T)
-    ops.rope_apply(dqkv, D, heads, hd, cos, sin, True, st)
+    ops.attn_bwd(qkv, att, datt, lse, dqkv, B, S, heads, hd, st, T, rope)                  # + fused adjoint RoPE
     dln1 = T((M, D), BF16)
     ops.gemm(dqkv, h.qkv_w, dln1, M, D, 3 * D, b_mn=True, st=st)
     ops.gemm(dqkv, ln1, g.qkv_w, 3 * D, D, M, a_mn=True, b_mn=True, residual=g.qkv_w, st=st)
@@ -134,14 +132,14 @@ def block_backward(h: BlockH, g: BlockG, saved, dx2, dx0, B, S, heads, hd, cos, 
     return dx0
 
 
-def _run_blocks_forward(blocks, x, B, S, heads, hd, cos, sin, save, st, ws, on_block=None):
+def _run_blocks_forward(blocks, x, B, S, heads, hd, rope, save, st, ws, on_block=None):
     """Runs the block stack.  save=True: every block output is a fresh ws.act tensor (it is the next block's
     saved input).  save=False: two ping-pong residual buffers, per-block temporaries released immediately."""
     saved_all = []
     if save:
         for i, h in enumerate(blocks):
             x_out = ws.act(tuple(x.shape), x.dtype)
-            saved_all.append(block_forward(h, x, x_out, B, S, heads, hd, cos, sin, True, st, ws))
+            saved_all.append(block_forward(h, x, x_out, B, S, heads, hd, rope, True, st, ws))
             x = x_out
             if on_block is not None:
                 on_block(i, x)
@@ -150,7 +148,7 @@ def _run_blocks_forward(blocks, x, B, S, heads, hd, cos, sin, save, st, ws, on_b
     for i, h in enumerate(blocks):
         x_out = pp[i & 1]
         mk = ws.mark()
-        block_forward(h, x, x_out, B, S, heads, hd, cos, sin, False, st, ws)
+        block_forward(h, x, x_out, B, S, heads, hd, rope, False, st, ws)
         ws.release(mk)
         x = x_out
         if on_block is not None:
@@ -219,7 +217,7 @@ def encoder_forward(rt: EncoderRT, clips, ids, grid_hw, save, ws=None, out_layer
         Bp, S = B, M // B
     x = A((M, D), BF16)
     ops.gemm(cols, rt.pe_w, x, M, D, rt.pe_k, bias=rt.pe_b, st=st)
-    cos, sin = ops.rope_table(ids, M, S, Hp, Wp, hd, dev, st, A)
+    rope = ops.rope_table(ids, M, S, Hp, Wp, hd, dev, st, A)
     outs = []
 
     def collect(i, xi):
@@ -228,7 +226,7 @@ def encoder_forward(rt: EncoderRT, clips, ids, grid_hw, save, ws=None, out_layer
             ops.layernorm_fwd(xi, rt.norm_w, rt.norm_b, o, None, None, 1e-6, st)
             outs.append(o.view(Bp, S, D))
 
-    x, blocks_saved = _run_blocks_forward(rt.blocks, x, Bp, S, heads, hd, cos, sin, save, st, ws,
+    x, blocks_saved = _run_blocks_forward(rt.blocks, x, Bp, S, heads, hd, rope, save, st, ws,
                                           collect if out_layers is not None else None)
     if out_layers is not None:
         return outs, None
@@ -238,7 +236,7 @@ def encoder_forward(rt: EncoderRT, clips, ids, grid_hw, save, ws=None, out_layer
         mean = A((M,), F32)
         rstd = A((M,), F32)
     ops.layernorm_fwd(x, rt.norm_w, rt.norm_b, out, mean, rstd, 1e-6, st)
-    saved = (cols, cos, sin, blocks_saved, x, mean, rstd, Bp, S) if save else None
+    saved = (cols, rope, blocks_saved, x, mean, rstd, Bp, S) if save else None
     return out.view(Bp, S, D), saved
 
 
@@ -246,7 +244,7 @@ def encoder_backward(rt: EncoderRT, saved, dout, gbuf, ws=None, on_block_done=No
     """dout: gradient w.r.t. the encoder output [B', S, D] (bf16 or fp32).  Accumulates parameter
     gradients into gbuf (flat fp32).  The input clip needs no gradient."""
     st = ops.stream()
-    cols, cos, sin, blocks_saved, x_last, mean, rstd, Bp, S = saved
+    cols, rope, blocks_saved, x_last, mean, rstd, Bp, S = saved
     D, heads, hd = rt.D, rt.heads, rt.hd
     M = Bp * S
     if ws is None:
@@ -263,7 +261,7 @@ def encoder_backward(rt: EncoderRT, saved, dout, gbuf, ws=None, on_block_done=No
     k = 0
     for i in range(len(rt.blocks) - 1, -1, -1):
         k ^= 1
-        dx = block_backward(rt.blocks[i], g["blocks"][i], blocks_saved[i], dx, pp[k], Bp, S, heads, hd, cos, sin, st, ws)
+        dx = block_backward(rt.blocks[i], g["blocks"][i], blocks_saved[i], dx, pp[k], Bp, S, heads, hd, rope, st, ws)
         blocks_saved[i] = None                  # release activations as we go (torch allocator path)
         if on_block_done is not None:
             on_block_done(i)
@@ -337,8 +335,8 @@ def predictor_forward(rt: PredictorRT, z, masks_x, masks_y, mask_index, save, ws
     mi = mask_index % len(rt.mask_tokens)
     x = A((B * S, D), F32)
     ops.gather_rows(emb, x, asm_idx, fill=rt.mask_tokens[mi], st=st)
-    cos, sin = ops.rope_table(ids_sorted, B * S, S, rt.grid, rt.grid, hd, dev, st, A)
-    x, blocks_saved = _run_blocks_forward(rt.blocks, x, B, S, heads, hd, cos, sin, save, st, ws)
+    rope = ops.rope_table(ids_sorted, B * S, S, rt.grid, rt.grid, hd, dev, st, A)
+    x, blocks_saved = _run_blocks_forward(rt.blocks, x, B, S, heads, hd, rope, save, st, ws)
     # LayerNorm is row-wise, so norm(x)[targets] == norm(x[targets]) (predictor.py:233,240-242)
     xg = A((B * Kp, D), F32)
     ops.gather_rows(x, xg, tgt_pos, st=st)
@@ -352,7 +350,7 @@ def predictor_forward(rt: PredictorRT, z, masks_x, masks_y, mask_index, save, ws
     ops.gemm(y16, rt.proj_w, out, B * Kp, Din, D, bias=rt.proj_b, st=st)
     saved = None
     if save:
-        saved = (z16, cos, sin, blocks_saved, xg, mean, rstd, y16, tgt_pos, ctx_pos, seq_to_tgt, mi, B, Kc, Kp)
+        saved = (z16, rope, blocks_saved, xg, mean, rstd, y16, tgt_pos, ctx_pos, seq_to_tgt, mi, B, Kc, Kp)
     return out.view(B, Kp, Din), saved
 
 
@@ -360,7 +358,7 @@ def predictor_backward(rt: PredictorRT, saved, dout, gbuf, ws=None, dz_out=None)
     """dout bf16 [B, Kp, D_in].  Accumulates parameter grads into gbuf; returns d(z) bf16 [B, Kc, D_in]
     (written to dz_out if given, else allocated from ws.act so it outlives this call's temporaries)."""
     st = ops.stream()
-    z16, cos, sin, blocks_saved, xg, mean, rstd, y16, tgt_pos, ctx_pos, seq_to_tgt, mi, B, Kc, Kp = saved
+    z16, rope, blocks_saved, xg, mean, rstd, y16, tgt_pos, ctx_pos, seq_to_tgt, mi, B, Kc, Kp = saved
     dev = z16.device
     if ws is None:
         ws = TorchAlloc(dev)
@@ -386,7 +384,7 @@ def predictor_backward(rt: PredictorRT, saved, dout, gbuf, ws=None, dz_out=None)
     k = 0
     for i in range(len(rt.blocks) - 1, -1, -1):
         k ^= 1
-        dx = block_backward(rt.blocks[i], g["blocks"][i], blocks_saved[i], dx, pp[k], B, S, heads, hd, cos, sin, st, ws)
+        dx = block_backward(rt.blocks[i], g["blocks"][i], blocks_saved[i], dx, pp[k], B, S, heads, hd, rope, st, ws)
         blocks_saved[i] = None
     # mask token: sum of the gradients of every target slot (predictor.py:195-197)
     dtg = T((B * Kp, D), F32)

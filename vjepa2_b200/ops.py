@@ -55,7 +55,7 @@ _gemm_args = C.GemmArgs()
 
 
 def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, bias=None, gelu=False, dgelu_aux=None, residual=None,
-         aux_out=None, round_bf16=False, st=None):
+         aux_out=None, round_bf16=False, rope=None, st=None):
     """out[M,N] = epi(A[M,K] @ B[N,K]^T).  a/b: 2-D bf16 views whose last dim is contiguous
     (a: [M,K] or, if a_mn, [K,M]; b likewise).  out: bf16 or fp32 [M,N]."""
     g = _gemm_args
@@ -76,6 +76,9 @@ def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, bias=None, gelu=False, d
         flags |= C.EPI_ROUND_BF16
     if aux_out is not None:
         flags |= C.EPI_AUX_OUT
+    if rope is not None:                    # (table, head_dim, D): fused 3-axis RoPE on the q/k thirds
+        flags |= C.EPI_ROPE
+        g.rope_table, g.rope_hd, g.rope_D = rope[0].data_ptr(), rope[1], rope[2]
     g.a, g.b, g.out = a.data_ptr(), b.data_ptr(), out.data_ptr()
     g.M, g.N, g.K = M, N, K
     g.lda, g.ldb, g.ldo = a.stride(0), b.stride(0), out.stride(0)
@@ -126,22 +129,19 @@ def rope_seg(head_dim: int) -> int:
 
 
 def rope_table(ids, n, period, Hp, Wp, head_dim, device, st=None, alloc=None):
-    """ids: int64 [n] flattened token ids, or None for id(row) = row % period -> (cos, sin) fp32 [n, 3*seg/2]."""
-    half = rope_seg(head_dim) // 2
-    if alloc is not None:
-        cos, sin = alloc((n, 3 * half), F32), alloc((n, 3 * half), F32)
-    else:
-        cos = torch.empty(n, 3 * half, dtype=F32, device=device)
-        sin = torch.empty_like(cos)
-    _counting_check(C.load().vj_rope_table(_p(ids), n, period, Hp, Wp, head_dim, cos.data_ptr(), sin.data_ptr(),
-                                   st if st is not None else stream()), "vj_rope_table")
-    return cos, sin
+    """ids: int64 [n] flattened token ids, or None for id(row) = row % period -> fp16 table [n, 2, head_dim]
+    (per-element cos then sin, see include/vjepa2_b200.h)."""
+    shape = (n, 2, head_dim)
+    table = alloc(shape, torch.float16) if alloc is not None else torch.empty(shape, dtype=torch.float16, device=device)
+    _counting_check(C.load().vj_rope_table(_p(ids), n, period, Hp, Wp, head_dim, table.data_ptr(),
+                                           st if st is not None else stream()), "vj_rope_table")
+    return table
 
 
-def rope_apply(qkv, D, heads, head_dim, cos, sin, transpose=False, st=None):
+def rope_apply(qkv, D, heads, head_dim, table, transpose=False, st=None):
     rows = qkv.shape[0]
-    _counting_check(C.load().vj_rope_apply(qkv.data_ptr(), rows, D, heads, head_dim, cos.data_ptr(), sin.data_ptr(),
-                                   int(transpose), st if st is not None else stream()), "vj_rope_apply")
+    _counting_check(C.load().vj_rope_apply(qkv.data_ptr(), rows, D, heads, head_dim, table.data_ptr(),
+                                           int(transpose), st if st is not None else stream()), "vj_rope_apply")
     return qkv
 
 
@@ -152,11 +152,12 @@ def attn_fwd(qkv, out, lse, B, S, H, head_dim, st=None):
     return out
 
 
-def attn_bwd(qkv, out, dout, lse, dqkv, B, S, H, head_dim, st=None, alloc=None):
+def attn_bwd(qkv, out, dout, lse, dqkv, B, S, H, head_dim, st=None, alloc=None, rope=None):
+    """rope: optional fp16 table (rope_table layout): the adjoint RoPE map is fused into the dq / dk outputs."""
     scratch = _scratch(C.load().vj_attn_bwd_scratch(B, S, H, head_dim), qkv.device, alloc)
-    _counting_check(C.load().vj_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-                                 scratch.data_ptr(), B, S, H, head_dim, st if st is not None else stream()),
-            "vj_attn_bwd")
+    _counting_check(C.load().vj_attn_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                         dqkv.data_ptr(), scratch.data_ptr(), _p(rope), B, S, H, head_dim,
+                                         st if st is not None else stream()), "vj_attn_bwd")
     return dqkv
 
 
