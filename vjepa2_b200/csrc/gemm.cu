@@ -285,7 +285,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -328,7 +328,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
           const uint32_t sb = sa + Cfg::A_BYTES;
           const uint64_t ad = A_MN ? desc_mnmajor<128>(sa, 8192) : desc_kmajor<128>(sa);
@@ -440,23 +440,25 @@ static int launch_gemm(const vj_gemm_args* g, cudaStream_t stream) {
   return 0;
 }
 
-// pick the N tile that wastes the fewest MMA columns; MN-major B needs a multiple of 64
+// Pick the N tile.  Measured on B200 (profiles/r01_*): per-FLOP speed of the mainloop is ~1.0 at BN=256,
+// ~0.85 at 176/192 and ~0.7 at 128 (smaller tiles re-read A more often and give the single MMA-issuing
+// thread less time per k-block), so a wide tile wins unless it leaves many dead columns.
 static int pick_bn(long long N, bool b_mn, long long M) {
-  const int cands_k[] = {256, 176, 128};
-  const int cands_mn[] = {256, 192, 128};
+  const int cands_k[] = {256, 192, 176, 128};
+  const int cands_mn[] = {256, 192, 192, 128};
+  const double speed[] = {1.0, 0.86, 0.85, 0.70};
   const int* c = b_mn ? cands_mn : cands_k;
   int best = 128;
   double best_cost = 1e30;
   const long long num_m = (M + 127) / 128;
-  for (int i = 0; i < 3; ++i) {
+  const long long sms = sm_count();
+  for (int i = 0; i < 4; ++i) {
     const int bn = c[i];
     const long long tiles_n = (N + bn - 1) / bn;
-    // cost ~ issued MMA columns, with a mild penalty for narrow tiles (smem bandwidth) and for
-    // grids that cannot fill the machine
-    double cost = (double)tiles_n * bn * (bn <= 128 ? 1.12 : 1.0);
     const long long tiles = tiles_n * num_m;
-    if (tiles < 148) cost *= 1.0 + 0.5 * (148 - tiles) / 148.0 * (bn > 128 ? 1.0 : 0.0);
-    if (cost < best_cost) { best_cost = cost; best = bn; }
+    const long long waves = (tiles + sms - 1) / sms;              // wave quantisation of the persistent grid
+    const double cost = (double)waves * bn / speed[i];
+    if (cost < best_cost * 0.999) { best_cost = cost; best = bn; }
   }
   return best;
 }
@@ -491,6 +493,7 @@ extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
 #define VJ_GEMM_CASE(BN_, A_, B_) \
   if (bn == BN_ && amn == A_ && bmn == B_) return launch_gemm<BN_, A_, B_>(g, stream);
   VJ_GEMM_CASE(256, false, false)
+  VJ_GEMM_CASE(192, false, false)
   VJ_GEMM_CASE(176, false, false)
   VJ_GEMM_CASE(128, false, false)
   VJ_GEMM_CASE(256, false, true)
