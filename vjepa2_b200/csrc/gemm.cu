@@ -1,16 +1,19 @@
 // Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> smem ring -> tcgen05.mma -> TMEM
-// (double-buffered accumulator) -> epilogue warps (tcgen05.ld, fused bias / GELU / dGELU / residual).
+// (double-buffered accumulator) -> epilogue warps -> swizzled smem staging -> TMA store / TMA reduce-add.
 //
 //   warp 0   TMA producer (one elected lane)
 //   warp 1   MMA issuer   (one elected lane issues tcgen05.mma / tcgen05.commit)
 //   warp 2   TMEM allocate / free
 //   warp 3   idle
 //   warps 4-11 epilogue, two warpgroups: warp (4+q) / (8+q) owns TMEM lanes [32q, 32q+32) == output rows
-//              m0+32q..+31; group 0 takes the even 32-column chunks of the tile, group 1 the odd ones.
-//              Residual / dGELU operands of the next chunk are prefetched while the current one is computed.
+//              m0+32q..+31; the 128-byte-wide column groups of the tile alternate between the groups.
+//              Each warp converts its 32x(128 B) block in registers (bias, RoPE, bf16 rounding, GELU,
+//              GELU', residual -- operands prefetched one step ahead), writes it to its own 4 KB swizzled
+//              staging buffer and hands it to the TMA unit: full-line coalesced stores, no LSU pressure.
+//              fp32 "out += acc" (weight gradients) uses cp.reduce.async.bulk.tensor (.add) -- no read at all.
 //
-// Tile: 128 (M) x BN (N) x 64 (K) per stage.  Operands may be K-major or MN-major (transposed
-// storage), which covers forward (x W^T), dgrad (dy W) and wgrad (dy^T x) without any transpose pass.
+// Tile: 128 (M) x BN (N) x 64 (K) per stage.  Operands may be K-major or MN-major (transposed storage), which
+// covers forward (x W^T), dgrad (dy W) and wgrad (dy^T x) without any transpose pass.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -22,30 +25,47 @@ namespace vj {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_STG_BYTES = 4096;          // per epilogue warp, per staging buffer: 32 rows x 128 B
+constexpr int EPI_INTERNAL_REDUCE = 1 << 20;  // out += acc through TMA reduce-add
+
+// Optional in-kernel cycle accounting (build with -DVJ_GEMM_PROFILE; used by `make build/selftest_prof`):
+//  [0] MMA warp total  [1] MMA wait full (TMA late)  [2] MMA wait tempty (epilogue late)
+//  [3] producer wait empty  [4] epilogue wait tfull  [5] epilogue busy  [6] CTAs  [7] epilogue tmem ld+wait
+#ifdef VJ_GEMM_PROFILE
+__device__ unsigned long long g_gemm_prof[8];
+#define VJ_PROF_T0(v) const long long v = clock64()
+#define VJ_PROF_ADD(acc, v) acc += clock64() - v
+#else
+#define VJ_PROF_T0(v)
+#define VJ_PROF_ADD(acc, v)
+#endif
 
 struct GemmEpi {
-  void* out;
   const float* bias;
   const void* residual;
-  void* aux_out;
   const void* aux_in;
-  long long ldo, ldr, ld_aux;
+  long long ldr, ld_aux;
   const __half* rope;
   int rope_hd, rope_D;
   int flags;
 };
 
-template <int BN>
+template <int BN, bool AUX>
 struct GemmCfg {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int STG_PER_WARP = (AUX ? 2 : 1) * GEMM_STG_BYTES;   // out (+ pre-activation) staging
+  static constexpr int STG_TOTAL = 8 * STG_PER_WARP;
+  static constexpr int STAGES_RAW = (227 * 1024 - STG_TOTAL - 2048) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;   // TMEM columns between the two accumulator stages
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static_assert(BN <= 256 && BN % 16 == 0, "UMMA N must be a multiple of 16 and <= 256");
-  static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-B alignment");
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_STG + STG_TOTAL;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024 /*align slack*/;
+  static_assert(BN <= 256 && BN % 64 == 0, "BN must be a multiple of 64 (128-byte bf16 store groups) and <= 256");
+  static_assert(STAGES >= 3, "need at least 3 pipeline stages");
 };
 
 __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& mb, int& nb) {
@@ -60,8 +80,24 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int&
   mb = first_m + (r - nb * gm);
 }
 
-// Side inputs of one 32-column chunk of one output row, fetched ahead of the accumulator:
-//   bf16 residual -> v[0..3];  fp32 residual -> v[0..7];  bf16 dGELU operand -> v[4..7]
+// ---------------------------------------------------------------- TMA store helpers
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------- epilogue math
+// Side inputs of one 32-column block of one output row, fetched ahead of the accumulator:
+//   bf16 residual -> v[0..3];  fp32 residual -> v[0..7];  bf16 dGELU operand -> v[4..7];  RoPE cos/sin -> v[0..7]
 struct EpiSide {
   uint4 v[8];
 };
@@ -117,34 +153,45 @@ __device__ __forceinline__ void rope_pairs8(float* v, const uint4 c, const uint4
   }
 }
 
-// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): one rcp + one ex2 instead of erff's two branches.
-// Returns erf(z) and e = exp(-z*z) (reused for the Gaussian pdf in gelu').
-__device__ __forceinline__ float erf_as(float z, float& e) {
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// erfc(|z|) via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 6 FMA-pipe ops.
+// Also returns e = exp(-z*z) (the Gaussian factor gelu' needs).
+__device__ __forceinline__ float erfc_abs(float z, float& e) {
   const float az = fabsf(z);
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
-  e = exp2f(-az * az * 1.4426950408889634f);
+  const float t = mufu_rcp(fmaf(0.3275911f, az, 1.0f));
+  e = mufu_ex2(az * az * -1.4426950408889634f);
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float r = 1.0f - p * t * e;
-  return copysignf(r, z);
+  return p * t * e;
 }
+// gelu(x) = x * Phi(x), Phi(x) = 1 - erfc(x/sqrt2)/2 for x >= 0, erfc(|x|/sqrt2)/2 for x < 0 (no cancellation)
 __device__ __forceinline__ float gelu_fast(float x) {
   float e;
-  return 0.5f * x * (1.0f + erf_as(x * 0.70710678118654752f, e));
+  const float h = 0.5f * erfc_abs(x * 0.70710678118654752f, e);
+  return x * (x >= 0.f ? 1.0f - h : h);
 }
 __device__ __forceinline__ float dgelu_fast(float x) {
   float e;
-  const float cdf = 0.5f * (1.0f + erf_as(x * 0.70710678118654752f, e));
+  const float h = 0.5f * erfc_abs(x * 0.70710678118654752f, e);
+  const float cdf = x >= 0.f ? 1.0f - h : h;
   return fmaf(x * 0.39894228040143268f, e, cdf);
 }
 
-template <int BN>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t (&acc)[32], const EpiSide& s,
-                                               long long row, int col0, int N) {
-  // 32 consecutive columns of one output row
-  float v[32];
+// 32 consecutive columns of one output row: accumulator -> final values (v) and optional pre-activation (pre)
+template <bool WANT_PRE>
+__device__ __forceinline__ void epilogue_math(const GemmEpi& e, const uint32_t (&acc)[32], const EpiSide& s, int col0,
+                                              int N, float (&v)[32], float (&pre)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
   const int flags = e.flags;
@@ -170,17 +217,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t 
       }
     }
   }
-  if (flags & VJ_EPI_AUX_OUT) {
-    bf16* ap = reinterpret_cast<bf16*>(e.aux_out) + row * e.ld_aux + col0;
+  if (WANT_PRE) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      if (col0 + i < N) {
-        uint4 u;
-        u.x = pack_bf16x2(v[i], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
-        u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
-        *reinterpret_cast<uint4*>(ap + i) = u;
-      }
-    }
+    for (int i = 0; i < 32; ++i) pre[i] = v[i];
   }
   if (flags & VJ_EPI_ROUND_BF16) {
 #pragma unroll
@@ -217,35 +256,36 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& e, const uint32_t 
       }
     }
   }
-  if (flags & VJ_EPI_OUT_F32) {
-    float* op = reinterpret_cast<float*>(e.out) + row * e.ldo + col0;
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      if (col0 + i < N) *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    }
-  } else {
-    bf16* op = reinterpret_cast<bf16*>(e.out) + row * e.ldo + col0;
-#pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      if (col0 + i < N) {
-        uint4 u;
-        u.x = pack_bf16x2(v[i], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
-        u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
-        *reinterpret_cast<uint4*>(op + i) = u;
-      }
-    }
-  }
 }
 
-template <int BN, bool A_MN, bool B_MN>
+// row `lane` of a [32 rows][128 B] staging block, 128-byte swizzle: 16-B chunk c of row r lives at c ^ (r & 7)
+__device__ __forceinline__ void stage_bf16x32(uint8_t* stg, int lane, int half, const float (&v)[32]) {
+  uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(v[i * 8], v[i * 8 + 1]); u.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
+    u.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]); u.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
+    *reinterpret_cast<uint4*>(rowp + (((half * 4 + i) ^ (lane & 7)) << 4)) = u;
+  }
+}
+__device__ __forceinline__ void stage_f32x32(uint8_t* stg, int lane, const float (&v)[32]) {
+  uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    *reinterpret_cast<float4*>(rowp + ((i ^ (lane & 7)) << 4)) = make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+}
+
+template <int BN, bool A_MN, bool B_MN, bool AUX>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpi epi, int M,
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, GemmEpi epi, int M,
             int N, int K) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, AUX>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -262,6 +302,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -288,12 +329,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      long long prof_a = 0;
+      (void)prof_a;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int mb, nb;
         tile_coords(tile, num_m, num_n, mb, nb);
         const int m0 = mb * GEMM_BM, n0 = nb * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
+          VJ_PROF_T0(tw);
           mbar_wait(&empty[stage], phase ^ 1);
+          VJ_PROF_ADD(prof_a, tw);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
           mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
@@ -312,6 +357,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+#ifdef VJ_GEMM_PROFILE
+      atomicAdd(&g_gemm_prof[3], (unsigned long long)prof_a);
+#endif
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
@@ -319,14 +367,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
+    long long prof_full = 0, prof_te = 0;
+    (void)prof_full; (void)prof_te;
+    VJ_PROF_T0(t_all);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
+      VJ_PROF_T0(t1);
       mbar_wait(&tempty[as], aphase ^ 1);
+      VJ_PROF_ADD(prof_te, t1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
       for (int kb = 0; kb < num_kb; ++kb) {
+        VJ_PROF_T0(t2);
         mbar_wait(&full[stage], phase);
+        VJ_PROF_ADD(prof_full, t2);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
@@ -346,51 +401,105 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
+#ifdef VJ_GEMM_PROFILE
+    if (lane == 0) {
+      atomicAdd(&g_gemm_prof[0], (unsigned long long)(clock64() - t_all));
+      atomicAdd(&g_gemm_prof[1], (unsigned long long)prof_full);
+      atomicAdd(&g_gemm_prof[2], (unsigned long long)prof_te);
+      atomicAdd(&g_gemm_prof[6], 1ull);
+    }
+#endif
   } else if (warp >= 4) {
     // ------------------------------------------------ epilogue
     const int q = warp & 3;
-    const int eg = (warp - 4) >> 2;                 // warpgroup 0: even chunks, 1: odd chunks
-    constexpr int NCH = (BN + 31) / 32;
+    const int ew = warp - 4;                         // 0..7
+    const int eg = ew >> 2;                          // warpgroup 0: even column groups, 1: odd
+    const bool out_f32 = (epi.flags & VJ_EPI_OUT_F32) != 0;
+    constexpr bool want_aux = AUX;
+    const bool reduce = (epi.flags & EPI_INTERNAL_REDUCE) != 0;
+    const int gw = out_f32 ? 32 : 64;                // columns per 128-byte store group
+    const int ngroups = BN / gw;
+    uint8_t* stg_out = smem + Cfg::OFF_STG + ew * Cfg::STG_PER_WARP;
+    uint8_t* stg_aux = stg_out + GEMM_STG_BYTES;
     int local = 0;
+    long long prof_w = 0, prof_b = 0, prof_ld = 0;
+    (void)prof_w; (void)prof_b; (void)prof_ld;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       int mb, nb;
       tile_coords(tile, num_m, num_n, mb, nb);
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
-      const long long row = (long long)mb * GEMM_BM + q * 32 + lane;
+      const int row0 = mb * GEMM_BM + q * 32;
+      const long long row = (long long)row0 + lane;
       const bool row_ok = row < M;
       const int n0 = nb * BN;
       const int nlim = min(N, n0 + BN);
       EpiSide side;
 #pragma unroll
       for (int i = 0; i < 8; ++i) side.v[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (row_ok && n0 + eg * 32 < nlim) epilogue_prefetch(epi, side, row, n0 + eg * 32, nlim);
+      if (row_ok && n0 + eg * gw < nlim) epilogue_prefetch(epi, side, row, n0 + eg * gw, nlim);
+      VJ_PROF_T0(t3);
       mbar_wait(&tfull[as], aphase);
+      VJ_PROF_ADD(prof_w, t3);
+      VJ_PROF_T0(t4);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
 #pragma unroll 1
-      for (int c = eg; c < NCH; c += 2) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= N) break;                       // warp-uniform
-        uint32_t acc[32];
-        if (BN % 32 != 0 && c == NCH - 1) {         // 16-column tail of the N tile (BN = 176)
-          uint32_t lo[16];
-          tmem_ld16(taddr + c * 32, lo);
+      for (int g = eg; g < ngroups; g += 2) {
+        const int gcol = n0 + g * gw;
+        if (gcol >= N) break;                       // warp-uniform
+        // the previous TMA store of this warp must have finished READING the staging buffers
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+        const int halves = out_f32 ? 1 : 2;
+#pragma unroll 1
+        for (int hh = 0; hh < halves; ++hh) {
+          const int col0 = gcol + hh * 32;
+          if (col0 >= nlim) break;                  // warp-uniform
+          uint32_t acc[32];
+          VJ_PROF_T0(t5);
+          tmem_ld32(taddr + g * gw + hh * 32, acc);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) { acc[i] = lo[i]; acc[16 + i] = 0u; }
-        } else {
-          tmem_ld32(taddr + c * 32, acc);
-          tmem_ld_wait();
+          VJ_PROF_ADD(prof_ld, t5);
+          const EpiSide cur = side;
+          // prefetch the side inputs of the next 32-column block this warp will process
+          {
+            int ncol = col0 + 32;
+            if (hh + 1 >= halves) ncol = gcol + 2 * gw;
+            if (row_ok && ncol < nlim) epilogue_prefetch(epi, side, row, ncol, nlim);
+          }
+          float v[32], pre[32];
+          if (want_aux) {
+            epilogue_math<true>(epi, acc, cur, col0, nlim, v, pre);
+            stage_bf16x32(stg_aux, lane, hh, pre);
+          } else {
+            epilogue_math<false>(epi, acc, cur, col0, nlim, v, pre);
+          }
+          if (out_f32) stage_f32x32(stg_out, lane, v);
+          else stage_bf16x32(stg_out, lane, hh, v);
         }
-        const EpiSide cur = side;
-        if (row_ok && col0 + 64 < nlim && c + 2 < NCH) epilogue_prefetch(epi, side, row, col0 + 64, nlim);
-        if (row_ok) epilogue_chunk<BN>(epi, acc, cur, row, col0, nlim);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (reduce) tma_reduce_add_2d(&tmOut, stg_out, gcol, row0);
+          else tma_store_2d(&tmOut, stg_out, gcol, row0);
+          if (want_aux) tma_store_2d(&tmAux, stg_aux, gcol, row0);
+          bulk_commit();
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
+      VJ_PROF_ADD(prof_b, t4);
     }
+    if (lane == 0) bulk_wait_all0();                // smem must outlive the last bulk stores
+#ifdef VJ_GEMM_PROFILE
+    if (warp == 4 && lane == 0) {
+      atomicAdd(&g_gemm_prof[4], (unsigned long long)prof_w);
+      atomicAdd(&g_gemm_prof[5], (unsigned long long)prof_b);
+      atomicAdd(&g_gemm_prof[7], (unsigned long long)prof_ld);
+    }
+#endif
   }
 
   tc_fence_before();
@@ -398,17 +507,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int BN, bool A_MN, bool B_MN>
-static int launch_gemm(const vj_gemm_args* g, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
-  CUtensorMap tmA, tmB;
+template <int BN, bool A_MN, bool B_MN, bool AUX>
+static int launch_gemm(const vj_gemm_args* g, int flags, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, AUX>;
+  CUtensorMap tmA, tmB, tmOut, tmAux;
   {
     const uint64_t dimsK[2] = {(uint64_t)g->K, (uint64_t)g->M};
     const uint64_t dimsM[2] = {(uint64_t)g->M, (uint64_t)g->K};
     const uint64_t str[1] = {(uint64_t)g->lda * 2};
     const uint32_t boxK[2] = {64, GEMM_BM};
     const uint32_t boxM[2] = {64, GEMM_BK};
-    int r = make_tmap_bf16(&tmA, g->a, 2, A_MN ? dimsM : dimsK, str, A_MN ? boxM : boxK, 128);
+    int r = make_tmap(&tmA, g->a, VJ_BF16, 2, A_MN ? dimsM : dimsK, str, A_MN ? boxM : boxK, 128);
     if (r) return r;
   }
   {
@@ -417,15 +526,30 @@ static int launch_gemm(const vj_gemm_args* g, cudaStream_t stream) {
     const uint64_t str[1] = {(uint64_t)g->ldb * 2};
     const uint32_t boxK[2] = {64, (uint32_t)BN};
     const uint32_t boxN[2] = {64, GEMM_BK};
-    int r = make_tmap_bf16(&tmB, g->b, 2, B_MN ? dimsN : dimsK, str, B_MN ? boxN : boxK, 128);
+    int r = make_tmap(&tmB, g->b, VJ_BF16, 2, B_MN ? dimsN : dimsK, str, B_MN ? boxN : boxK, 128);
     if (r) return r;
   }
+  {
+    const bool f32 = (flags & VJ_EPI_OUT_F32) != 0;
+    const uint64_t dims[2] = {(uint64_t)g->N, (uint64_t)g->M};
+    const uint64_t str[1] = {(uint64_t)g->ldo * (f32 ? 4 : 2)};
+    const uint32_t box[2] = {f32 ? 32u : 64u, 32u};
+    int r = make_tmap(&tmOut, g->out, f32 ? VJ_F32 : VJ_BF16, 2, dims, str, box, 128);
+    if (r) return r;
+    tmAux = tmOut;
+    if (flags & VJ_EPI_AUX_OUT) {
+      const uint64_t stra[1] = {(uint64_t)g->ld_aux * 2};
+      const uint32_t boxa[2] = {64u, 32u};
+      r = make_tmap(&tmAux, g->aux_out, VJ_BF16, 2, dims, stra, boxa, 128);
+      if (r) return r;
+    }
+  }
   GemmEpi e;
-  e.out = g->out; e.bias = g->bias; e.residual = g->residual; e.aux_out = g->aux_out; e.aux_in = g->aux_in;
-  e.ldo = g->ldo; e.ldr = g->ldr; e.ld_aux = g->ld_aux; e.flags = g->flags;
+  e.bias = g->bias; e.residual = g->residual; e.aux_in = g->aux_in;
+  e.ldr = g->ldr; e.ld_aux = g->ld_aux; e.flags = flags;
   e.rope = reinterpret_cast<const __half*>(g->rope_table); e.rope_hd = g->rope_hd; e.rope_D = g->rope_D;
 
-  auto kern = gemm_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_kernel<BN, A_MN, B_MN, AUX>;
   static bool attr_set = false;
   if (!attr_set) {
     VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -435,25 +559,23 @@ static int launch_gemm(const vj_gemm_args* g, cudaStream_t stream) {
   const int num_n = (int)((g->N + BN - 1) / BN);
   const int tiles = num_m * num_n;
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, e, (int)g->M, (int)g->N, (int)g->K);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmAux, e, (int)g->M, (int)g->N, (int)g->K);
   VJ_LAUNCH_CHECK();
   return 0;
 }
 
 // Pick the N tile.  Measured on B200 (profiles/r01_*): per-FLOP speed of the mainloop is ~1.0 at BN=256,
-// ~0.85 at 176/192 and ~0.7 at 128 (smaller tiles re-read A more often and give the single MMA-issuing
-// thread less time per k-block), so a wide tile wins unless it leaves many dead columns.
-static int pick_bn(long long N, bool b_mn, long long M) {
-  const int cands_k[] = {256, 192, 176, 128};
-  const int cands_mn[] = {256, 192, 192, 128};
-  const double speed[] = {1.0, 0.86, 0.85, 0.70};
-  const int* c = b_mn ? cands_mn : cands_k;
+// ~0.86 at 192 and ~0.7 at 128 (smaller tiles re-read A more often and give the single MMA-issuing thread
+// less time per k-block), so a wide tile wins unless it leaves many dead columns or a ragged last wave.
+static int pick_bn(long long N, long long M) {
+  const int cands[] = {256, 192, 128};
+  const double speed[] = {1.0, 0.86, 0.70};
   int best = 128;
   double best_cost = 1e30;
   const long long num_m = (M + 127) / 128;
   const long long sms = sm_count();
-  for (int i = 0; i < 4; ++i) {
-    const int bn = c[i];
+  for (int i = 0; i < 3; ++i) {
+    const int bn = cands[i];
     const long long tiles_n = (N + bn - 1) / bn;
     const long long tiles = tiles_n * num_m;
     const long long waves = (tiles + sms - 1) / sms;              // wave quantisation of the persistent grid
@@ -476,25 +598,39 @@ extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
   VJ_CHECK(g->lda % 8 == 0 && g->ldb % 8 == 0, "vj_gemm: lda/ldb must be multiples of 8 elements (TMA 16-B pitch)");
   VJ_CHECK(g->ldo % 8 == 0, "vj_gemm: ldo must be a multiple of 8");
   VJ_CHECK(g->a && g->b && g->out, "vj_gemm: null operand");
-  if (g->flags & VJ_EPI_BIAS) VJ_CHECK(g->bias != nullptr, "vj_gemm: bias flag without pointer");
-  if (g->flags & VJ_EPI_RESIDUAL) VJ_CHECK(g->residual != nullptr && g->ldr % 8 == 0, "vj_gemm: bad residual");
-  if (g->flags & VJ_EPI_AUX_OUT) VJ_CHECK(g->aux_out != nullptr && g->ld_aux % 8 == 0, "vj_gemm: bad aux_out");
-  if (g->flags & VJ_EPI_DGELU) VJ_CHECK(g->aux_in != nullptr && g->ld_aux % 8 == 0, "vj_gemm: bad aux_in");
-  VJ_CHECK(!((g->flags & VJ_EPI_DGELU) && (g->flags & VJ_EPI_RES_F32)), "vj_gemm: DGELU with an fp32 residual is not supported");
-  if (g->flags & VJ_EPI_ROPE) {
-    VJ_CHECK(!(g->flags & (VJ_EPI_RESIDUAL | VJ_EPI_DGELU | VJ_EPI_GELU)), "vj_gemm: ROPE combines with BIAS only");
+  int flags = g->flags;
+  if (flags & VJ_EPI_BIAS) VJ_CHECK(g->bias != nullptr, "vj_gemm: bias flag without pointer");
+  if (flags & VJ_EPI_RESIDUAL) VJ_CHECK(g->residual != nullptr && g->ldr % 8 == 0, "vj_gemm: bad residual");
+  if (flags & VJ_EPI_AUX_OUT) VJ_CHECK(g->aux_out != nullptr && g->ld_aux % 8 == 0, "vj_gemm: bad aux_out");
+  if (flags & VJ_EPI_DGELU) VJ_CHECK(g->aux_in != nullptr && g->ld_aux % 8 == 0, "vj_gemm: bad aux_in");
+  if (flags & VJ_EPI_AUX_OUT) VJ_CHECK(!(flags & VJ_EPI_OUT_F32), "vj_gemm: AUX_OUT needs a bf16 output");
+  VJ_CHECK(!((flags & VJ_EPI_DGELU) && (flags & VJ_EPI_RES_F32)), "vj_gemm: DGELU with an fp32 residual is not supported");
+  if (flags & VJ_EPI_ROPE) {
+    VJ_CHECK(!(flags & (VJ_EPI_RESIDUAL | VJ_EPI_DGELU | VJ_EPI_GELU)), "vj_gemm: ROPE combines with BIAS only");
     VJ_CHECK(g->rope_table && (g->rope_hd == 32 || g->rope_hd == 64) && g->rope_D > 0 && g->rope_D % g->rope_hd == 0 &&
                  g->N == 3 * (int64_t)g->rope_D && g->rope_D % 16 == 0,
              "vj_gemm: bad ROPE arguments (hd=%d D=%d N=%lld)", g->rope_hd, g->rope_D, (long long)g->N);
   }
+  // fp32 "out += acc": residual aliases out with the same pitch -> TMA reduce-add, no read in the epilogue
+  if ((flags & VJ_EPI_RESIDUAL) && g->residual == g->out) {
+    VJ_CHECK((flags & VJ_EPI_RES_F32) && (flags & VJ_EPI_OUT_F32) && g->ldr == g->ldo &&
+                 !(flags & (VJ_EPI_GELU | VJ_EPI_DGELU | VJ_EPI_ROUND_BF16 | VJ_EPI_AUX_OUT)),
+             "vj_gemm: in-place residual is only supported as a plain fp32 accumulate");
+    flags = (flags & ~(VJ_EPI_RESIDUAL | VJ_EPI_RES_F32)) | EPI_INTERNAL_REDUCE;
+  }
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
   VJ_CHECK(!(amn && !bmn), "vj_gemm: (A MN-major, B K-major) is not instantiated");
-  const int bn = pick_bn(g->N, bmn, g->M);
+  const int bn = pick_bn(g->N, g->M);
+  if (flags & VJ_EPI_AUX_OUT) {
+    VJ_CHECK(!amn && !bmn, "vj_gemm: AUX_OUT is only instantiated for K-major operands");
+    if (bn == 256) return launch_gemm<256, false, false, true>(g, flags, stream);
+    if (bn == 192) return launch_gemm<192, false, false, true>(g, flags, stream);
+    return launch_gemm<128, false, false, true>(g, flags, stream);
+  }
 #define VJ_GEMM_CASE(BN_, A_, B_) \
-  if (bn == BN_ && amn == A_ && bmn == B_) return launch_gemm<BN_, A_, B_>(g, stream);
+  if (bn == BN_ && amn == A_ && bmn == B_) return launch_gemm<BN_, A_, B_, false>(g, flags, stream);
   VJ_GEMM_CASE(256, false, false)
   VJ_GEMM_CASE(192, false, false)
-  VJ_GEMM_CASE(176, false, false)
   VJ_GEMM_CASE(128, false, false)
   VJ_GEMM_CASE(256, false, true)
   VJ_GEMM_CASE(192, false, true)
@@ -506,3 +642,15 @@ extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
   set_error("vj_gemm: no kernel for BN=%d a_mn=%d b_mn=%d", bn, (int)amn, (int)bmn);
   return -1;
 }
+
+#ifdef VJ_GEMM_PROFILE
+extern "C" int vj_gemm_prof_read(unsigned long long* out8, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out8, vj::g_gemm_prof, 8 * sizeof(unsigned long long));
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(vj::g_gemm_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif

@@ -38,9 +38,13 @@ int sm_count();
     }                                                                                      \
   } while (0)
 
-// bf16 tiled tensor map, up to 3 dims.  dims[0] is the contiguous dimension; strides_bytes[i] is the
-// byte stride of dims[i+1].  swizzle_bytes in {32, 64, 128} must equal box[0]*2.
-int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+// Tiled tensor map (dtype VJ_BF16 / VJ_F32), up to 3 dims.  dims[0] is the contiguous dimension;
+// strides_bytes[i] is the byte stride of dims[i+1].  swizzle_bytes in {32, 64, 128} must equal box[0]*elt.
+int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+inline int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                          const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  return make_tmap(out, base, 0 /*VJ_BF16*/, rank, dims, strides_bytes, box, swizzle_bytes);
+}
 
 }  // namespace vj

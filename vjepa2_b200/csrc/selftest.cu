@@ -96,7 +96,7 @@ static void test_gemm(const char* name, int M, int N, int K, int a_mn, int b_mn,
   if (rf32) fillf((float*)res, (long long)M * N, 5, 1.0f); else fill((bf16*)res, (long long)M * N, 5, 1.0f);
   CK(cudaMemset(out, 0xFF, (size_t)M * N * (of32 ? 4 : 2)));
   // in-place accumulate variant: residual aliases out
-  const bool alias = (flags & VJ_EPI_RESIDUAL) && of32 && rf32;
+  const bool alias = (flags & VJ_EPI_RESIDUAL) && of32 && rf32 && !(flags & (VJ_EPI_ROUND_BF16 | VJ_EPI_GELU | VJ_EPI_DGELU));
   if (alias) CK(cudaMemcpy(out, res, (size_t)M * N * 4, cudaMemcpyDeviceToDevice));
   vj_gemm_args g;
   memset(&g, 0, sizeof(g));
@@ -315,24 +315,35 @@ static void test_attn(int B, int S, int H, int hd, bool bwd) {
   cudaFree(qkv); cudaFree(out); cudaFree(lse); cudaFree(oref); cudaFree(lref);
 }
 
+#ifdef VJ_GEMM_PROFILE
+extern "C" int vj_gemm_prof_read(unsigned long long* out8, int reset);
+#endif
+
 static void bench_gemm(const char* name, long long M, long long N, long long K, int a_mn, int b_mn, int flags) {
   bf16* A = dalloc<bf16>((size_t)M * K);
   bf16* B = dalloc<bf16>((size_t)N * K);
   const bool of32 = flags & VJ_EPI_OUT_F32;
   void* out = dalloc<char>((size_t)M * N * (of32 ? 4 : 2));
+  void* side = dalloc<char>((size_t)M * N * 4);   // residual / aux operand (separate buffer unless accumulating)
+  CK(cudaMemset(side, 0, (size_t)M * N * 4));
   float* bias = dalloc<float>(N);
   fill(A, M * K, 1, 1.0f); fill(B, N * K, 2, 0.05f); fillf(bias, N, 3, 1.0f);
   CK(cudaMemset(out, 0, (size_t)M * N * (of32 ? 4 : 2)));
   vj_gemm_args g;
   memset(&g, 0, sizeof(g));
   g.a = A; g.b = B; g.out = out; g.M = M; g.N = N; g.K = K; g.lda = a_mn ? M : K; g.ldb = b_mn ? N : K; g.ldo = N;
-  g.a_mn_major = a_mn; g.b_mn_major = b_mn; g.flags = flags; g.bias = bias; g.residual = out; g.ldr = N;
-  g.aux_out = out; g.aux_in = out; g.ld_aux = N;
+  const bool accumulate = (flags & VJ_EPI_RESIDUAL) && of32 && (flags & VJ_EPI_RES_F32);
+  g.a_mn_major = a_mn; g.b_mn_major = b_mn; g.flags = flags; g.bias = bias; g.residual = accumulate ? out : side; g.ldr = N;
+  g.aux_out = side; g.aux_in = side; g.ld_aux = N;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) VJ(vj_gemm(&g, 0));
   CK(cudaDeviceSynchronize());
   const int iters = 10;
+#ifdef VJ_GEMM_PROFILE
+  unsigned long long pr[8];
+  vj_gemm_prof_read(pr, 1);
+#endif
   cudaEventRecord(e0);
   for (int i = 0; i < iters; ++i) VJ(vj_gemm(&g, 0));
   cudaEventRecord(e1);
@@ -342,7 +353,14 @@ static void bench_gemm(const char* name, long long M, long long N, long long K, 
   ms /= iters;
   printf("[bench gemm] %-28s M=%lld N=%lld K=%lld  %.3f ms  %.1f TFLOP/s\n", name, M, N, K, ms,
          2.0 * M * N * K / ms * 1e-9);
-  cudaFree(A); cudaFree(B); cudaFree(out); cudaFree(bias);
+#ifdef VJ_GEMM_PROFILE
+  vj_gemm_prof_read(pr, 1);
+  const double n = (double)pr[6];
+  printf("      per-CTA cycles: mma_total %.0f | mma wait TMA %.1f%% | mma wait epilogue %.1f%% | producer wait slot %.1f%%"
+         " | epilogue wait acc %.0f busy %.0f (tmem ld+wait %.0f)\n",
+         pr[0] / n, 100.0 * pr[1] / pr[0], 100.0 * pr[2] / pr[0], 100.0 * pr[3] / pr[0], pr[4] / n, pr[5] / n, pr[7] / n);
+#endif
+  cudaFree(A); cudaFree(B); cudaFree(out); cudaFree(bias); cudaFree(side);
 }
 
 static void bench_attn(int B, int S, int H, int hd, bool bwd) {
