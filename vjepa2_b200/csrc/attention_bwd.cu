@@ -1,17 +1,19 @@
 // Flash-attention backward on tcgen05 for sm_100a.
 //
-// One CTA = one (batch, head, 128-key tile); it loops over 128-query tiles.  192 threads:
-//   warps 0-3  compute: thread r owns key row r (TMEM lane r) of S^T / dP^T, and query row r of dQ
-//   warp  4    TMA producer (K,V once; Q_i / dO_i double-buffered) + TMEM allocate/free
-//   warp  5    MMA issuer, five GEMMs per query tile:
+// One CTA = one (batch, head, 128-key tile); it loops over 128-query tiles.  320 threads:
+//   warps 0-7  compute: thread (r = tid & 127, half = tid >> 7) owns key row r (TMEM lane r) and 64 of the 128
+//              query columns of S^T / dP^T, and half of the columns of query row r of dQ
+//   warp  8    TMA producer (K,V once; Q_i / dO_i double-buffered) + TMEM allocate/free
+//   warp  9    MMA issuer, five GEMMs per query tile:
 //                S^T  = K Q_i^T          (128 keys x 128 q, K=d)        -> TMEM [0,128)
 //                dP^T = V dO_i^T         (128 keys x 128 q, K=d)        -> TMEM [128,256)
 //                dV  += P^T dO_i         (128 keys x d,   K=128 q)      -> TMEM [256,256+d)
 //                dK  += dS^T Q_i         (128 keys x d,   K=128 q)      -> TMEM [256+d,256+2d)
 //                dQ_i = dS K             (128 q x d,      K=128 keys)   -> TMEM [256+2d,256+3d)
-//   P^T and dS^T are written to smem as bf16 K-major tiles; the same dS^T buffer is consumed as an
-//   MN-major A operand for dQ (no transpose).  dQ partial tiles are accumulated across key tiles with
-//   fp32 reductions into a scratch buffer and converted to bf16 by a small follow-up kernel.
+//   P^T and dS^T are written to smem as bf16 K-major tiles; the same dS^T buffer is consumed as an MN-major A
+//   operand for dQ (no transpose).  dQ partial tiles are staged as fp32 in smem and accumulated across key tiles
+//   by the TMA unit (cp.reduce.async.bulk.tensor .add) into an fp32 scratch buffer -- no per-element atomics --
+//   which a small follow-up kernel converts to bf16 (applying the adjoint RoPE map on the way).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -32,7 +34,8 @@ struct AttnBwdCfg {
   static constexpr int OFF_DO = OFF_Q + 2 * TILE_BYTES; // 2 stages
   static constexpr int OFF_PT = OFF_DO + 2 * TILE_BYTES;
   static constexpr int OFF_DS = OFF_PT + PT_BYTES;
-  static constexpr int OFF_LSE = OFF_DS + PT_BYTES;    // 128 floats lse + 128 floats delta
+  static constexpr int OFF_DQ = OFF_DS + PT_BYTES;     // fp32 dQ staging: 128 rows x HD x 4 B
+  static constexpr int OFF_LSE = OFF_DQ + BT * HD * 4; // 128 floats lse + 128 floats delta
   static constexpr int OFF_BAR = OFF_LSE + 1024;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int COL_ST = 0, COL_DPT = 128, COL_DV = 256, COL_DK = 256 + HD, COL_DQ = 256 + 2 * HD;
@@ -61,6 +64,10 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const bf16* __restrict_
   }
   delta[(b * H + h) * S + q] = acc;
 }
+
+__device__ __forceinline__ void bulk_commit_bwd() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0_bwd() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0_bwd() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // adjoint of the RoPE pair map on 8 consecutive head dims (cos/sin: 8 fp16 each, vj_rope_table layout)
 __device__ __forceinline__ void rope_adjoint8(float* g, const uint4 c, const uint4 s) {
@@ -98,13 +105,22 @@ __global__ void __launch_bounds__(256) attn_dq_convert_kernel(const float* __res
   *reinterpret_cast<uint4*>(dqkv + row * 3 * (long long)D + c) = u;
 }
 
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(m),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
+// 320 threads: warps 0-7 compute (thread: key row r = tid & 127 == TMEM lane, half = tid >> 7 -> 64 of the 128 query
+// columns of S^T / dP^T, and half of the columns of the dQ / dK / dV rows), warp 8 TMA producer + TMEM, warp 9 MMA.
 template <int HD>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                const float* __restrict__ lse, const float* __restrict__ delta, float* __restrict__ dq_acc,
-                bf16* __restrict__ dqkv, const __half* __restrict__ rope, int S, int H, int D, float scale,
-                float scale_log2) {
+                const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse,
+                const float* __restrict__ delta, bf16* __restrict__ dqkv, const __half* __restrict__ rope, int S, int H,
+                int D, float scale, float scale_log2) {
   using Cfg = AttnBwdCfg<HD>;
+  constexpr int HO = HD / 2;                               // output columns per compute thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem + Cfg::OFF_K;
@@ -113,6 +129,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint8_t* sDO = smem + Cfg::OFF_DO;
   uint8_t* sPT = smem + Cfg::OFF_PT;
   uint8_t* sDS = smem + Cfg::OFF_DS;
+  uint8_t* sDQ = smem + Cfg::OFF_DQ;                        // fp32 dQ tile staging: [HD/32 atoms][128 rows][128 B]
   float* s_lse = reinterpret_cast<float*>(smem + Cfg::OFF_LSE);
   float* s_delta = s_lse + 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -120,11 +137,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   uint64_t* qdo_full = bars + 1;     // 2
   uint64_t* qdo_empty = bars + 3;    // 2
   uint64_t* sdp_full = bars + 5;     // 1
-  uint64_t* pds_full = bars + 6;     // 1 (128 arrivals)
+  uint64_t* pds_full = bars + 6;     // 1 (256 arrivals)
   uint64_t* dq_full = bars + 7;      // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
   const int k0 = blockIdx.x * Cfg::BT;
   const int h = blockIdx.y, b = blockIdx.z;
   const int n_q = (S + Cfg::BT - 1) / Cfg::BT;
@@ -133,11 +150,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, 256);
     mbar_init(dq_full, 1);
     mbar_fence_init();
   }
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -146,9 +163,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       tma_prefetch_desc(&tmQKV);
       tma_prefetch_desc(&tmDO);
       mbar_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
@@ -162,7 +179,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         tma_load_3d(sDO + st * Cfg::TILE_BYTES, &tmDO, &qdo_full[st], h * HD, i * Cfg::BT, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ---------------------------------------------------------------- MMA issuer
     constexpr uint32_t id_s = make_idesc(128, 128, false, false);
     constexpr uint32_t id_dv = make_idesc(128, HD, false, true);
@@ -180,7 +197,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       tc_fence_after();
       const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
       const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t qd_k = desc_kmajor<Cfg::SWB>(q_addr);
         const uint64_t dod_k = desc_kmajor<Cfg::SWB>(do_addr);
 #pragma unroll
@@ -194,7 +211,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       __syncwarp();
       mbar_wait(pds_full, i & 1);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint64_t qd_mn = desc_mnmajor<Cfg::SWB>(q_addr, Cfg::TILE_BYTES);
         const uint64_t dod_mn = desc_mnmajor<Cfg::SWB>(do_addr, Cfg::TILE_BYTES);
 #pragma unroll
@@ -216,20 +233,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     }
   } else {
     // ---------------------------------------------------------------- compute warps
-    const int r = threadIdx.x;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const int r = threadIdx.x & 127;
+    const int half = threadIdx.x >> 7;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const bool key_ok = (k0 + r) < S;
     const float* lse_bh = lse + ((long long)b * H + h) * S;
     const float* delta_bh = delta + ((long long)b * H + h) * S;
     for (int i = 0; i < n_q; ++i) {
-      const int q = i * Cfg::BT + r;
-      s_lse[r] = q < S ? lse_bh[q] : INFINITY;
-      s_delta[r] = q < S ? delta_bh[q] : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (half == 0) {
+        const int q = i * Cfg::BT + r;
+        s_lse[r] = q < S ? lse_bh[q] : INFINITY;
+        s_delta[r] = q < S ? delta_bh[q] : 0.f;
+      } else if (r == 0 && i > 0) {
+        bulk_wait_read0_bwd();                            // dQ staging of iteration i-1 has been read by the TMA
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int cc2 = 0; cc2 < 2; ++cc2) {
+        const int c = half * 2 + cc2;                      // 32-column chunk of the 128 query columns
         uint32_t sv[32], dv[32];
         tmem_ld32(lane_addr + Cfg::COL_ST + c * 32, sv);
         tmem_ld32(lane_addr + Cfg::COL_DPT + c * 32, dv);
@@ -237,8 +260,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
         uint32_t pp[16], dd[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
-          float p0 = exp2f(__uint_as_float(sv[j]) * scale_log2 - s_lse[c * 32 + j]);
-          float p1 = exp2f(__uint_as_float(sv[j + 1]) * scale_log2 - s_lse[c * 32 + j + 1]);
+          float p0 = ex2_approx(fmaf(__uint_as_float(sv[j]), scale_log2, -s_lse[c * 32 + j]));
+          float p1 = ex2_approx(fmaf(__uint_as_float(sv[j + 1]), scale_log2, -s_lse[c * 32 + j + 1]));
           if (!key_ok) { p0 = 0.f; p1 = 0.f; }
           const float d0 = p0 * (__uint_as_float(dv[j]) - s_delta[c * 32 + j]);
           const float d1 = p1 * (__uint_as_float(dv[j + 1]) - s_delta[c * 32 + j + 1]);
@@ -257,59 +280,82 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);
-      // dQ_i tile: lane r == query row r
+      // dQ_i tile: lane r == query row r; stage scale*dQ as fp32 and let the TMA reduce-add it into dq_acc
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
-      float* dq_row = dq_acc + ((long long)b * S + q) * D + h * HD;
-#pragma unroll
-      for (int c0 = 0; c0 < HD; c0 += 32) {
+      if constexpr (HO == 32) {
         uint32_t o[32];
-        tmem_ld32(lane_addr + Cfg::COL_DQ + c0, o);
+        tmem_ld32(lane_addr + Cfg::COL_DQ + half * HO, o);
         tmem_ld_wait();
-        if (q < S) {
+        uint8_t* rowp = sDQ + half * 16384 + r * 128;     // atom = half
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dq_row + c0 + j, __uint_as_float(o[j]) * scale);
-        }
+        for (int u = 0; u < 8; ++u)
+          *reinterpret_cast<float4*>(rowp + ((u ^ (r & 7)) << 4)) =
+              make_float4(__uint_as_float(o[u * 4]) * scale, __uint_as_float(o[u * 4 + 1]) * scale,
+                          __uint_as_float(o[u * 4 + 2]) * scale, __uint_as_float(o[u * 4 + 3]) * scale);
+      } else {
+        uint32_t o[16];
+        tmem_ld16(lane_addr + Cfg::COL_DQ + half * HO, o);
+        tmem_ld_wait();
+        uint8_t* rowp = sDQ + r * 128;                    // single atom, this half fills chunks 4*half..
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          *reinterpret_cast<float4*>(rowp + (((half * 4 + u) ^ (r & 7)) << 4)) =
+              make_float4(__uint_as_float(o[u * 4]) * scale, __uint_as_float(o[u * 4 + 1]) * scale,
+                          __uint_as_float(o[u * 4 + 2]) * scale, __uint_as_float(o[u * 4 + 3]) * scale);
       }
       tc_fence_before();
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (threadIdx.x == 128) {                            // same thread that waits on the bulk group above
+#pragma unroll
+        for (int a = 0; a < HD / 32; ++a)
+          tma_reduce_add_3d(&tmDQ, sDQ + a * 16384, h * HD + a * 32, i * Cfg::BT, b);
+        bulk_commit_bwd();
+      }
     }
+    if (threadIdx.x == 128) bulk_wait_all0_bwd();
     // dK / dV epilogue (all MMAs retired: dq_full of the last iteration was committed after them)
     const int key = k0 + r;
-    bf16* dk_row = dqkv + ((long long)b * S + key) * 3 * D + D + h * HD;
+    bf16* dk_row = dqkv + ((long long)b * S + key) * 3 * D + D + h * HD + half * HO;
     bf16* dv_row = dk_row + D;
+    constexpr int NV = HO / 8;
+    uint32_t a[HO], c[HO];
+    if constexpr (HO == 32) {
+      tmem_ld32(lane_addr + Cfg::COL_DK + half * HO, a);
+      tmem_ld32(lane_addr + Cfg::COL_DV + half * HO, c);
+    } else {
+      tmem_ld16(lane_addr + Cfg::COL_DK + half * HO, a);
+      tmem_ld16(lane_addr + Cfg::COL_DV + half * HO, c);
+    }
+    tmem_ld_wait();
+    if (key_ok) {
+      const __half* tr = rope ? rope + ((long long)b * S + key) * 2 * HD + half * HO : nullptr;
 #pragma unroll
-    for (int c0 = 0; c0 < HD; c0 += 32) {
-      uint32_t a[32], c[32];
-      tmem_ld32(lane_addr + Cfg::COL_DK + c0, a);
-      tmem_ld32(lane_addr + Cfg::COL_DV + c0, c);
-      tmem_ld_wait();
-      if (key_ok) {
-        const __half* tr = rope ? rope + ((long long)b * S + key) * 2 * HD + c0 : nullptr;
+      for (int jj = 0; jj < NV; ++jj) {
+        const int j = jj * 8;
+        uint4 u, w;
+        float gk[8];
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 u, w;
-          float gk[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) gk[e] = __uint_as_float(a[j + e]) * scale;
-          if (rope) rope_adjoint8(gk, *reinterpret_cast<const uint4*>(tr + j), *reinterpret_cast<const uint4*>(tr + HD + j));
-          u.x = pack_bf16x2(gk[0], gk[1]);
-          u.y = pack_bf16x2(gk[2], gk[3]);
-          u.z = pack_bf16x2(gk[4], gk[5]);
-          u.w = pack_bf16x2(gk[6], gk[7]);
-          w.x = pack_bf16x2(__uint_as_float(c[j]), __uint_as_float(c[j + 1]));
-          w.y = pack_bf16x2(__uint_as_float(c[j + 2]), __uint_as_float(c[j + 3]));
-          w.z = pack_bf16x2(__uint_as_float(c[j + 4]), __uint_as_float(c[j + 5]));
-          w.w = pack_bf16x2(__uint_as_float(c[j + 6]), __uint_as_float(c[j + 7]));
-          *reinterpret_cast<uint4*>(dk_row + c0 + j) = u;
-          *reinterpret_cast<uint4*>(dv_row + c0 + j) = w;
-        }
+        for (int e = 0; e < 8; ++e) gk[e] = __uint_as_float(a[j + e]) * scale;
+        if (rope) rope_adjoint8(gk, *reinterpret_cast<const uint4*>(tr + j), *reinterpret_cast<const uint4*>(tr + HD + j));
+        u.x = pack_bf16x2(gk[0], gk[1]);
+        u.y = pack_bf16x2(gk[2], gk[3]);
+        u.z = pack_bf16x2(gk[4], gk[5]);
+        u.w = pack_bf16x2(gk[6], gk[7]);
+        w.x = pack_bf16x2(__uint_as_float(c[j]), __uint_as_float(c[j + 1]));
+        w.y = pack_bf16x2(__uint_as_float(c[j + 2]), __uint_as_float(c[j + 3]));
+        w.z = pack_bf16x2(__uint_as_float(c[j + 4]), __uint_as_float(c[j + 5]));
+        w.w = pack_bf16x2(__uint_as_float(c[j + 6]), __uint_as_float(c[j + 7]));
+        *reinterpret_cast<uint4*>(dk_row + j) = u;
+        *reinterpret_cast<uint4*>(dv_row + j) = w;
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == 8) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 template <int HD>
@@ -341,6 +387,14 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
     int r = make_tmap_bf16(&tmDO, dout, 3, dims, strides, box, Cfg::SWB);
     if (r) return r;
   }
+  CUtensorMap tmDQ;
+  {
+    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)S, (uint64_t)B};
+    const uint64_t strides[2] = {(uint64_t)D * 4, (uint64_t)S * D * 4};
+    const uint32_t box[3] = {32, Cfg::BT, 1};
+    int r = make_tmap(&tmDQ, dq_acc, VJ_F32, 3, dims, strides, box, 128);
+    if (r) return r;
+  }
   auto kern = attn_bwd_kernel<HD>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -349,7 +403,7 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
   }
   dim3 grid((S + Cfg::BT - 1) / Cfg::BT, H, B);
   const float scale = 1.0f / sqrtf((float)HD);
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmQKV, tmDO, lse, delta, dq_acc, reinterpret_cast<bf16*>(dqkv),
+  kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, reinterpret_cast<bf16*>(dqkv),
                                               reinterpret_cast<const __half*>(rope), S, H, D, scale,
                                               scale * 1.4426950408889634f);
   VJ_LAUNCH_CHECK();

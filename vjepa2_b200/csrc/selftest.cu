@@ -363,6 +363,10 @@ static void bench_gemm(const char* name, long long M, long long N, long long K, 
   cudaFree(A); cudaFree(B); cudaFree(out); cudaFree(bias); cudaFree(side);
 }
 
+#ifdef VJ_ATTN_PROFILE
+extern "C" int vj_attn_prof_read(unsigned long long* out16, int reset);
+#endif
+
 static void bench_attn(int B, int S, int H, int hd, bool bwd) {
   const int D = H * hd;
   const size_t nq = (size_t)B * S * 3 * D, no = (size_t)B * S * D, nl = (size_t)B * H * S;
@@ -378,6 +382,10 @@ static void bench_attn(int B, int S, int H, int hd, bool bwd) {
   for (int i = 0; i < 2; ++i) VJ(vj_attn_fwd(qkv, out, lse, B, S, H, hd, 0));
   CK(cudaDeviceSynchronize());
   const int iters = 5;
+#ifdef VJ_ATTN_PROFILE
+  unsigned long long ap[16];
+  vj_attn_prof_read(ap, 1);
+#endif
   cudaEventRecord(e0);
   for (int i = 0; i < iters; ++i) VJ(vj_attn_fwd(qkv, out, lse, B, S, H, hd, 0));
   cudaEventRecord(e1);
@@ -387,6 +395,16 @@ static void bench_attn(int B, int S, int H, int hd, bool bwd) {
   ms /= iters;
   const double fl = 4.0 * B * H * (double)S * S * hd;
   printf("[bench attn fwd] B=%d S=%d H=%d hd=%d  %.3f ms  %.1f TFLOP/s\n", B, S, H, hd, ms, fl / ms * 1e-9);
+#ifdef VJ_ATTN_PROFILE
+  vj_attn_prof_read(ap, 1);
+  {
+    const double n = (double)ap[9], tiles = (double)((S + 63) / 64);
+    printf("      per CTA per KV tile (cycles): softmax total %.0f = wait S %.0f + tmem ld %.0f + max/exp/pack %.0f + wait PV %.0f"
+           " + O rescale %.0f + P store/arrive %.0f | MMA warp: total %.0f wait P %.0f wait KV %.0f\n",
+           ap[0] / n / tiles, ap[1] / n / tiles, ap[2] / n / tiles, ap[3] / n / tiles, ap[4] / n / tiles, ap[5] / n / tiles,
+           ap[6] / n / tiles, ap[10] / n / tiles, ap[7] / n / tiles, ap[8] / n / tiles);
+  }
+#endif
   if (bwd) {
     for (int i = 0; i < 2; ++i) VJ(vj_attn_bwd(qkv, out, dout, lse, dqkv, scratch, nullptr, B, S, H, hd, 0));
     CK(cudaDeviceSynchronize());
