@@ -163,6 +163,9 @@ def main():
     ap.add_argument("--batch", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-ops", action="store_true",
+                    help="after the timed region, run one extra step with CUDA events around every C-ABI call and "
+                         "print a per-op time table to stderr")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -340,6 +343,51 @@ def main():
                     traffic=None, launches=len(recs), gemm_ms_per_step=g_ms, step_ms_instrumented=evs.elapsed_time(eve),
                     gemm_share_of_step=g_ms / evs.elapsed_time(eve))
     barrier()
+
+    if args.profile_ops and rank == 0 and world == 1:
+        import collections
+        agg = collections.defaultdict(list)
+        names = ["gemm", "layernorm_fwd", "layernorm_bwd", "attn_fwd", "attn_bwd", "gather_rows", "im2col_tubelets",
+                 "colsum", "l1_loss", "pred_indices", "rope_table", "cast_f32_bf16", "adamw_step", "ema_update",
+                 "grad_check", "scaler_update"]
+        saved = {n: getattr(ops, n) for n in names}
+
+        def wrap(name, fn):
+            def w(*a, **kw):
+                s0, e0 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                r = fn(*a, **kw)
+                e0.record()
+                key = name
+                if name == "gemm":
+                    M, N, K = a[3], a[4], a[5]
+                    key = f"gemm {'wgrad' if kw.get('a_mn') else ('dgrad' if kw.get('b_mn') else 'fwd')} " \
+                          f"N={N} K={K}" + (" gelu" if kw.get("gelu") else "") + (" dgelu" if kw.get("dgelu_aux") is not None else "") + \
+                          (" rope" if kw.get("rope") is not None else "") + (" +res" if kw.get("residual") is not None else "")
+                    agg[key].append((s0, e0, 2.0 * M * N * K))
+                else:
+                    agg[key].append((s0, e0, 0.0))
+                return r
+            return w
+
+        for n in names:
+            setattr(ops, n, wrap(n, saved[n]))
+        evs, eve = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evs.record()
+        run_step(total - 1, clips_dev)
+        eve.record()
+        torch.cuda.synchronize()
+        for n in names:
+            setattr(ops, n, saved[n])
+        rows = []
+        for k, v in agg.items():
+            ms = sum(s0.elapsed_time(e0) for s0, e0, _ in v)
+            fl = sum(f for _, _, f in v)
+            rows.append((ms, k, len(v), fl))
+        tot = sum(r[0] for r in rows)
+        log(f"per-op profile of one step: {evs.elapsed_time(eve):.1f} ms wall, {tot:.1f} ms inside ops")
+        for ms, k, n, fl in sorted(rows, reverse=True):
+            log(f"  {ms:8.2f} ms {100 * ms / tot:5.1f}%  n={n:4d}  {k}" + (f"  {fl / ms / 1e9:7.1f} TFLOP/s" if fl else ""))
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same step on the host cores
     cpu = None

@@ -46,113 +46,195 @@ __device__ __forceinline__ void rope_load8(const __half* p, float (&v)[8]) {
   }
 }
 
-// ---------------------------------------------------------------- LayerNorm forward
+// ---------------------------------------------------------------- LayerNorm forward / backward
+// One warp per row, rows taken in a grid-stride loop by a persistent grid.  The row stays in registers in its
+// STORAGE format (bf16 rows: NV uint4 per lane) and is converted on the fly in each pass, which keeps the
+// kernels at ~40-60 registers -> high occupancy, many 128-bit loads in flight per SM.
 constexpr int LN_MAXV = 8;  // vectors of 8 per lane -> D <= 2048
 
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const void* __restrict__ x, int x_dtype,
-                                                     const float* __restrict__ gamma,
+template <bool F32> struct RawVec;
+template <> struct RawVec<false> {                       // 8 bf16
+  uint4 u;
+  __device__ __forceinline__ void load(const void* base, long long off) {
+    u = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + off);
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+    v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+  }
+};
+template <> struct RawVec<true> {                        // 8 fp32
+  float4 a, b;
+  __device__ __forceinline__ void load(const void* base, long long off) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
+    a = p[0]; b = p[1];
+  }
+  __device__ __forceinline__ void get(float (&v)[8]) const {
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+};
+template <bool F32>
+__device__ __forceinline__ void store8t(void* base, long long off, const float (&v)[8]) {
+  if (F32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
+    p[0] = make_float4(v[0], v[1], v[2], v[3]);
+    p[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + off) = u;
+  }
+}
+
+template <bool XF32, bool YF32, int NV>
+__global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, void* __restrict__ y,
-                                                     int y_dtype, float* __restrict__ mean_out,
-                                                     float* __restrict__ rstd_out, long long rows, int D, float eps) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + warp;
-  if (row >= rows) return;
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                     long long rows, int D, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * 8;
   const int nvec = D >> 3;
-  float v[LN_MAXV][8];
-  float s = 0.f;
+  const float inv_d = 1.0f / D;
+  for (long long row = wid; row < rows; row += nw) {
+    RawVec<XF32> raw[NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      load8(x, x_dtype, row * D + vi * 8, v[i]);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += v[i][j];
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) raw[i].load(x, row * D + vi * 8);
     }
-  }
-  const float mean = warp_sum(s) / D;
-  float ss = 0.f;
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; ss += d * d; }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(ss) / D + eps);
-  if (lane == 0) {
-    if (mean_out) mean_out[row] = mean;
-    if (rstd_out) rstd_out[row] = rstd;
-  }
-#pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      float o[8];
-      if (gamma) {
-        float g[8], b[8];
-        load8(gamma, VJ_F32, vi * 8, g);
-        if (beta) load8(beta, VJ_F32, vi * 8, b);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + (beta ? b[j] : 0.f);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd;
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nvec) {
+        float v[8];
+        raw[i].get(v);
+        s += ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
       }
-      store8(y, y_dtype, row * D + vi * 8, o);
+    }
+    const float mean = warp_sum(s) * inv_d;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + i * 32 < nvec) {
+        float v[8];
+        raw[i].get(v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = v[j] - mean; ss = fmaf(d, d, ss); }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float v[8], o[8];
+        raw[i].get(v);
+        if (gamma) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (beta) {
+            b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+            b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+          }
+          o[0] = fmaf((v[0] - mean) * rstd, g0.x, b0.x); o[1] = fmaf((v[1] - mean) * rstd, g0.y, b0.y);
+          o[2] = fmaf((v[2] - mean) * rstd, g0.z, b0.z); o[3] = fmaf((v[3] - mean) * rstd, g0.w, b0.w);
+          o[4] = fmaf((v[4] - mean) * rstd, g1.x, b1.x); o[5] = fmaf((v[5] - mean) * rstd, g1.y, b1.y);
+          o[6] = fmaf((v[6] - mean) * rstd, g1.z, b1.z); o[7] = fmaf((v[7] - mean) * rstd, g1.w, b1.w);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rstd;
+        }
+        store8t<YF32>(y, row * D + vi * 8, o);
+      }
     }
   }
 }
 
-// ---------------------------------------------------------------- LayerNorm backward (dx)
-__global__ void __launch_bounds__(256) ln_bwd_dx_kernel(const void* __restrict__ dy, int dy_dtype,
-                                                        const void* __restrict__ x, int x_dtype,
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres), g = dy * gamma
+template <bool DYF32, bool XF32, bool DXF32, int NV>
+__global__ void __launch_bounds__(256, 3) ln_bwd_dx_kernel(const void* __restrict__ dy, const void* __restrict__ x,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ mean_in,
                                                         const float* __restrict__ rstd_in,
                                                         const void* __restrict__ dres, void* __restrict__ dx,
-                                                        int dx_dtype, long long rows, int D) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + warp;
-  if (row >= rows) return;
+                                                        long long rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long nw = (long long)gridDim.x * 8;
   const int nvec = D >> 3;
-  const float mean = mean_in[row], rstd = rstd_in[row];
-  float xh[LN_MAXV][8], g[LN_MAXV][8];
-  float s1 = 0.f, s2 = 0.f;
+  const float inv_d = 1.0f / D;
+  for (long long row = wid; row < rows; row += nw) {
+    RawVec<DYF32> rdy[NV];
+    RawVec<XF32> rx[NV];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      float xv[8], dv[8], gm[8];
-      load8(x, x_dtype, row * D + vi * 8, xv);
-      load8(dy, dy_dtype, row * D + vi * 8, dv);
-      if (gamma) load8(gamma, VJ_F32, vi * 8, gm);
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        rdy[i].load(dy, row * D + vi * 8);
+        rx[i].load(x, row * D + vi * 8);
+      }
+    }
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        xh[i][j] = (xv[j] - mean) * rstd;
-        g[i][j] = gamma ? dv[j] * gm[j] : dv[j];
-        s1 += g[i][j];
-        s2 += g[i][j] * xh[i][j];
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float dv[8], xv[8], gm[8];
+        rdy[i].get(dv);
+        rx[i].get(xv);
+        if (gamma) load8(gamma, VJ_F32, vi * 8, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g = gamma ? dv[j] * gm[j] : dv[j];
+          s1 += g;
+          s2 = fmaf(g, (xv[j] - mean) * rstd, s2);
+        }
+      }
+    }
+    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        float dv[8], xv[8], gm[8], o[8];
+        rdy[i].get(dv);
+        rx[i].get(xv);
+        if (gamma) load8(gamma, VJ_F32, vi * 8, gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g = gamma ? dv[j] * gm[j] : dv[j];
+          o[j] = rstd * (g - c1 - (xv[j] - mean) * rstd * c2);
+        }
+        if (dres) {
+          RawVec<DXF32> rr;
+          rr.load(dres, row * D + vi * 8);
+          float r[8];
+          rr.get(r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        store8t<DXF32>(dx, row * D + vi * 8, o);
       }
     }
   }
-  const float c1 = warp_sum(s1) / D, c2 = warp_sum(s2) / D;
-#pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - c1 - xh[i][j] * c2);
-      if (dres) {
-        float r[8];
-        load8(dres, dx_dtype, row * D + vi * 8, r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += r[j];
-      }
-      store8(dx, dx_dtype, row * D + vi * 8, o);
-    }
-  }
+}
+
+static inline int ln_pick_nv(long long D) {
+  const long long need = (D / 8 + 31) / 32;
+  return need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : need <= 6 ? 6 : 8;
+}
+static inline unsigned ln_grid(long long rows) {
+  const long long want = (rows + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;      // 8 blocks x 8 warps per SM in flight, grid-stride beyond
+  return (unsigned)(want < cap ? want : cap);
 }
 
 // ---------------------------------------------------------------- column reductions
@@ -627,6 +709,15 @@ static int check_rowvec(const char* who, int64_t rows, int64_t D) {
   return 0;
 }
 
+template <bool XF32, bool YF32>
+static void ln_fwd_launch(int nv, unsigned grid, cudaStream_t st, const void* x, const float* gamma, const float* beta,
+                          void* y, float* mean, float* rstd, long long rows, int D, float eps) {
+#define VJ_LN_CASE(NV_) \
+  case NV_: ln_fwd_kernel<XF32, YF32, NV_><<<grid, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, D, eps); break;
+  switch (nv) { VJ_LN_CASE(1) VJ_LN_CASE(2) VJ_LN_CASE(4) VJ_LN_CASE(6) VJ_LN_CASE(8) }
+#undef VJ_LN_CASE
+}
+
 extern "C" int vj_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
                                 int y_dtype, float* mean, float* rstd, int64_t rows, int64_t D, float eps,
                                 void* stream) {
@@ -634,10 +725,25 @@ extern "C" int vj_layernorm_fwd(const void* x, int x_dtype, const float* gamma, 
   VJ_CHECK(D <= LN_MAXV * 256, "vj_layernorm_fwd: D=%lld exceeds %d", (long long)D, LN_MAXV * 256);
   VJ_CHECK(x && y, "vj_layernorm_fwd: null pointer");
   if (rows == 0) return 0;
-  ln_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(x, x_dtype, gamma, beta, y, y_dtype, mean,
-                                                                         rstd, rows, (int)D, eps);
+  const int nv = ln_pick_nv(D);
+  const unsigned grid = ln_grid(rows);
+  cudaStream_t st = STREAM(stream);
+  const bool xf = x_dtype == VJ_F32, yf = y_dtype == VJ_F32;
+  if (!xf && !yf) ln_fwd_launch<false, false>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, eps);
+  else if (!xf && yf) ln_fwd_launch<false, true>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, eps);
+  else if (xf && !yf) ln_fwd_launch<true, false>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, eps);
+  else ln_fwd_launch<true, true>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, eps);
   VJ_LAUNCH_CHECK();
   return 0;
+}
+
+template <bool DYF32, bool XF32, bool DXF32>
+static void ln_bwd_launch(int nv, unsigned grid, cudaStream_t st, const void* dy, const void* x, const float* gamma,
+                          const float* mean, const float* rstd, const void* dres, void* dx, long long rows, int D) {
+#define VJ_LN_CASE(NV_) \
+  case NV_: ln_bwd_dx_kernel<DYF32, XF32, DXF32, NV_><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, dres, dx, rows, D); break;
+  switch (nv) { VJ_LN_CASE(1) VJ_LN_CASE(2) VJ_LN_CASE(4) VJ_LN_CASE(6) VJ_LN_CASE(8) }
+#undef VJ_LN_CASE
 }
 
 extern "C" size_t vj_layernorm_bwd_scratch(int64_t rows, int64_t D) {
@@ -651,8 +757,22 @@ extern "C" int vj_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int
   VJ_CHECK(D <= LN_MAXV * 256, "vj_layernorm_bwd: D=%lld exceeds %d", (long long)D, LN_MAXV * 256);
   VJ_CHECK(dy && x && mean && rstd && dx, "vj_layernorm_bwd: null pointer");
   if (rows == 0) return 0;
-  ln_bwd_dx_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, STREAM(stream)>>>(dy, dy_dtype, x, x_dtype, gamma, mean, rstd,
-                                                                            dres, dx, dx_dtype, rows, (int)D);
+  {
+    const int nv = ln_pick_nv(D);
+    const unsigned grid = ln_grid(rows);
+    cudaStream_t st = STREAM(stream);
+    const int key = (dy_dtype == VJ_F32 ? 4 : 0) | (x_dtype == VJ_F32 ? 2 : 0) | (dx_dtype == VJ_F32 ? 1 : 0);
+    switch (key) {   // the dtype combinations the engine produces (encoder bf16 stream, predictor fp32 stream)
+      case 0: ln_bwd_launch<false, false, false>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
+      case 1: ln_bwd_launch<false, false, true>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
+      case 2: ln_bwd_launch<false, true, false>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
+      case 3: ln_bwd_launch<false, true, true>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
+      case 4: ln_bwd_launch<true, false, false>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
+      case 5: ln_bwd_launch<true, false, true>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
+      case 6: ln_bwd_launch<true, true, false>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
+      default: ln_bwd_launch<true, true, true>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
+    }
+  }
   VJ_LAUNCH_CHECK();
   if (dgamma || dbeta) {
     VJ_CHECK(scratch != nullptr, "vj_layernorm_bwd: scratch required for dgamma/dbeta");
