@@ -150,7 +150,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 256);
+    mbar_init(pds_full, 8);               // one arrival per compute warp
     mbar_init(dq_full, 1);
     mbar_fence_init();
   }
@@ -279,7 +279,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(pds_full);
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(pds_full);
       // dQ_i tile: lane r == query row r; stage scale*dQ as fp32 and let the TMA reduce-add it into dq_acc
       mbar_wait(dq_full, i & 1);
       tc_fence_after();

@@ -71,7 +71,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* v_full = bars + 7;       // 3
   uint64_t* v_empty = bars + 10;     // 3
   uint64_t* s_full = bars + 13;      // 2
-  uint64_t* p_full = bars + 15;      // 1 (256 arrivals)
+  uint64_t* p_full = bars + 15;      // 1 (8 arrivals: one per softmax warp)
   uint64_t* pv_done = bars + 16;     // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
@@ -87,7 +87,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
     mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 256);
+    mbar_init(p_full, 8);                 // one arrival per softmax warp
     mbar_init(pv_done, 1);
     mbar_fence_init();
   }
@@ -272,7 +272,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
       AP_ADD(ap6, b6);
     }
 #ifdef VJ_ATTN_PROFILE

@@ -280,7 +280,7 @@ template <int BN, bool A_MN, bool B_MN, bool AUX>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, GemmEpi epi, int M,
-            int N, int K) {
+            int N, int K, int splits) {
   using Cfg = GemmCfg<BN, AUX>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -298,6 +298,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  // split-K (reduce-add outputs only): work item w = split * num_tiles + tile handles k-blocks [kb0, kb1)
+  const int kb_per = (num_kb + splits - 1) / splits;
+  const int num_work = num_tiles * splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -331,11 +334,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t phase = 0;
       long long prof_a = 0;
       (void)prof_a;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int split = work / num_tiles, tile = work - split * num_tiles;
         int mb, nb;
         tile_coords(tile, num_m, num_n, mb, nb);
         const int m0 = mb * GEMM_BM, n0 = nb * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
           VJ_PROF_T0(tw);
           mbar_wait(&empty[stage], phase ^ 1);
           VJ_PROF_ADD(prof_a, tw);
@@ -370,7 +375,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     long long prof_full = 0, prof_te = 0;
     (void)prof_full; (void)prof_te;
     VJ_PROF_T0(t_all);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++local) {
+      const int split = work / num_tiles;
+      const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       VJ_PROF_T0(t1);
@@ -378,7 +385,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       VJ_PROF_ADD(prof_te, t1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         VJ_PROF_T0(t2);
         mbar_wait(&full[stage], phase);
         VJ_PROF_ADD(prof_full, t2);
@@ -392,10 +399,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t adk = desc_advance(ad, A_MN ? k * 2048 : k * 32);
             const uint64_t bdk = desc_advance(bd, B_MN ? k * 2048 : k * 32);
-            umma_bf16(d_tmem, adk, bdk, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, adk, bdk, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           umma_commit(&empty[stage]);
-          if (kb == num_kb - 1) umma_commit(&tfull[as]);
+          if (kb == kb1 - 1) umma_commit(&tfull[as]);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -424,7 +431,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int local = 0;
     long long prof_w = 0, prof_b = 0, prof_ld = 0;
     (void)prof_w; (void)prof_b; (void)prof_ld;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++local) {
+      const int tile = work % num_tiles;
       int mb, nb;
       tile_coords(tile, num_m, num_n, mb, nb);
       const int as = local & 1;
@@ -558,8 +566,27 @@ static int launch_gemm(const vj_gemm_args* g, int flags, cudaStream_t stream) {
   const int num_m = (int)((g->M + GEMM_BM - 1) / GEMM_BM);
   const int num_n = (int)((g->N + BN - 1) / BN);
   const int tiles = num_m * num_n;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmAux, e, (int)g->M, (int)g->N, (int)g->K);
+  const int num_kb = (int)((g->K + GEMM_BK - 1) / GEMM_BK);
+  // split-K for reduce-add outputs (weight gradients: few output tiles, very long K): pick the split count that
+  // fills whole waves of the persistent grid; an epilogue pass costs about as much as 6 k-blocks of mainloop
+  int splits = 1;
+  if ((flags & EPI_INTERNAL_REDUCE) && !(flags & VJ_EPI_BIAS)) {
+    const int sms = sm_count();
+    double best = 0.0;
+    for (int sp = 1; sp <= 32; ++sp) {
+      const int kb_per = (num_kb + sp - 1) / sp;
+      if (sp > 1 && kb_per < 8) break;
+      const int sp_eff = (num_kb + kb_per - 1) / kb_per;
+      const long long items = (long long)tiles * sp_eff;
+      const long long waves = (items + sms - 1) / sms;
+      const double score = (double)items / (double)(waves * sms) * kb_per / (kb_per + 6.0);
+      if (score > best * 1.02) { best = score; splits = sp_eff; }
+    }
+  }
+  const long long work = (long long)tiles * splits;
+  const int grid = work < sm_count() ? (int)work : sm_count();
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmAux, e, (int)g->M, (int)g->N, (int)g->K,
+                                                       splits);
   VJ_LAUNCH_CHECK();
   return 0;
 }

@@ -465,6 +465,10 @@ int main(int argc, char** argv) {
     bench_gemm("fc1 dgrad (ctx)", 12096, 1408, 6144, 0, 1, 0);
     bench_gemm("fc2 dgrad dgelu (ctx)", 12096, 6144, 1408, 0, 1, VJ_EPI_DGELU);
     bench_gemm("fc1 wgrad (ctx)", 6144, 1408, 12096, 1, 1, VJ_EPI_OUT_F32 | VJ_EPI_RES_F32 | VJ_EPI_RESIDUAL);
+    bench_gemm("qkv wgrad (ctx)", 4224, 1408, 12096, 1, 1, VJ_EPI_OUT_F32 | VJ_EPI_RES_F32 | VJ_EPI_RESIDUAL);
+    bench_gemm("proj wgrad (ctx)", 1408, 1408, 12096, 1, 1, VJ_EPI_OUT_F32 | VJ_EPI_RES_F32 | VJ_EPI_RESIDUAL);
+    bench_gemm("pred qkv wgrad", 1152, 384, 36000, 1, 1, VJ_EPI_OUT_F32 | VJ_EPI_RES_F32 | VJ_EPI_RESIDUAL);
+    bench_gemm("pred proj wgrad", 384, 384, 36000, 1, 1, VJ_EPI_OUT_F32 | VJ_EPI_RES_F32 | VJ_EPI_RESIDUAL);
     bench_gemm("8192^3", 8192, 8192, 8192, 0, 0, 0);
     bench_attn(24, 2048, 22, 64, false);
   }
