@@ -235,8 +235,8 @@ def main():
         f"{sum(p.numel() for p in step.encoder.parameters()) / 1e6:.1f}M")
 
     B = args.batch
-    n_e2e = 0 if args.no_e2e else max(2, min(args.steps, 5))
-    total = args.warmup + args.steps + n_e2e + 1
+    n_e2e = 0 if args.no_e2e else args.steps      # e2e replays the SAME mask draws as the timed region
+    total = args.warmup + args.steps + 1
     collator = MaskCollator(cfgs_mask=MASK_CFG, dataset_fpcs=[FRAMES], crop_size=(CROP, CROP), patch_size=(PATCH, PATCH),
                             tubelet_size=TUB)
     torch.manual_seed(239 + rank)                      # config seed 239; rank-local mask / clip streams
@@ -259,6 +259,30 @@ def main():
 
     for i in range(args.warmup):
         run_step(i, clips_dev)
+    barrier()
+    if rank == 0:   # host-side enqueue cost of one step (GPU idle at start, nothing awaited): must stay < GPU time
+        t_enq = time.perf_counter()
+        run_step(args.warmup - 1 if args.warmup else 0, clips_dev)
+        t_enq = time.perf_counter() - t_enq
+        log(f"host enqueue time of one step (incl. launch-queue back-pressure): {t_enq * 1e3:.1f} ms")
+        # pure host cost: same step with every C-ABI entry point stubbed out (no kernel is launched)
+        from vjepa2_b200 import _cabi as _C
+
+        class _Stub:
+            def __getattr__(self, name):
+                real = getattr(_real_lib, name)
+                if name.endswith("_scratch"):
+                    return real
+                return lambda *a: 0
+        _real_lib = _C.load()
+        torch.cuda.synchronize()
+        _C._lib = _Stub()
+        t_py = time.perf_counter()
+        run_step(args.warmup - 1 if args.warmup else 0, clips_dev)
+        t_py = time.perf_counter() - t_py
+        _C._lib = _real_lib
+        torch.cuda.synchronize()
+        log(f"pure host (Python + ctypes marshalling, kernels stubbed) time of one step: {t_py * 1e3:.1f} ms")
     barrier()
 
     # ---- timed region: device-resident inputs, CUDA events on the launching stream
@@ -287,19 +311,30 @@ def main():
     clips_s = world * B * args.steps / (ms_total / 1e3)
     tflops_gpu = flops_timed / (ms_total / 1e3) / 1e12          # per GPU (each rank does B clips)
 
-    # ---- e2e: public API with pinned host inputs; H2D + D2H inside the timed region (wall clock)
+    # ---- e2e: public API with pinned host inputs; every step's H2D (clips + masks, on a side stream, double
+    #      buffered by train.HostFeeder) and D2H (loss) are inside the timed region (wall clock)
     e2e = None
     if n_e2e:
-        base = args.warmup + args.steps
+        base = args.warmup
         h2d = clips_host.numel() * 4 + sum(m.numel() * 8 for m in masks_host[base][0] + masks_host[base][1])
         pinned_masks = [([m.pin_memory() for m in e], [m.pin_memory() for m in p]) for e, p in masks_host]
+        feeder = T.HostFeeder(dev)
+        # copy bandwidth alone, for the record
+        torch.cuda.synchronize()
+        tcp = time.perf_counter()
+        _tmp = clips_host.to(dev, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbs = clips_host.numel() * 4 / (time.perf_counter() - tcp) / 1e9
+        del _tmp
         barrier()
         t_start = time.perf_counter()
+        feeder.prefetch([clips_host], [pinned_masks[base][0]], [pinned_masks[base][1]])
         for i in range(base, base + n_e2e):
-            c = clips_host.to(dev, non_blocking=True)
-            e = [m.to(dev, non_blocking=True) for m in pinned_masks[i][0]]
-            p = [m.to(dev, non_blocking=True) for m in pinned_masks[i][1]]
-            l, _, _ = step.step([c], [e], [p])
+            c, e, p = feeder.get()
+            if i + 1 < base + n_e2e:
+                feeder.prefetch([clips_host], [pinned_masks[i + 1][0]], [pinned_masks[i + 1][1]])
+            l, _, _ = step.step(c, e, p)
+            feeder.release()
             _ = float(l.item())                                 # train.py:468 host read of the loss
         torch.cuda.synchronize()
         dt = time.perf_counter() - t_start
@@ -307,7 +342,9 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = dict(value=world * B * n_e2e / float(tt.item()), unit="clips/s", h2d_bytes_per_step=h2d,
-                   d2h_bytes_per_step=4, steps=n_e2e)
+                   d2h_bytes_per_step=4, steps=n_e2e, ms_per_step=1e3 * float(tt.item()) / n_e2e,
+                   h2d_gbs_measured=h2d_gbs,
+                   note="H2D of step i+1 overlaps compute of step i (side stream, pinned host memory)")
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA events, one instrumented step
     #      (every rank runs the step -- it contains the gradient all-reduce -- rank 0 instruments it)

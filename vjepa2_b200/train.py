@@ -72,6 +72,60 @@ class GradBucketer:
         self._works = []
 
 
+class HostFeeder:
+    """Pinned-host -> device staging of a step's inputs on a side stream, double buffered, so the H2D copies of
+    step i+1 (train.py:393-402: clips + mask indices) overlap the compute of step i.
+
+        feeder.prefetch(clips, masks_enc, masks_pred)      # host (pinned) tensors of the NEXT step
+        clips_d, me_d, mp_d = feeder.get()                  # device tensors of the oldest prefetched step
+    """
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._q = []
+        self._clip_bufs = {}      # (slot, group index) -> persistent device buffer
+        self._slot = 0
+        self._free = [None, None]  # event: compute finished reading this slot
+
+    def prefetch(self, clips, masks_enc, masks_pred):
+        slot = self._slot
+        self._slot ^= 1
+        st = self.stream
+        if self._free[slot] is not None:
+            st.wait_event(self._free[slot])
+        with torch.cuda.stream(st):
+            dc = []
+            for gi, c in enumerate(clips):
+                buf = self._clip_bufs.get((slot, gi))
+                if buf is None or buf.shape != c.shape:
+                    buf = torch.empty(c.shape, dtype=torch.float32, device=self.device)
+                    self._clip_bufs[(slot, gi)] = buf
+                buf.copy_(c, non_blocking=True)
+                dc.append(buf)
+            me = [[m.to(self.device, non_blocking=True) for m in g] for g in masks_enc]
+            mp = [[m.to(self.device, non_blocking=True) for m in g] for g in masks_pred]
+            ev = torch.cuda.Event()
+            ev.record(st)
+        self._q.append((slot, ev, dc, me, mp))
+
+    def get(self):
+        slot, ev, dc, me, mp = self._q.pop(0)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for g in me + mp:
+            for m in g:
+                m.record_stream(cur)
+        self._pending_slot = slot
+        return dc, me, mp
+
+    def release(self):
+        """Call after the step that consumed the last get() has been enqueued."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._free[self._pending_slot] = ev
+
+
 def _unwrap(m):
     return m.backbone if hasattr(m, "backbone") else m
 
