@@ -161,19 +161,25 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="vit_giant_xformers", choices=list(MODELS))
     ap.add_argument("--batch", type=int, default=24)
+    ap.add_argument("--frames", type=int, default=16, help="frames per clip (16 = pretrain configs, 64 = cooldown)")
+    ap.add_argument("--crop", type=int, default=256, help="crop size (256 pretrain, 384 cooldown)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-ops", action="store_true",
                     help="after the timed region, run one extra step with CUDA events around every C-ABI call and "
                          "print a per-op time table to stderr")
     args = ap.parse_args()
+    global FRAMES, CROP, NTOK
+    FRAMES, CROP = args.frames, args.crop
+    NTOK = (FRAMES // TUB) * (CROP // PATCH) ** 2
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     metric = f"clips/sec ({'ViT-g/16' if args.model == 'vit_giant_xformers' else 'ViT-L/16'} V-JEPA 2 pretrain step, " \
-             f"16x256x256 clips, fwd+bwd+AdamW+EMA)"
-    config = dict(workload=f"{args.model} pretrain step (configs/train/vitg16/pretrain-256px-16f.yaml shapes), "
+             f"{args.frames}x{args.crop}x{args.crop} clips, fwd+bwd+AdamW+EMA)"
+    config = dict(workload=f"{args.model} pretrain step (configs/train/vitg16/"
+                           f"{'pretrain-256px-16f' if args.frames == 16 else 'cooldown-384px-64f'}.yaml shapes), "
                            f"batch {args.batch}/GPU, multiblock3d masks (8x0.15 + 2x0.7), predictor depth 12 / 384",
                   global_batch=args.batch * world, tokens_per_clip=NTOK, parallelism=f"dp{world}",
                   l2_policy="working set (>= 2 GB of bf16 weights + activations per step) exceeds the 126 MB L2; no flush")
