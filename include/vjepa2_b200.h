@@ -71,7 +71,7 @@ typedef struct {
   const void* aux_in;    /* bf16, ld = ld_aux */
   int64_t ld_aux;
   const void* rope_table; /* fp16 [M][2][rope_hd] (VJ_EPI_ROPE) */
-  int32_t rope_hd;        /* head dim (32 or 64) */
+  int32_t rope_hd;        /* head dim (32, 64 or 80) */
   int32_t rope_D;         /* model width: N == 3*rope_D */
 } vj_gemm_args;
 
@@ -110,7 +110,7 @@ int vj_rope_apply(void* qkv, int64_t rows, int64_t D, int heads, int head_dim, c
  * qkv: [B*S][3*D] bf16, feature = which*D + head*d + i (modules.py:330-331), q/k already rotated.
  * out: [B*S][D] bf16 (head-major features = x.transpose(1,2).reshape, modules.py:379).
  * lse: [B][H][S] fp32, log2-domain log-sum-exp (saved for backward).
- * head_dim in {32, 64}.  S arbitrary >= 1. */
+ * head_dim in {32, 64, 80} (80 = ViT-H: handled as a 64 + 16 split of every head-dim operand).  S >= 1. */
 int vj_attn_fwd(const void* qkv, void* out, float* lse, int B, int S, int H, int head_dim, void* stream);
 /* dqkv: [B*S][3*D] bf16: gradient w.r.t. the rotated q/k and v; if rope_table != NULL (vj_rope_table layout,
  * rows = B*S) the adjoint RoPE map is applied to dq and dk on the way out, giving the gradient w.r.t. the

@@ -195,6 +195,15 @@ def main():
     for k in ["predictor_embed.weight", "mask_tokens.0", "mask_tokens.1", "predictor_proj.bias"]:
         G["step.after.pred." + k] = pred.state_dict()[k].clone()
 
+    # 7. ViT-H geometry in miniature: head_dim 80 (RoPE segments 26/26/26 + 2 pass-through dims)
+    encH = VisionTransformer(img_size=TINY["img"], patch_size=16, num_frames=TINY["frames"], tubelet_size=2,
+                             embed_dim=160, depth=2, num_heads=2, mlp_ratio=4.0, qkv_bias=True,
+                             norm_layer=partial(nn.LayerNorm, eps=1e-6), use_rope=True)
+    encH.load_state_dict(O.init_encoder_weights(160, 2, 4.0, seed=3, rand_bias=True), strict=True)
+    with torch.no_grad():
+        G["encH.full"] = encH(clips)
+        G["encH.masked"] = encH(clips, me)
+
     out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     path = os.path.join(out_dir, "ref_golden.pt")

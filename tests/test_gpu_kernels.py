@@ -104,7 +104,8 @@ def _sdpa_ref(qkv, B, S, H, hd):
     return (att.softmax(-1) @ v).transpose(1, 2).reshape(B * S, D)
 
 
-@pytest.mark.parametrize("B,S,H,hd", [(2, 200, 3, 64), (1, 1000, 2, 64), (2, 72, 2, 32), (1, 700, 3, 32), (3, 8, 2, 64)])
+@pytest.mark.parametrize("B,S,H,hd", [(2, 200, 3, 64), (1, 1000, 2, 64), (2, 72, 2, 32), (1, 700, 3, 32), (3, 8, 2, 64),
+                                      (2, 200, 2, 80), (1, 520, 3, 80)])
 def test_attention_fwd_bwd(dev, B, S, H, hd):
     from vjepa2_b200 import ops
     D = H * hd
@@ -168,7 +169,7 @@ def test_layernorm_fwd_bwd(dev, rows, D, xd, yd):
 
 
 # ----------------------------------------------------------------------------------------------- RoPE
-@pytest.mark.parametrize("hd,H", [(64, 2), (32, 3)])
+@pytest.mark.parametrize("hd,H", [(64, 2), (32, 3), (80, 2)])
 def test_rope_matches_oracle(dev, hd, H):
     """Stand-alone kernel, the fused GEMM epilogue (VJ_EPI_ROPE) and the fused adjoint in attention backward
     all against the oracle's restatement of rotate_queries_or_keys (modules.py:26-50)."""

@@ -64,6 +64,33 @@ def test_encoder_forward_vs_reference_golden(dev, golden):
     assert relerr(both[2:].flip(1), golden["enc.masked"]) < 1e-2
 
 
+def test_encoder_head_dim_80_vs_reference_golden(dev, golden):
+    """ViT-H geometry in miniature (head_dim 80 = 64 + 16 split inside the attention kernels), forward against the
+    real reference, backward against the fp32 oracle."""
+    import vjepa_oracle as O
+    from vjepa2_b200.vision_transformer import VisionTransformer
+    enc = VisionTransformer(img_size=TINY["img"], patch_size=16, num_frames=TINY["frames"], tubelet_size=2,
+                            embed_dim=160, depth=2, num_heads=2, mlp_ratio=4.0, qkv_bias=True,
+                            norm_layer=partial(nn.LayerNorm, eps=1e-6), use_rope=True)
+    w = O.init_encoder_weights(160, 2, 4.0, seed=3, rand_bias=True)
+    enc.load_state_dict(w, strict=True)
+    enc.to(dev)
+    clips = tiny_clips(2).to(dev)
+    me, _ = tiny_masks(2)
+    with torch.no_grad():
+        assert relerr(enc(clips), golden["encH.full"]) < 1e-2
+    out = enc(clips, me.to(dev))
+    assert relerr(out, golden["encH.masked"]) < 1e-2
+    g = torch.Generator().manual_seed(4)
+    dy = torch.randn(out.shape, generator=g)
+    out.backward(dy.to(dev))
+    wr = {k: v.clone().requires_grad_(True) for k, v in w.items()}
+    O.vit_forward(wr, tiny_clips(2), me, 2, 2).backward(dy)
+    for name in ["blocks.0.attn.qkv.weight", "blocks.1.attn.proj.weight", "blocks.0.mlp.fc1.weight", "patch_embed.proj.weight"]:
+        got = dict(enc.named_parameters())[name].grad
+        assert relerr(got, wr[name].grad) < 3e-2, (name, relerr(got, wr[name].grad))
+
+
 def test_predictor_forward_vs_reference_golden(dev, golden):
     _, pred, _, _ = build_models(dev)
     me, mp = tiny_masks(2)

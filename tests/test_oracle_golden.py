@@ -36,6 +36,15 @@ def test_encoder_forward(golden):
     close(O.vit_forward(w_enc, clips, me, TINY["depth"], TINY["heads"]), golden["enc.masked"])
 
 
+def test_encoder_forward_head_dim_80(golden):
+    """ViT-H's head_dim (80): RoPE segment width 26, two pass-through dims."""
+    w = O.init_encoder_weights(160, 2, 4.0, seed=3, rand_bias=True)
+    clips = tiny_clips(2)
+    me, _ = tiny_masks(2)
+    close(O.vit_forward(w, clips, None, 2, 2), golden["encH.full"])
+    close(O.vit_forward(w, clips, me, 2, 2), golden["encH.masked"])
+
+
 def test_predictor_forward(golden):
     _, w_pred = tiny_weights()
     me, mp = tiny_masks(2)

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "host_common.h"
+#include "attn_common.cuh"
 #include "../../include/vjepa2_b200.h"
 
 namespace vj {
@@ -25,7 +26,6 @@ namespace vj {
 template <int HD>
 struct AttnBwdCfg {
   static constexpr int BT = 128;                       // keys per CTA == queries per iteration
-  static constexpr int SWB = HD * 2;
   static constexpr int TILE_BYTES = BT * HD * 2;       // K, V, Q_i, dO_i tiles
   static constexpr int PT_BYTES = BT * BT * 2;         // 32 KB: two [128 rows][128 B] atoms
   static constexpr int OFF_K = 0;
@@ -34,13 +34,19 @@ struct AttnBwdCfg {
   static constexpr int OFF_DO = OFF_Q + 2 * TILE_BYTES; // 2 stages
   static constexpr int OFF_PT = OFF_DO + 2 * TILE_BYTES;
   static constexpr int OFF_DS = OFF_PT + PT_BYTES;
-  static constexpr int OFF_DQ = OFF_DS + PT_BYTES;     // fp32 dQ staging: 128 rows x HD x 4 B
-  static constexpr int OFF_LSE = OFF_DQ + BT * HD * 4; // 128 floats lse + 128 floats delta
+  // the fp32 dQ staging tile (128 rows x HD x 4 B <= 40 KB) ALIASES P^T / dS^T: both are dead once the MMAs of
+  // the iteration have retired (dq_full), and are only rewritten after the TMA has finished reading the staging
+  static constexpr int OFF_DQ = OFF_PT;
+  static constexpr int OFF_LSE = OFF_DS + PT_BYTES;    // 128 floats lse + 128 floats delta
   static constexpr int OFF_BAR = OFF_LSE + 1024;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int COL_ST = 0, COL_DPT = 128, COL_DV = 256, COL_DK = 256 + HD, COL_DQ = 256 + 2 * HD;
   static constexpr int TMEM_COLS = 512;
-  static_assert(HD == 64 || HD == 32, "head_dim 64 or 32");
+  static constexpr bool DQ_DENSE = (HD % 32) != 0;     // HD = 80: un-swizzled [128][HD] fp32 staging, one TMA box
+  static_assert(HD == 80 || HD == 64 || HD == 32, "head_dim 80, 64 or 32");
+  static_assert(COL_DQ + HD <= 512, "TMEM budget");
+  static_assert(BT * HD * 4 <= 2 * PT_BYTES, "dQ staging must fit the aliased region");
+  static_assert(TILE_BYTES % 1024 == 0, "tiles must keep 1024-B alignment");
 };
 
 // delta[b][h][q] = sum_i dO[q, h, i] * O[q, h, i]
@@ -115,7 +121,7 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* m, const vo
 // columns of S^T / dP^T, and half of the columns of the dQ / dK / dV rows), warp 8 TMA producer + TMEM, warp 9 MMA.
 template <int HD>
 __global__ void __launch_bounds__(320, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+attn_bwd_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__ TMapPair tmDO,
                 const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse,
                 const float* __restrict__ delta, bf16* __restrict__ dqkv, const __half* __restrict__ rope, int S, int H,
                 int D, float scale, float scale_log2) {
@@ -166,27 +172,23 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
   if (warp == 8) {
     // ---------------------------------------------------------------- TMA producer
     if (elect_one()) {
-      tma_prefetch_desc(&tmQKV);
-      tma_prefetch_desc(&tmDO);
+      tma_prefetch_desc(&tmQKV.m[0]);
+      tma_prefetch_desc(&tmDO.m[0]);
       mbar_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
-      tma_load_3d(sK, &tmQKV, kv_full, D + h * HD, k0, b);
-      tma_load_3d(sV, &tmQKV, kv_full, 2 * D + h * HD, k0, b);
+      tma_load_head_tile<HD>(sK, &tmQKV, kv_full, Cfg::BT, D + h * HD, k0, b);
+      tma_load_head_tile<HD>(sV, &tmQKV, kv_full, Cfg::BT, 2 * D + h * HD, k0, b);
       for (int i = 0; i < n_q; ++i) {
         const int st = i & 1;
         mbar_wait(&qdo_empty[st], ((i >> 1) & 1) ^ 1);
         mbar_expect_tx(&qdo_full[st], 2 * Cfg::TILE_BYTES);
-        tma_load_3d(sQ + st * Cfg::TILE_BYTES, &tmQKV, &qdo_full[st], h * HD, i * Cfg::BT, b);
-        tma_load_3d(sDO + st * Cfg::TILE_BYTES, &tmDO, &qdo_full[st], h * HD, i * Cfg::BT, b);
+        tma_load_head_tile<HD>(sQ + st * Cfg::TILE_BYTES, &tmQKV, &qdo_full[st], Cfg::BT, h * HD, i * Cfg::BT, b);
+        tma_load_head_tile<HD>(sDO + st * Cfg::TILE_BYTES, &tmDO, &qdo_full[st], Cfg::BT, h * HD, i * Cfg::BT, b);
       }
     }
   } else if (warp == 9) {
     // ---------------------------------------------------------------- MMA issuer
     constexpr uint32_t id_s = make_idesc(128, 128, false, false);
-    constexpr uint32_t id_dv = make_idesc(128, HD, false, true);
-    constexpr uint32_t id_dq = make_idesc(128, HD, true, true);
-    const uint64_t kd_k = desc_kmajor<Cfg::SWB>(smem_u32(sK));
-    const uint64_t vd_k = desc_kmajor<Cfg::SWB>(smem_u32(sV));
-    const uint64_t kd_mn = desc_mnmajor<Cfg::SWB>(smem_u32(sK), Cfg::TILE_BYTES);
+    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
     const uint64_t pt_k = desc_kmajor<128>(smem_u32(sPT));
     const uint64_t ds_k = desc_kmajor<128>(smem_u32(sDS));
     const uint64_t ds_mn = desc_mnmajor<128>(smem_u32(sDS), 16384);
@@ -198,34 +200,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
       const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
       if (elect_one()) {
-        const uint64_t qd_k = desc_kmajor<Cfg::SWB>(q_addr);
-        const uint64_t dod_k = desc_kmajor<Cfg::SWB>(do_addr);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(tmem_base + Cfg::COL_ST, desc_advance(kd_k, k * 32), desc_advance(qd_k, k * 32), id_s, k != 0);
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(tmem_base + Cfg::COL_DPT, desc_advance(vd_k, k * 32), desc_advance(dod_k, k * 32), id_s, k != 0);
+        mma_over_hd<HD>(tmem_base + Cfg::COL_ST, k_addr, Cfg::BT, q_addr, Cfg::BT, id_s);     // S^T  = K Q^T
+        mma_over_hd<HD>(tmem_base + Cfg::COL_DPT, v_addr, Cfg::BT, do_addr, Cfg::BT, id_s);   // dP^T = V dO^T
         umma_commit(sdp_full);
       }
       __syncwarp();
       mbar_wait(pds_full, i & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t qd_mn = desc_mnmajor<Cfg::SWB>(q_addr, Cfg::TILE_BYTES);
-        const uint64_t dod_mn = desc_mnmajor<Cfg::SWB>(do_addr, Cfg::TILE_BYTES);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)   // dV += P^T dO
-          umma_bf16(tmem_base + Cfg::COL_DV, desc_advance(pt_k, (k >> 2) * 16384 + (k & 3) * 32),
-                    desc_advance(dod_mn, k * 16 * Cfg::SWB), id_dv, (i | k) != 0);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)   // dK += dS^T Q
-          umma_bf16(tmem_base + Cfg::COL_DK, desc_advance(ds_k, (k >> 2) * 16384 + (k & 3) * 32),
-                    desc_advance(qd_mn, k * 16 * Cfg::SWB), id_dv, (i | k) != 0);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)   // dQ_i = dS K
-          umma_bf16(tmem_base + Cfg::COL_DQ, desc_advance(ds_mn, k * 2048), desc_advance(kd_mn, k * 16 * Cfg::SWB),
-                    id_dq, k != 0);
+        // dV += P^T dO ; dK += dS^T Q   (A: K-major 2-atom tiles, k-step k lives in atom k/4)
+        mma_into_hd<HD, false, Cfg::BT>(tmem_base + Cfg::COL_DV,
+                                        [&](int k) { return desc_advance(pt_k, (k >> 2) * 16384 + (k & 3) * 32); },
+                                        do_addr, i != 0);
+        mma_into_hd<HD, false, Cfg::BT>(tmem_base + Cfg::COL_DK,
+                                        [&](int k) { return desc_advance(ds_k, (k >> 2) * 16384 + (k & 3) * 32); },
+                                        q_addr, i != 0);
+        // dQ_i = dS K   (A: the same dS^T buffer read MN-major)
+        mma_into_hd<HD, true, Cfg::BT>(tmem_base + Cfg::COL_DQ, [&](int k) { return desc_advance(ds_mn, k * 2048); },
+                                       k_addr, false);
         umma_commit(&qdo_empty[st]);
         umma_commit(dq_full);
       }
@@ -284,34 +276,39 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
       // dQ_i tile: lane r == query row r; stage scale*dQ as fp32 and let the TMA reduce-add it into dq_acc
       mbar_wait(dq_full, i & 1);
       tc_fence_after();
-      if constexpr (HO == 32) {
-        uint32_t o[32];
-        tmem_ld32(lane_addr + Cfg::COL_DQ + half * HO, o);
+      {
+        uint32_t o[HO];
+        tmem_ld_n<HO>(lane_addr + Cfg::COL_DQ + half * HO, o);
         tmem_ld_wait();
-        uint8_t* rowp = sDQ + half * 16384 + r * 128;     // atom = half
+        if constexpr (Cfg::DQ_DENSE) {
+          float* rowp = reinterpret_cast<float*>(sDQ) + r * HD + half * HO;     // dense [128][HD] fp32
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          *reinterpret_cast<float4*>(rowp + ((u ^ (r & 7)) << 4)) =
-              make_float4(__uint_as_float(o[u * 4]) * scale, __uint_as_float(o[u * 4 + 1]) * scale,
-                          __uint_as_float(o[u * 4 + 2]) * scale, __uint_as_float(o[u * 4 + 3]) * scale);
-      } else {
-        uint32_t o[16];
-        tmem_ld16(lane_addr + Cfg::COL_DQ + half * HO, o);
-        tmem_ld_wait();
-        uint8_t* rowp = sDQ + r * 128;                    // single atom, this half fills chunks 4*half..
+          for (int u = 0; u < HO / 4; ++u)
+            *reinterpret_cast<float4*>(rowp + u * 4) =
+                make_float4(__uint_as_float(o[u * 4]) * scale, __uint_as_float(o[u * 4 + 1]) * scale,
+                            __uint_as_float(o[u * 4 + 2]) * scale, __uint_as_float(o[u * 4 + 3]) * scale);
+        } else {
+          // 128-byte swizzled atoms of 32 fp32: HD = 64 -> atom = half (8 chunks); HD = 32 -> one atom, 4 chunks each
+          uint8_t* rowp = sDQ + (HO == 32 ? half * 16384 : 0) + r * 128;
+          const int cbase = HO == 32 ? 0 : half * 4;
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          *reinterpret_cast<float4*>(rowp + (((half * 4 + u) ^ (r & 7)) << 4)) =
-              make_float4(__uint_as_float(o[u * 4]) * scale, __uint_as_float(o[u * 4 + 1]) * scale,
-                          __uint_as_float(o[u * 4 + 2]) * scale, __uint_as_float(o[u * 4 + 3]) * scale);
+          for (int u = 0; u < HO / 4; ++u)
+            *reinterpret_cast<float4*>(rowp + (((cbase + u) ^ (r & 7)) << 4)) =
+                make_float4(__uint_as_float(o[u * 4]) * scale, __uint_as_float(o[u * 4 + 1]) * scale,
+                            __uint_as_float(o[u * 4 + 2]) * scale, __uint_as_float(o[u * 4 + 3]) * scale);
+        }
       }
       tc_fence_before();
       fence_proxy_async_smem();
       asm volatile("bar.sync 2, 256;" ::: "memory");
       if (threadIdx.x == 128) {                            // same thread that waits on the bulk group above
+        if constexpr (Cfg::DQ_DENSE) {
+          tma_reduce_add_3d(&tmDQ, sDQ, h * HD, i * Cfg::BT, b);
+        } else {
 #pragma unroll
-        for (int a = 0; a < HD / 32; ++a)
-          tma_reduce_add_3d(&tmDQ, sDQ + a * 16384, h * HD + a * 32, i * Cfg::BT, b);
+          for (int a = 0; a < HD / 32; ++a)
+            tma_reduce_add_3d(&tmDQ, sDQ + a * 16384, h * HD + a * 32, i * Cfg::BT, b);
+        }
         bulk_commit_bwd();
       }
     }
@@ -322,13 +319,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant
     bf16* dv_row = dk_row + D;
     constexpr int NV = HO / 8;
     uint32_t a[HO], c[HO];
-    if constexpr (HO == 32) {
-      tmem_ld32(lane_addr + Cfg::COL_DK + half * HO, a);
-      tmem_ld32(lane_addr + Cfg::COL_DV + half * HO, c);
-    } else {
-      tmem_ld16(lane_addr + Cfg::COL_DK + half * HO, a);
-      tmem_ld16(lane_addr + Cfg::COL_DV + half * HO, c);
-    }
+    tmem_ld_n<HO>(lane_addr + Cfg::COL_DK + half * HO, a);
+    tmem_ld_n<HO>(lane_addr + Cfg::COL_DV + half * HO, c);
     tmem_ld_wait();
     if (key_ok) {
       const __half* tr = rope ? rope + ((long long)b * S + key) * 2 * HD + half * HO : nullptr;
@@ -373,27 +365,19 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
         reinterpret_cast<const bf16*>(out), reinterpret_cast<const bf16*>(dout), delta, B, S, H, HD);
     VJ_LAUNCH_CHECK();
   }
-  CUtensorMap tmQKV, tmDO;
+  TMapPair tmQKV, tmDO;
   {
-    const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)S, (uint64_t)B};
-    const uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)S * 3 * D * 2};
-    const uint32_t box[3] = {HD, Cfg::BT, 1};
-    int r = make_tmap_bf16(&tmQKV, qkv, 3, dims, strides, box, Cfg::SWB);
+    int r = make_head_tmaps<HD>(&tmQKV, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, Cfg::BT);
     if (r) return r;
-  }
-  {
-    const uint64_t dims[3] = {(uint64_t)D, (uint64_t)S, (uint64_t)B};
-    const uint64_t strides[2] = {(uint64_t)D * 2, (uint64_t)S * D * 2};
-    const uint32_t box[3] = {HD, Cfg::BT, 1};
-    int r = make_tmap_bf16(&tmDO, dout, 3, dims, strides, box, Cfg::SWB);
+    r = make_head_tmaps<HD>(&tmDO, dout, (uint64_t)D, (uint64_t)S, (uint64_t)B, Cfg::BT);
     if (r) return r;
   }
   CUtensorMap tmDQ;
   {
     const uint64_t dims[3] = {(uint64_t)D, (uint64_t)S, (uint64_t)B};
     const uint64_t strides[2] = {(uint64_t)D * 4, (uint64_t)S * D * 4};
-    const uint32_t box[3] = {32, Cfg::BT, 1};
-    int r = make_tmap(&tmDQ, dq_acc, VJ_F32, 3, dims, strides, box, 128);
+    const uint32_t box[3] = {Cfg::DQ_DENSE ? (uint32_t)HD : 32u, Cfg::BT, 1};
+    int r = make_tmap(&tmDQ, dq_acc, VJ_F32, 3, dims, strides, box, Cfg::DQ_DENSE ? 0 : 128);
     if (r) return r;
   }
   auto kern = attn_bwd_kernel<HD>;
@@ -432,6 +416,7 @@ extern "C" int vj_attn_bwd(const void* qkv, const void* out, const void* dout, c
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (head_dim == 64) return launch_attn_bwd<64>(qkv, out, dout, lse, dqkv, scratch, rope_table, B, S, H, st);
   if (head_dim == 32) return launch_attn_bwd<32>(qkv, out, dout, lse, dqkv, scratch, rope_table, B, S, H, st);
-  set_error("vj_attn_bwd: head_dim %d not supported (32, 64)", head_dim);
+  if (head_dim == 80) return launch_attn_bwd<80>(qkv, out, dout, lse, dqkv, scratch, rope_table, B, S, H, st);
+  set_error("vj_attn_bwd: head_dim %d not supported (32, 64, 80)", head_dim);
   return -1;
 }

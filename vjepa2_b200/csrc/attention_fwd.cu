@@ -4,6 +4,7 @@
 // [B*S][3D] with a 3-D tensor map (d, S, B) -- no head-major relayout pass.  Roles: see attn_fwd_kernel.
 #include "common.cuh"
 #include "host_common.h"
+#include "attn_common.cuh"
 #include "../../include/vjepa2_b200.h"
 
 namespace vj {
@@ -23,7 +24,6 @@ __device__ unsigned long long g_attn_prof[16];
 template <int HD>
 struct AttnFwdCfg {
   static constexpr int BM = 128, BN = 64, KV_STAGES = 3;
-  static constexpr int SWB = HD * 2;                 // operand row bytes == swizzle width (128 or 64)
   static constexpr int Q_BYTES = BM * HD * 2;
   static constexpr int KV_BYTES = BN * HD * 2;
   static constexpr int P_BYTES = BM * BN * 2;        // 16 KB, 128-B rows
@@ -37,7 +37,8 @@ struct AttnFwdCfg {
   static constexpr int TMEM_COLS = 256;
   static constexpr int O_COL = 128;
   static constexpr int THREADS = 320;                // 8 softmax warps + producer + MMA
-  static_assert(HD == 64 || HD == 32, "head_dim 64 or 32");
+  static_assert(HD == 80 || HD == 64 || HD == 32, "head_dim 80, 64 or 32");
+  static_assert(Q_BYTES % 1024 == 0 && KV_BYTES % 1024 == 0, "tiles must keep 1024-B alignment");
 };
 
 __device__ __forceinline__ void pair_barrier(int q) {   // the two warps that share TMEM lane quarter q
@@ -53,7 +54,7 @@ __device__ __forceinline__ void pair_barrier(int q) {   // the two warps that sh
 // is rare after the first tiles; exp2 goes straight to MUFU (ex2.approx), the kernel's limiting pipe.
 template <int HD>
 __global__ void __launch_bounds__(320, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+attn_fwd_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TMapPair tmKV,
                 bf16* __restrict__ out, float* __restrict__ lse, int S, int H, int D, float scale_log2) {
   using Cfg = AttnFwdCfg<HD>;
   constexpr int HO = HD / 2;                         // O columns per softmax thread
@@ -103,26 +104,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 8) {
     // ---------------------------------------------------------------- TMA producer
     if (elect_one()) {
-      tma_prefetch_desc(&tmQ);
-      tma_prefetch_desc(&tmKV);
+      tma_prefetch_desc(&tmQ.m[0]);
+      tma_prefetch_desc(&tmKV.m[0]);
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
-      tma_load_3d(sQ, &tmQ, q_full, h * HD, q0, b);
+      tma_load_head_tile<HD>(sQ, &tmQ, q_full, Cfg::BM, h * HD, q0, b);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % 3;
         const uint32_t ph = (j / 3) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
-        tma_load_3d(sK + st * Cfg::KV_BYTES, &tmKV, &k_full[st], D + h * HD, j * Cfg::BN, b);
+        tma_load_head_tile<HD>(sK + st * Cfg::KV_BYTES, &tmKV, &k_full[st], Cfg::BN, D + h * HD, j * Cfg::BN, b);
         mbar_wait(&v_empty[st], ph ^ 1);
         mbar_expect_tx(&v_full[st], Cfg::KV_BYTES);
-        tma_load_3d(sV + st * Cfg::KV_BYTES, &tmKV, &v_full[st], 2 * D + h * HD, j * Cfg::BN, b);
+        tma_load_head_tile<HD>(sV + st * Cfg::KV_BYTES, &tmKV, &v_full[st], Cfg::BN, 2 * D + h * HD, j * Cfg::BN, b);
       }
     }
   } else if (warp == 9) {
     // ---------------------------------------------------------------- MMA issuer
     constexpr uint32_t idesc_qk = make_idesc(128, Cfg::BN, false, false);
-    constexpr uint32_t idesc_pv = make_idesc(128, HD, false, true);
-    const uint64_t qd = desc_kmajor<Cfg::SWB>(smem_u32(sQ));
     const uint64_t pd = desc_kmajor<128>(smem_u32(sP));
     mbar_wait(q_full, 0);
     long long ap_p = 0, ap_kv = 0;
@@ -135,11 +134,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       AP_ADD(ap_kv, a0);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t kd = desc_kmajor<Cfg::SWB>(smem_u32(sK + st * Cfg::KV_BYTES));
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_bf16(tmem_base + (j & 1) * Cfg::BN, desc_advance(qd, k * 32), desc_advance(kd, k * 32), idesc_qk,
-                    k != 0 ? 1u : 0u);
+        mma_over_hd<HD>(tmem_base + (j & 1) * Cfg::BN, smem_u32(sQ), Cfg::BM, smem_u32(sK + st * Cfg::KV_BYTES), Cfg::BN,
+                        idesc_qk);
         umma_commit(&k_empty[st]);
         umma_commit(&s_full[j & 1]);
       }
@@ -157,11 +153,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       AP_ADD(ap_p, a2);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t vd = desc_mnmajor<Cfg::SWB>(smem_u32(sV + st * Cfg::KV_BYTES), Cfg::KV_BYTES);
-#pragma unroll
-        for (int k = 0; k < Cfg::BN / 16; ++k)
-          umma_bf16(tmem_base + Cfg::O_COL, desc_advance(pd, k * 32), desc_advance(vd, k * 16 * Cfg::SWB), idesc_pv,
-                    (j | k) != 0 ? 1u : 0u);
+        mma_into_hd<HD, false, Cfg::BN>(tmem_base + Cfg::O_COL, [&](int k) { return desc_advance(pd, k * 32); },
+                                        smem_u32(sV + st * Cfg::KV_BYTES), j != 0);
         umma_commit(&v_empty[st]);
         umma_commit(pv_done);
       }
@@ -244,21 +237,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         AP_T0(b5);
         tc_fence_after();
         if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-          if constexpr (HO == 32) {
-            uint32_t o[32];
-            tmem_ld32(lane_addr + Cfg::O_COL + half * HO, o);
-            tmem_ld_wait();
+          uint32_t o[HO];
+          tmem_ld_n<HO>(lane_addr + Cfg::O_COL + half * HO, o);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(lane_addr + Cfg::O_COL + half * HO, o);
-          } else {
-            uint32_t o[16];
-            tmem_ld16(lane_addr + Cfg::O_COL + half * HO, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(lane_addr + Cfg::O_COL + half * HO, o);
-          }
+          for (int i = 0; i < HO; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st_n<HO>(lane_addr + Cfg::O_COL + half * HO, o);
           tmem_st_wait();
         }
         AP_ADD(ap5, b5);
@@ -297,28 +281,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int qrow = q0 + r;
     const float inv_l = 1.0f / l_tot;
     bf16* orow = out + ((long long)b * S + qrow) * D + h * HD + half * HO;
-    if constexpr (HO == 32) {
-      uint32_t o[32];
-      tmem_ld32(lane_addr + Cfg::O_COL + half * HO, o);
+    {
+      uint32_t o[HO];
+      tmem_ld_n<HO>(lane_addr + Cfg::O_COL + half * HO, o);
       tmem_ld_wait();
       if (qrow < S) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          uint4 u;
-          u.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
-          u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
-          u.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv_l, __uint_as_float(o[i + 5]) * inv_l);
-          u.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv_l, __uint_as_float(o[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + i) = u;
-        }
-      }
-    } else {
-      uint32_t o[16];
-      tmem_ld16(lane_addr + Cfg::O_COL + half * HO, o);
-      tmem_ld_wait();
-      if (qrow < S) {
-#pragma unroll
-        for (int i = 0; i < 16; i += 8) {
+        for (int i = 0; i < HO; i += 8) {
           uint4 u;
           u.x = pack_bf16x2(__uint_as_float(o[i]) * inv_l, __uint_as_float(o[i + 1]) * inv_l);
           u.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv_l, __uint_as_float(o[i + 3]) * inv_l);
@@ -340,14 +309,10 @@ template <int HD>
 static int launch_attn_fwd(const void* qkv, void* out, float* lse, int B, int S, int H, cudaStream_t stream) {
   using Cfg = AttnFwdCfg<HD>;
   const int D = H * HD;
-  CUtensorMap tmQ, tmKV;
-  const uint64_t dims[3] = {(uint64_t)3 * D, (uint64_t)S, (uint64_t)B};
-  const uint64_t strides[2] = {(uint64_t)3 * D * 2, (uint64_t)S * 3 * D * 2};
-  const uint32_t boxq[3] = {HD, Cfg::BM, 1};
-  const uint32_t boxkv[3] = {HD, Cfg::BN, 1};
-  int r = make_tmap_bf16(&tmQ, qkv, 3, dims, strides, boxq, Cfg::SWB);
+  TMapPair tmQ, tmKV;
+  int r = make_head_tmaps<HD>(&tmQ, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, Cfg::BM);
   if (r) return r;
-  r = make_tmap_bf16(&tmKV, qkv, 3, dims, strides, boxkv, Cfg::SWB);
+  r = make_head_tmaps<HD>(&tmKV, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, Cfg::BN);
   if (r) return r;
   auto kern = attn_fwd_kernel<HD>;
   static bool attr_set = false;
@@ -372,7 +337,8 @@ extern "C" int vj_attn_fwd(const void* qkv, void* out, float* lse, int B, int S,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (head_dim == 64) return launch_attn_fwd<64>(qkv, out, lse, B, S, H, st);
   if (head_dim == 32) return launch_attn_fwd<32>(qkv, out, lse, B, S, H, st);
-  set_error("vj_attn_fwd: head_dim %d not supported (32, 64)", head_dim);
+  if (head_dim == 80) return launch_attn_fwd<80>(qkv, out, lse, B, S, H, st);
+  set_error("vj_attn_fwd: head_dim %d not supported (32, 64, 80)", head_dim);
   return -1;
 }
 

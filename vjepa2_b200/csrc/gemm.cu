@@ -634,7 +634,7 @@ extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
   VJ_CHECK(!((flags & VJ_EPI_DGELU) && (flags & VJ_EPI_RES_F32)), "vj_gemm: DGELU with an fp32 residual is not supported");
   if (flags & VJ_EPI_ROPE) {
     VJ_CHECK(!(flags & (VJ_EPI_RESIDUAL | VJ_EPI_DGELU | VJ_EPI_GELU)), "vj_gemm: ROPE combines with BIAS only");
-    VJ_CHECK(g->rope_table && (g->rope_hd == 32 || g->rope_hd == 64) && g->rope_D > 0 && g->rope_D % g->rope_hd == 0 &&
+    VJ_CHECK(g->rope_table && (g->rope_hd == 32 || g->rope_hd == 64 || g->rope_hd == 80) && g->rope_D > 0 && g->rope_D % g->rope_hd == 0 &&
                  g->N == 3 * (int64_t)g->rope_D && g->rope_D % 16 == 0,
              "vj_gemm: bad ROPE arguments (hd=%d D=%d N=%lld)", g->rope_hd, g->rope_D, (long long)g->N);
   }

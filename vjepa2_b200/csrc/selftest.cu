@@ -161,7 +161,7 @@ __global__ void ref_attn_fwd_kernel(const bf16* qkv, float* out, float* lse2, in
   const int D = H * hd;
   const bf16* Q = qkv + ((long long)b * S + q) * 3 * D + h * hd;
   const float scale = rsqrtf((float)hd);
-  float m = -INFINITY, l = 0.f, acc[64];
+  float m = -INFINITY, l = 0.f, acc[128];
   for (int i = 0; i < hd; ++i) acc[i] = 0.f;
   for (int k = 0; k < S; ++k) {
     const bf16* Kp = qkv + ((long long)b * S + k) * 3 * D + D + h * hd;
@@ -197,7 +197,7 @@ __global__ void ref_attn_bwd_kernel(const bf16* qkv, const float* o_ref, const b
     float delta = 0.f;
     for (int i = 0; i < hd; ++i) delta += __bfloat162float(dO[i]) * O[i];
     const float l2 = lse2[((long long)b * H + h) * S + t];
-    float dq[64];
+    float dq[128];
     for (int i = 0; i < hd; ++i) dq[i] = 0.f;
     for (int k = 0; k < S; ++k) {
       const bf16* Kp = qkv + ((long long)b * S + k) * 3 * D + D + h * hd;
@@ -218,7 +218,7 @@ __global__ void ref_attn_bwd_kernel(const bf16* qkv, const float* o_ref, const b
   {
     const bf16* Kp = qkv + ((long long)b * S + t) * 3 * D + D + h * hd;
     const bf16* Vp = Kp + D;
-    float dk[64], dv[64];
+    float dk[128], dv[128];
     for (int i = 0; i < hd; ++i) dk[i] = dv[i] = 0.f;
     for (int q = 0; q < S; ++q) {
       const bf16* Q = qkv + ((long long)b * S + q) * 3 * D + h * hd;
@@ -449,6 +449,8 @@ int main(int argc, char** argv) {
     test_attn(1, 1000, 2, 64, false);
     test_attn(2, 72, 2, 32, false);
     test_attn(1, 700, 3, 32, false);
+    test_attn(2, 200, 2, 80, false);
+    test_attn(1, 1000, 3, 80, false);
   }
   if (all || !strcmp(what, "attnbwd")) {
     test_attn(1, 128, 1, 64, true);
@@ -456,6 +458,8 @@ int main(int argc, char** argv) {
     test_attn(1, 520, 2, 64, true);
     test_attn(2, 72, 2, 32, true);
     test_attn(1, 700, 3, 32, true);
+    test_attn(2, 200, 2, 80, true);
+    test_attn(1, 520, 3, 80, true);
   }
   if (all || !strcmp(what, "bench")) {
     bench_gemm("qkv fwd (ViT-g target)", 49152, 4224, 1408, 0, 0, VJ_EPI_BIAS);
@@ -475,6 +479,8 @@ int main(int argc, char** argv) {
   if (all || !strcmp(what, "benchbwd")) {
     bench_attn(24, 504, 22, 64, true);
     bench_attn(24, 1448, 12, 32, true);
+    bench_attn(24, 504, 16, 80, true);
+    bench_attn(24, 2048, 16, 80, false);
   }
   printf(g_fail ? "SELFTEST FAILED\n" : "SELFTEST PASSED\n");
   return g_fail;

@@ -51,8 +51,8 @@ class RoPEAttention(nn.Module):
                                       "non-causal (the pre-training configs)")
         self.num_heads = num_heads
         self.head_dim = dim // num_heads
-        if self.head_dim not in (32, 64):
-            raise NotImplementedError(f"vjepa2_b200: head_dim {self.head_dim} not supported yet (32 and 64 are)")
+        if self.head_dim not in (32, 64, 80):
+            raise NotImplementedError(f"vjepa2_b200: head_dim {self.head_dim} not supported (32, 64 and 80 are)")
         self.scale = self.head_dim ** -0.5
         self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
         self.attn_drop = nn.Dropout(attn_drop)

@@ -175,7 +175,7 @@ def _vit(embed_dim, depth, num_heads, mlp_ratio, patch_size=16, **kwargs):
                              mlp_ratio=mlp_ratio, qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), **kwargs)
 
 
-# factories with the reference's names (vision_transformer.py:275-475); head_dim must be 32 or 64 for now
+# factories with the reference's names (vision_transformer.py:275-475); head_dim must be 32, 64 or 80
 def vit_large(patch_size=16, **kwargs):
     return _vit(1024, 24, 16, 4, patch_size, **kwargs)
 
@@ -185,7 +185,7 @@ def vit_giant_xformers(patch_size=16, **kwargs):
 
 
 def vit_huge(patch_size=16, **kwargs):
-    # head_dim 80: rejected by RoPEAttention until the 64+16 split-K attention tile lands
+    # head_dim 80: the attention kernels split every head-dim operand into a 64-wide and a 16-wide chunk
     return _vit(1280, 32, 16, 4, patch_size, **kwargs)
 
 
