@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 
 MODELS = {  # name: (embed_dim, depth, heads, mlp_hidden)
     "vit_large": (1024, 24, 16, 4096),
+    "vit_huge": (1280, 32, 16, 5120),
     "vit_giant_xformers": (1408, 40, 22, 6144),
 }
 PRED = dict(dim=384, depth=12, heads=12, hidden=1536)
@@ -176,7 +177,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    metric = f"clips/sec ({'ViT-g/16' if args.model == 'vit_giant_xformers' else 'ViT-L/16'} V-JEPA 2 pretrain step, " \
+    pretty = {"vit_giant_xformers": "ViT-g/16", "vit_large": "ViT-L/16", "vit_huge": "ViT-H/16"}[args.model]
+    metric = f"clips/sec ({pretty} V-JEPA 2 pretrain step, " \
              f"{args.frames}x{args.crop}x{args.crop} clips, fwd+bwd+AdamW+EMA)"
     config = dict(workload=f"{args.model} pretrain step (configs/train/vitg16/"
                            f"{'pretrain-256px-16f' if args.frames == 16 else 'cooldown-384px-64f'}.yaml shapes), "
