@@ -268,7 +268,8 @@ def main():
     for i in range(args.warmup):
         run_step(i, clips_dev)
     barrier()
-    if rank == 0:   # host-side enqueue cost of one step (GPU idle at start, nothing awaited): must stay < GPU time
+    if rank == 0 and world == 1:   # single-process only: an extra step on one rank would dead-lock the collectives
+        # host-side enqueue cost of one step (GPU idle at start, nothing awaited): must stay < GPU time
         t_enq = time.perf_counter()
         run_step(args.warmup - 1 if args.warmup else 0, clips_dev)
         t_enq = time.perf_counter() - t_enq
