@@ -279,7 +279,7 @@ __device__ __forceinline__ void stage_f32x32(uint8_t* stg, int lane, const float
 template <int BN, bool A_MN, bool B_MN, bool AUX>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, GemmEpi epi, int M,
+            const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, GemmEpi epi, int M,
             int N, int K, int splits) {
   using Cfg = GemmCfg<BN, AUX>;
   constexpr int STAGES = Cfg::STAGES;
@@ -340,13 +340,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tile_coords(tile, num_m, num_n, mb, nb);
         const int m0 = mb * GEMM_BM, n0 = nb * BN;
         const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        // a narrow last N tile only fetches the B rows / column groups it needs
+        const int n_live = min(BN, ((N - n0) + 15) & ~15);
+        const bool half_b = !B_MN && n_live <= BN / 2;
+        const int b_boxes = B_MN ? (n_live + 63) / 64 : 0;
+        const uint32_t tx_bytes = Cfg::A_BYTES + (B_MN ? b_boxes * 8192 : (half_b ? Cfg::B_BYTES / 2 : Cfg::B_BYTES));
         for (int kb = kb0; kb < kb1; ++kb) {
           VJ_PROF_T0(tw);
           mbar_wait(&empty[stage], phase ^ 1);
           VJ_PROF_ADD(prof_a, tw);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+          mbar_expect_tx(&full[stage], tx_bytes);
           if (!A_MN) {
             tma_load_2d(sa, &tmA, &full[stage], kb * GEMM_BK, m0);
           } else {
@@ -354,10 +359,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int c = 0; c < GEMM_BM / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, &full[stage], m0 + c * 64, kb * GEMM_BK);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tmB, &full[stage], kb * GEMM_BK, n0);
+            tma_load_2d(sb, half_b ? &tmBh : &tmB, &full[stage], kb * GEMM_BK, n0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, &full[stage], n0 + c * 64, kb * GEMM_BK);
+            for (int c = 0; c < BN / 64; ++c)
+              if (c < b_boxes) tma_load_2d(sb + c * 8192, &tmB, &full[stage], n0 + c * 64, kb * GEMM_BK);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -368,7 +374,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc(GEMM_BM, BN, A_MN, B_MN);
+    // The last N tile may be narrower than BN: its MMAs are issued with N = the live columns rounded up to 16, so
+    // e.g. N = 1408 costs 5 x 256 + 1 x 128 columns of tensor time instead of 6 x 256 (TMA still zero-fills the box).
     int stage = 0;
     uint32_t phase = 0;
     int local = 0;
@@ -378,6 +385,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++local) {
       const int split = work / num_tiles;
       const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      int mb_, nb_;
+      tile_coords(work - split * num_tiles, num_m, num_n, mb_, nb_);
+      const int n_live = min(BN, ((N - nb_ * BN) + 15) & ~15);
+      const uint32_t idesc = make_idesc(GEMM_BM, n_live, A_MN, B_MN);
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       VJ_PROF_T0(t1);
@@ -518,7 +529,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 template <int BN, bool A_MN, bool B_MN, bool AUX>
 static int launch_gemm(const vj_gemm_args* g, int flags, cudaStream_t stream) {
   using Cfg = GemmCfg<BN, AUX>;
-  CUtensorMap tmA, tmB, tmOut, tmAux;
+  CUtensorMap tmA, tmB, tmBh, tmOut, tmAux;
   {
     const uint64_t dimsK[2] = {(uint64_t)g->K, (uint64_t)g->M};
     const uint64_t dimsM[2] = {(uint64_t)g->M, (uint64_t)g->K};
@@ -536,6 +547,12 @@ static int launch_gemm(const vj_gemm_args* g, int flags, cudaStream_t stream) {
     const uint32_t boxN[2] = {64, GEMM_BK};
     int r = make_tmap(&tmB, g->b, VJ_BF16, 2, B_MN ? dimsN : dimsK, str, B_MN ? boxN : boxK, 128);
     if (r) return r;
+    tmBh = tmB;
+    if (!B_MN) {   // half-height box for a narrow last N tile
+      const uint32_t boxH[2] = {64, (uint32_t)BN / 2};
+      r = make_tmap(&tmBh, g->b, VJ_BF16, 2, dimsK, str, boxH, 128);
+      if (r) return r;
+    }
   }
   {
     const bool f32 = (flags & VJ_EPI_OUT_F32) != 0;
@@ -585,8 +602,8 @@ static int launch_gemm(const vj_gemm_args* g, int flags, cudaStream_t stream) {
   }
   const long long work = (long long)tiles * splits;
   const int grid = work < sm_count() ? (int)work : sm_count();
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmOut, tmAux, e, (int)g->M, (int)g->N, (int)g->K,
-                                                       splits);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmBh, tmOut, tmAux, e, (int)g->M, (int)g->N,
+                                                       (int)g->K, splits);
   VJ_LAUNCH_CHECK();
   return 0;
 }
