@@ -23,7 +23,7 @@ __device__ unsigned long long g_attn_prof[16];
 
 template <int HD>
 struct AttnFwdCfg {
-  static constexpr int BM = 128, BN = 64, KV_STAGES = 3;
+  static constexpr int BM = 128, BN = 64, KV_STAGES = (HD == 80) ? 2 : 3;   // two CTAs must fit one SM
   static constexpr int Q_BYTES = BM * HD * 2;
   static constexpr int KV_BYTES = BN * HD * 2;
   static constexpr int P_BYTES = BM * BN * 2;        // 16 KB, 128-B rows
@@ -31,7 +31,7 @@ struct AttnFwdCfg {
   static constexpr int OFF_K = OFF_Q + Q_BYTES;
   static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
   static constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;
-  static constexpr int OFF_X = OFF_P + P_BYTES;      // row-max / row-sum exchange: [2 parity][2 half][128] floats
+  static constexpr int OFF_X = OFF_P + 2 * P_BYTES;  // (P is double-buffered) row-max / row-sum exchange: [2 parity][2 half][128] floats
   static constexpr int OFF_BAR = OFF_X + 2 * 2 * 128 * 4;
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
   static constexpr int TMEM_COLS = 256;
@@ -63,18 +63,19 @@ attn_fwd_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TM
   uint8_t* sQ = smem + Cfg::OFF_Q;
   uint8_t* sK = smem + Cfg::OFF_K;
   uint8_t* sV = smem + Cfg::OFF_V;
-  uint8_t* sP = smem + Cfg::OFF_P;
+  uint8_t* sP = smem + Cfg::OFF_P;          // two 16 KB buffers (tile parity)
   float* xch = reinterpret_cast<float*>(smem + Cfg::OFF_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* q_full = bars;           // 1
-  uint64_t* k_full = bars + 1;       // 3
-  uint64_t* k_empty = bars + 4;      // 3
-  uint64_t* v_full = bars + 7;       // 3
-  uint64_t* v_empty = bars + 10;     // 3
-  uint64_t* s_full = bars + 13;      // 2
-  uint64_t* p_full = bars + 15;      // 1 (8 arrivals: one per softmax warp)
-  uint64_t* pv_done = bars + 16;     // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  constexpr int NST = Cfg::KV_STAGES;
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = bars + 1;             // NST
+  uint64_t* k_empty = k_full + NST;        // NST
+  uint64_t* v_full = k_empty + NST;        // NST
+  uint64_t* v_empty = v_full + NST;        // NST
+  uint64_t* s_full = v_empty + NST;        // 2
+  uint64_t* p_full = s_full + 2;           // 2 (8 arrivals each: one per softmax warp)
+  uint64_t* pv_done = p_full + 2;          // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * Cfg::BM;
@@ -83,13 +84,15 @@ attn_fwd_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TM
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < NST; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
-    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
-    mbar_init(p_full, 8);                 // one arrival per softmax warp
-    mbar_init(pv_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);           // one arrival per softmax warp
+      mbar_init(&pv_done[i], 1);
+    }
     mbar_fence_init();
   }
   if (warp == 8) {
@@ -109,8 +112,8 @@ attn_fwd_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TM
       mbar_expect_tx(q_full, Cfg::Q_BYTES);
       tma_load_head_tile<HD>(sQ, &tmQ, q_full, Cfg::BM, h * HD, q0, b);
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % 3;
-        const uint32_t ph = (j / 3) & 1;
+        const int st = j % NST;
+        const uint32_t ph = (j / NST) & 1;
         mbar_wait(&k_empty[st], ph ^ 1);
         mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
         tma_load_head_tile<HD>(sK + st * Cfg::KV_BYTES, &tmKV, &k_full[st], Cfg::BN, D + h * HD, j * Cfg::BN, b);
@@ -122,15 +125,15 @@ attn_fwd_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TM
   } else if (warp == 9) {
     // ---------------------------------------------------------------- MMA issuer
     constexpr uint32_t idesc_qk = make_idesc(128, Cfg::BN, false, false);
-    const uint64_t pd = desc_kmajor<128>(smem_u32(sP));
+    const uint64_t pd0 = desc_kmajor<128>(smem_u32(sP));
     mbar_wait(q_full, 0);
     long long ap_p = 0, ap_kv = 0;
     (void)ap_p; (void)ap_kv;
     AP_T0(ap_all);
     auto issue_qk = [&](int j) {
-      const int st = j % 3;
+      const int st = j % NST;
       AP_T0(a0);
-      mbar_wait(&k_full[st], (j / 3) & 1);
+      mbar_wait(&k_full[st], (j / NST) & 1);
       AP_ADD(ap_kv, a0);
       tc_fence_after();
       if (elect_one()) {
@@ -143,20 +146,22 @@ attn_fwd_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TM
     };
     issue_qk(0);
     for (int j = 0; j < n_tiles; ++j) {
+      // S_{j+1} overwrites the buffer of S_{j-1}: every softmax warp finished reading it before p_full(j-1)
       if (j + 1 < n_tiles) issue_qk(j + 1);
-      const int st = j % 3;
+      const int st = j % NST;
       AP_T0(a1);
-      mbar_wait(&v_full[st], (j / 3) & 1);
+      mbar_wait(&v_full[st], (j / NST) & 1);
       AP_ADD(ap_kv, a1);
       AP_T0(a2);
-      mbar_wait(p_full, j & 1);
+      mbar_wait(&p_full[j & 1], (j >> 1) & 1);
       AP_ADD(ap_p, a2);
       tc_fence_after();
       if (elect_one()) {
+        const uint64_t pd = desc_advance(pd0, (j & 1) * Cfg::P_BYTES);
         mma_into_hd<HD, false, Cfg::BN>(tmem_base + Cfg::O_COL, [&](int k) { return desc_advance(pd, k * 32); },
                                         smem_u32(sV + st * Cfg::KV_BYTES), j != 0);
         umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
+        umma_commit(&pv_done[j & 1]);
       }
       __syncwarp();
     }
@@ -175,20 +180,19 @@ attn_fwd_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TM
     const int q = warp & 3;                                 // TMEM lane quarter (shared with warp ^ 4)
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* prow = sP + r * 128;
+    const uint32_t prow = smem_u32(sP) + r * 128;
+    const uint32_t xch_mine = smem_u32(xch) + (half * 128 + r) * 4;
+    const uint32_t xch_peer = smem_u32(xch) + ((half ^ 1) * 128 + r) * 4;
     long long ap1 = 0, ap2 = 0, ap3 = 0, ap4 = 0, ap5 = 0, ap6 = 0;
     (void)ap1; (void)ap2; (void)ap3; (void)ap4; (void)ap5; (void)ap6;
     AP_T0(ap_tot);
+    uint32_t sr[32];
+    mbar_wait(&s_full[0], 0);
+    tc_fence_after();
+    tmem_ld32(lane_addr + half * 32, sr);
+    tmem_ld_wait_regs(sr);
     for (int j = 0; j < n_tiles; ++j) {
-      AP_T0(b1);
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      AP_ADD(ap1, b1);
-      tc_fence_after();
-      uint32_t sr[32];
-      AP_T0(b2);
-      tmem_ld32(lane_addr + (j & 1) * Cfg::BN + half * 32, sr);
-      tmem_ld_wait();
-      AP_ADD(ap2, b2);
+      // sr holds this thread's 32 columns of S_j
       AP_T0(b3);
       const int valid = S - j * Cfg::BN - half * 32;        // columns of this half that are real keys
       if (valid < 32) {                                     // only in the last tile
@@ -205,10 +209,10 @@ attn_fwd_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TM
         mx3 = fmaxf(mx3, __uint_as_float(sr[i + 3]));
       }
       const float mloc = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      float* xm = xch + (j & 1) * 256;
-      xm[half * 128 + r] = mloc;
+      const uint32_t xoff = (j & 1) * 1024;
+      st_shared_f32(xch_mine + xoff, mloc);
       pair_barrier(q);
-      const float m_tile = fmaxf(mloc, xm[(half ^ 1) * 128 + r]) * scale_log2;
+      const float m_tile = fmaxf(mloc, ld_shared_f32(xch_peer + xoff)) * scale_log2;
       // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
       float alpha = 1.0f;
       if (m_tile > m_run + 8.0f) {
@@ -229,36 +233,50 @@ attn_fwd_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TM
       }
       l_run = l_run * alpha + ((rs0 + rs1) + (rs2 + rs3));
       AP_ADD(ap3, b3);
-      if (j > 0) {
-        // PV_{j-1} finished: P buffer is free and O holds tiles < j
-        AP_T0(b4);
-        mbar_wait(pv_done, (j - 1) & 1);
-        AP_ADD(ap4, b4);
-        AP_T0(b5);
+      // start fetching S_{j+1} (issued by the MMA warp a whole tile ago) while P_j is being published
+      const bool more = j + 1 < n_tiles;
+      if (more) {
+        AP_T0(b1);
+        mbar_wait(&s_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+        AP_ADD(ap1, b1);
         tc_fence_after();
-        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-          uint32_t o[HO];
-          tmem_ld_n<HO>(lane_addr + Cfg::O_COL + half * HO, o);
-          tmem_ld_wait();
+        tmem_ld32(lane_addr + ((j + 1) & 1) * Cfg::BN + half * 32, sr);
+      }
+      if (j >= 2) {                                         // P buffer (j & 1) was last read by PV_{j-2}
+        AP_T0(b4);
+        mbar_wait(&pv_done[j & 1], ((j - 2) >> 1) & 1);
+        AP_ADD(ap4, b4);
+      }
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        // O correction needs exclusive access to the accumulator: PV_{j-1} must have landed
+        AP_T0(b5);
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        uint32_t o[HO];
+        tmem_ld_n<HO>(lane_addr + Cfg::O_COL + half * HO, o);
+        tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < HO; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_n<HO>(lane_addr + Cfg::O_COL + half * HO, o);
-          tmem_st_wait();
-        }
+        for (int i = 0; i < HO; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+        tmem_st_n<HO>(lane_addr + Cfg::O_COL + half * HO, o);
+        tmem_st_wait();
         AP_ADD(ap5, b5);
       }
       AP_T0(b6);
       // P half-row -> smem, K-major 128-B swizzled rows: 16-B chunk c lands at c ^ (r & 7)
+      const uint32_t pdst = prow + (j & 1) * Cfg::P_BYTES;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 u = make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-        *reinterpret_cast<uint4*>(prow + (((half * 4 + c) ^ (r & 7)) << 4)) = u;
-      }
+      for (int c = 0; c < 4; ++c)
+        st_shared_v4(pdst + (((half * 4 + c) ^ (r & 7)) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
       AP_ADD(ap6, b6);
+      if (more) {
+        AP_T0(b2);
+        tmem_ld_wait_regs(sr);
+        AP_ADD(ap2, b2);
+      }
     }
 #ifdef VJ_ATTN_PROFILE
     if (threadIdx.x == 0) {
@@ -272,11 +290,11 @@ attn_fwd_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TM
     }
 #endif
     // combine the two partial row sums (same reference max in both halves)
-    float* xl = xch + (n_tiles & 1) * 256;
-    xl[half * 128 + r] = l_run;
+    const uint32_t xoff = (n_tiles & 1) * 1024;
+    st_shared_f32(xch_mine + xoff, l_run);
     pair_barrier(q);
-    const float l_tot = l_run + xl[(half ^ 1) * 128 + r];
-    mbar_wait(pv_done, (n_tiles - 1) & 1);
+    const float l_tot = l_run + ld_shared_f32(xch_peer + xoff);
+    mbar_wait(&pv_done[(n_tiles - 1) & 1], ((n_tiles - 1) >> 1) & 1);
     tc_fence_after();
     const int qrow = q0 + r;
     const float inv_l = 1.0f / l_tot;
@@ -303,6 +321,347 @@ attn_fwd_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TM
   tc_fence_before();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Dual-stream variant (head_dim 64 / 32): the kernel above is a single dependent chain per CTA
+// (S -> max -> exp -> P -> PV -> ...), and with two CTAs per SM only two chains share the MUFU pipe, which
+// then idles whenever both sit in their latency-bound phases.  Here the even and the odd KV tiles of a CTA are
+// two INDEPENDENT online-softmax streams: softmax warpgroup g (128 threads, thread = full 64-column row, so no
+// cross-thread max exchange) owns S buffer g, P buffer g and its own O accumulator g in TMEM, one MMA warp issues
+// both streams' QK^T / PV in tile order, and the two (m, l, O) partial results are merged once at the end.  Four chains per
+// SM keep the exp pipe fed.  TMEM: S0 [0,64) S1 [64,128) O0 [128,128+d) O1 [128+d,128+2d).
+// Register budget: 2 CTAs x 384 threads -> 80 at launch; setmaxnreg moves registers from the producer/MMA
+// warpgroup (32) to the softmax warpgroups (104).
+template <int HD>
+struct AttnFwd2Cfg {
+  static constexpr int BM = 128, BN = 64, KV_STAGES = 3;
+  static constexpr int Q_BYTES = BM * HD * 2;
+  static constexpr int KV_BYTES = BN * HD * 2;
+  static constexpr int P_BYTES = BM * BN * 2;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + Q_BYTES;
+  static constexpr int OFF_V = OFF_K + KV_STAGES * KV_BYTES;
+  static constexpr int OFF_P = OFF_V + KV_STAGES * KV_BYTES;     // one P buffer per stream
+  static constexpr int OFF_X = OFF_P + 2 * P_BYTES;              // merge exchange: [m|l][2 streams][128] floats
+  static constexpr int OFF_BAR = OFF_X + 2 * 2 * 128 * 4;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+  static constexpr int TMEM_COLS = 256;
+  static constexpr int O_COL = 128;
+  static constexpr int THREADS = 384;                            // 2 softmax warpgroups + {producer, MMA, 2 idle}
+  static_assert(HD == 64 || HD == 32, "dual-stream kernel: head_dim 64 or 32");
+  static_assert(O_COL + 2 * HD <= TMEM_COLS, "TMEM budget");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(384, 2)
+attn_fwd2_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TMapPair tmKV,
+                 bf16* __restrict__ out, float* __restrict__ lse, int S, int H, int D, float scale_log2) {
+  using Cfg = AttnFwd2Cfg<HD>;
+  constexpr int HO = HD / 2;                         // output columns per thread in the merge
+  constexpr int NST = Cfg::KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sP = smem + Cfg::OFF_P;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* k_full = bars + 1;             // NST
+  uint64_t* k_empty = k_full + NST;        // NST
+  uint64_t* v_full = k_empty + NST;        // NST
+  uint64_t* v_empty = v_full + NST;        // NST
+  uint64_t* s_full = v_empty + NST;        // 2: S_j of stream g landed in TMEM
+  uint64_t* s_free = s_full + 2;           // 2: stream g copied S_j to registers (4 warp arrivals)
+  uint64_t* p_full = s_free + 2;           // 2: P_j of stream g is in smem (4 warp arrivals)
+  uint64_t* pv_done = p_full + 2;          // 2: O_g += P_j V_j finished
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * Cfg::BM;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = (S + Cfg::BN - 1) / Cfg::BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NST; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_free[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (warp == 8) {
+      // -------------------------------------------------------------- TMA producer
+      if (elect_one()) {
+        tma_prefetch_desc(&tmQ.m[0]);
+        tma_prefetch_desc(&tmKV.m[0]);
+        mbar_expect_tx(q_full, Cfg::Q_BYTES);
+        tma_load_head_tile<HD>(sQ, &tmQ, q_full, Cfg::BM, h * HD, q0, b);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int st = j % NST;
+          const uint32_t ph = (j / NST) & 1;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
+          tma_load_head_tile<HD>(sK + st * Cfg::KV_BYTES, &tmKV, &k_full[st], Cfg::BN, D + h * HD, j * Cfg::BN, b);
+          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_expect_tx(&v_full[st], Cfg::KV_BYTES);
+          tma_load_head_tile<HD>(sV + st * Cfg::KV_BYTES, &tmKV, &v_full[st], Cfg::BN, 2 * D + h * HD, j * Cfg::BN, b);
+        }
+      }
+    } else if (warp == 9) {
+      // -------------------------------------------------------------- MMA issuer (both streams)
+      // One warp consumes the K ring (QK_0, QK_1, QK_2, ...) and the V ring (PV_0, PV_1, ...) strictly in tile
+      // order, so every parity wait on a ring stage follows the wait on that stage's previous fill.  (Two
+      // issuers, one per stream, skip every other fill of a stage and their parity waits can pass vacuously.)
+      // The fixed order QK_{t+2}, PV_t also keeps the two streams half a period apart.
+      constexpr uint32_t idesc_qk = make_idesc(128, Cfg::BN, false, false);
+      const uint64_t pd0 = desc_kmajor<128>(smem_u32(sP));
+      mbar_wait(q_full, 0);
+      auto issue_qk = [&](int j) {
+        const int st = j % NST;
+        mbar_wait(&k_full[st], (j / NST) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          mma_over_hd<HD>(tmem_base + (j & 1) * Cfg::BN, smem_u32(sQ), Cfg::BM, smem_u32(sK + st * Cfg::KV_BYTES),
+                          Cfg::BN, idesc_qk);
+          umma_commit(&k_empty[st]);
+          umma_commit(&s_full[j & 1]);
+        }
+        __syncwarp();
+      };
+      issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int g = t & 1, jl = t >> 1;
+        if (t + 2 < n_tiles) {                   // S buffer g is free once the stream holds S_t in registers
+          mbar_wait(&s_free[g], jl & 1);
+          issue_qk(t + 2);
+        }
+        const int st = t % NST;
+        mbar_wait(&v_full[st], (t / NST) & 1);
+        mbar_wait(&p_full[g], jl & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t pd = desc_advance(pd0, g * Cfg::P_BYTES);
+          mma_into_hd<HD, false, Cfg::BN>(tmem_base + Cfg::O_COL + g * HD, [&](int k) { return desc_advance(pd, k * 32); },
+                                          smem_u32(sV + st * Cfg::KV_BYTES), jl != 0);
+          umma_commit(&v_empty[st]);
+          umma_commit(&pv_done[g]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax stream g
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int r = threadIdx.x & 127;                        // query row in tile == TMEM lane
+    const int g = threadIdx.x >> 7;                         // stream: KV tiles j with j % 2 == g
+    const int q = warp & 3;                                 // TMEM lane quarter
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t s_addr = lane_addr + g * Cfg::BN;
+    const uint32_t o_addr = lane_addr + Cfg::O_COL + g * HD;
+    const uint32_t prow = smem_u32(sP) + g * Cfg::P_BYTES + r * 128;
+    const int swz = r & 7;
+    float m_run = -INFINITY, l_run = 0.f;
+    int jl = 0;
+    long long ap1 = 0, ap2 = 0, ap3 = 0, ap4 = 0, ap5 = 0, ap6 = 0;
+    (void)ap1; (void)ap2; (void)ap3; (void)ap4; (void)ap5; (void)ap6;
+    AP_T0(ap_tot);
+    for (int j = g; j < n_tiles; j += 2, ++jl) {
+      AP_T0(b1);
+      mbar_wait(&s_full[g], jl & 1);
+      AP_ADD(ap1, b1);
+      tc_fence_after();
+      uint32_t sa[32], sb[32];
+      AP_T0(b2);
+      tmem_ld32(s_addr, sa);
+      tmem_ld32(s_addr + 32, sb);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);               // QK_{j+2} may overwrite the S buffer now
+      AP_ADD(ap2, b2);
+      AP_T0(b3);
+      const int valid = S - j * Cfg::BN;                    // real keys in this tile
+      if (valid < Cfg::BN) {                                // only in the last tile
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if (i >= valid) sa[i] = 0xff800000u;              // -inf
+          if (i + 32 >= valid) sb[i] = 0xff800000u;
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sa[i]), __uint_as_float(sb[i])));
+        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sa[i + 1]), __uint_as_float(sb[i + 1])));
+        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sa[i + 2]), __uint_as_float(sb[i + 2])));
+        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sa[i + 3]), __uint_as_float(sb[i + 3])));
+      }
+      const float m_tile = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale_log2;
+      // lazy rescale: keep the old reference max unless the new one is more than 2^8 larger
+      float alpha = 1.0f;
+      if (m_tile > m_run + 8.0f) {
+        alpha = ex2_approx(m_run - m_tile);                 // 0 on the first tile
+        m_run = m_tile;
+      }
+      AP_ADD(ap3, b3);
+      AP_T0(b4);
+      if (jl > 0) {
+        // PV of this stream's previous tile: P buffer free again, O accumulator quiescent
+        mbar_wait(&pv_done[g], (jl - 1) & 1);
+        if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < HD; c0 += 8) {     // rare path: small chunks keep the S registers resident
+            uint32_t o[8];
+            tmem_ld8(o_addr + c0, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st8(o_addr + c0, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      AP_ADD(ap4, b4);
+      AP_T0(b5);
+      // exp2(s * scale - m) on packed fp32 pairs: FFMA2 / FADD2 halve the non-MUFU issue slots
+      const uint64_t sc2 = f32x2_pack(scale_log2, scale_log2), nm2 = f32x2_pack(-m_run, -m_run);
+      uint64_t rsum[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {                         // 8 keys -> one 16-byte chunk of the P row
+        const uint32_t* src = c < 4 ? &sa[c * 8] : &sb[(c - 4) * 8];
+        uint32_t pk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint64_t x = f32x2_fma(f32x2_pack(__uint_as_float(src[2 * i]), __uint_as_float(src[2 * i + 1])), sc2, nm2);
+          float x0, x1;
+          f32x2_unpack(x, x0, x1);
+          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          rsum[i] = f32x2_add(rsum[i], f32x2_pack(p0, p1));
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        // K-major 128-B swizzled rows: 16-B chunk c lands at c ^ (r & 7)
+        st_shared_v4(prow + ((c ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+      }
+      {
+        const uint64_t t = f32x2_add(f32x2_add(rsum[0], rsum[1]), f32x2_add(rsum[2], rsum[3]));
+        float t0, t1;
+        f32x2_unpack(t, t0, t1);
+        l_run = l_run * alpha + (t0 + t1);
+      }
+      AP_ADD(ap5, b5);
+      AP_T0(b6);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      AP_ADD(ap6, b6);
+    }
+#ifdef VJ_ATTN_PROFILE
+    if (threadIdx.x == 0) {
+      atomicAdd(&g_attn_prof[0], (unsigned long long)(clock64() - ap_tot));
+      atomicAdd(&g_attn_prof[1], (unsigned long long)ap1);
+      atomicAdd(&g_attn_prof[2], (unsigned long long)ap2);
+      atomicAdd(&g_attn_prof[3], (unsigned long long)ap3);
+      atomicAdd(&g_attn_prof[4], (unsigned long long)ap4);
+      atomicAdd(&g_attn_prof[5], (unsigned long long)ap5);
+      atomicAdd(&g_attn_prof[6], (unsigned long long)ap6);
+      atomicAdd(&g_attn_prof[9], 1ull);
+    }
+#endif
+    // ---- merge the two streams: thread (r, g) finishes output columns [g*HO, g*HO+HO) of row r
+    const int n_mine = (n_tiles - g + 1) >> 1, n_peer = (n_tiles - (g ^ 1) + 1) >> 1;
+    const uint32_t xm = smem_u32(smem + Cfg::OFF_X);
+    st_shared_f32(xm + (g * 128 + r) * 4, m_run);
+    st_shared_f32(xm + (256 + g * 128 + r) * 4, l_run);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float m_peer = ld_shared_f32(xm + ((g ^ 1) * 128 + r) * 4);
+    const float l_peer = ld_shared_f32(xm + (256 + (g ^ 1) * 128 + r) * 4);
+    const float m_all = fmaxf(m_run, m_peer);
+    const float w_mine = n_mine > 0 ? ex2_approx(m_run - m_all) : 0.f;
+    const float w_peer = n_peer > 0 ? ex2_approx(m_peer - m_all) : 0.f;
+    const float l_tot = l_run * w_mine + l_peer * w_peer;
+    const float inv_l = 1.0f / l_tot;
+    const float w0 = (g == 0 ? w_mine : w_peer) * inv_l, w1 = (g == 0 ? w_peer : w_mine) * inv_l;
+    const int n0 = (n_tiles + 1) >> 1, n1 = n_tiles >> 1;
+    mbar_wait(&pv_done[0], (n0 - 1) & 1);
+    if (n1 > 0) mbar_wait(&pv_done[1], (n1 - 1) & 1);
+    tc_fence_after();
+    const int qrow = q0 + r;
+    bf16* orow = out + ((long long)b * S + qrow) * D + h * HD + g * HO;
+    {
+      uint32_t o0[HO], o1[HO];
+      tmem_ld_n<HO>(lane_addr + Cfg::O_COL + g * HO, o0);
+      if (n1 > 0) {
+        tmem_ld_n<HO>(lane_addr + Cfg::O_COL + HD + g * HO, o1);
+      } else {
+#pragma unroll
+        for (int i = 0; i < HO; ++i) o1[i] = 0u;
+      }
+      tmem_ld_wait();
+      if (qrow < S) {
+        float f[HO];
+#pragma unroll
+        for (int i = 0; i < HO; ++i) f[i] = __uint_as_float(o0[i]) * w0 + __uint_as_float(o1[i]) * w1;
+#pragma unroll
+        for (int i = 0; i < HO; i += 8) {
+          uint4 u;
+          u.x = pack_bf16x2(f[i], f[i + 1]);
+          u.y = pack_bf16x2(f[i + 2], f[i + 3]);
+          u.z = pack_bf16x2(f[i + 4], f[i + 5]);
+          u.w = pack_bf16x2(f[i + 6], f[i + 7]);
+          *reinterpret_cast<uint4*>(orow + i) = u;
+        }
+      }
+    }
+    if (g == 0 && qrow < S) lse[((long long)b * H + h) * S + qrow] = m_all + log2f(l_tot);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int HD>
+static int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int S, int H, cudaStream_t stream) {
+  using Cfg = AttnFwd2Cfg<HD>;
+  const int D = H * HD;
+  TMapPair tmQ, tmKV;
+  int r = make_head_tmaps<HD>(&tmQ, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, Cfg::BM);
+  if (r) return r;
+  r = make_head_tmaps<HD>(&tmKV, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, Cfg::BN);
+  if (r) return r;
+  auto kern = attn_fwd2_kernel<HD>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((S + Cfg::BM - 1) / Cfg::BM, H, B);
+  const float scale_log2 = (1.0f / sqrtf((float)HD)) * 1.4426950408889634f;
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmQ, tmKV, reinterpret_cast<bf16*>(out), lse, S, H, D, scale_log2);
+  VJ_LAUNCH_CHECK();
+  return 0;
 }
 
 template <int HD>
@@ -335,8 +694,8 @@ extern "C" int vj_attn_fwd(const void* qkv, void* out, float* lse, int B, int S,
   VJ_CHECK(B > 0 && S > 0 && H > 0, "vj_attn_fwd: bad shape B=%d S=%d H=%d", B, S, H);
   VJ_CHECK(B <= 65535 && H <= 65535, "vj_attn_fwd: B/H exceed grid limits");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (head_dim == 64) return launch_attn_fwd<64>(qkv, out, lse, B, S, H, st);
-  if (head_dim == 32) return launch_attn_fwd<32>(qkv, out, lse, B, S, H, st);
+  if (head_dim == 64) return launch_attn_fwd2<64>(qkv, out, lse, B, S, H, st);
+  if (head_dim == 32) return launch_attn_fwd2<32>(qkv, out, lse, B, S, H, st);
   if (head_dim == 80) return launch_attn_fwd<80>(qkv, out, lse, B, S, H, st);
   set_error("vj_attn_fwd: head_dim %d not supported (32, 64, 80)", head_dim);
   return -1;

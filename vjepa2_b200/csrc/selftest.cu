@@ -398,11 +398,12 @@ static void bench_attn(int B, int S, int H, int hd, bool bwd) {
 #ifdef VJ_ATTN_PROFILE
   vj_attn_prof_read(ap, 1);
   {
-    const double n = (double)ap[9], tiles = (double)((S + 63) / 64);
-    printf("      per CTA per KV tile (cycles): softmax total %.0f = wait S %.0f + tmem ld %.0f + max/exp/pack %.0f + wait PV %.0f"
-           " + O rescale %.0f + P store/arrive %.0f | MMA warp: total %.0f wait P %.0f wait KV %.0f\n",
+    // dual-stream kernel (hd 64/32): stream 0 of each CTA reports; it owns every other KV tile
+    const double n = (double)ap[9], tiles = (double)((((S + 63) / 64) + 1) / 2);
+    printf("      stream 0, per own KV tile (cycles): total %.0f = wait S %.0f + tmem ld/release %.0f + max %.0f + wait PV/rescale %.0f"
+           " + exp/pack/store %.0f + fence/arrive %.0f\n",
            ap[0] / n / tiles, ap[1] / n / tiles, ap[2] / n / tiles, ap[3] / n / tiles, ap[4] / n / tiles, ap[5] / n / tiles,
-           ap[6] / n / tiles, ap[10] / n / tiles, ap[7] / n / tiles, ap[8] / n / tiles);
+           ap[6] / n / tiles);
   }
 #endif
   if (bwd) {
@@ -475,6 +476,20 @@ int main(int argc, char** argv) {
     bench_gemm("pred proj wgrad", 384, 384, 36000, 1, 1, VJ_EPI_OUT_F32 | VJ_EPI_RES_F32 | VJ_EPI_RESIDUAL);
     bench_gemm("8192^3", 8192, 8192, 8192, 0, 0, 0);
     bench_attn(24, 2048, 22, 64, false);
+  }
+  if (!strcmp(what, "stressattn")) {   // back-to-back launches (CTAs of consecutive launches overlap on the SMs)
+    const int reps = argc > 2 ? atoi(argv[2]) : 20;
+    for (int i = 0; i < reps; ++i) {
+      bench_attn(24, 2048, 22, 64, false);
+      bench_attn(24, 504, 22, 64, i % 4 == 0);
+      bench_attn(24, 1448, 12, 32, i % 4 == 1);
+      bench_attn(3, 200, 5, 64, false);
+    }
+  }
+  if (!strcmp(what, "benchattn")) {
+    bench_attn(24, 2048, 22, 64, false);
+    bench_attn(24, 2048, 12, 32, false);
+    bench_attn(24, 504, 22, 64, true);
   }
   if (all || !strcmp(what, "benchbwd")) {
     bench_attn(24, 504, 22, 64, true);
