@@ -409,7 +409,7 @@ attn_fwd2_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ T
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (warp == 8) {
-      // -------------------------------------------------------------- TMA producer
+      // -------------------------------------------------------------- TMA producer: Q, then the K ring
       if (elect_one()) {
         tma_prefetch_desc(&tmQ.m[0]);
         tma_prefetch_desc(&tmKV.m[0]);
@@ -417,11 +417,18 @@ attn_fwd2_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ T
         tma_load_head_tile<HD>(sQ, &tmQ, q_full, Cfg::BM, h * HD, q0, b);
         for (int j = 0; j < n_tiles; ++j) {
           const int st = j % NST;
-          const uint32_t ph = (j / NST) & 1;
-          mbar_wait(&k_empty[st], ph ^ 1);
+          mbar_wait(&k_empty[st], ((j / NST) & 1) ^ 1);
           mbar_expect_tx(&k_full[st], Cfg::KV_BYTES);
           tma_load_head_tile<HD>(sK + st * Cfg::KV_BYTES, &tmKV, &k_full[st], Cfg::BN, D + h * HD, j * Cfg::BN, b);
-          mbar_wait(&v_empty[st], ph ^ 1);
+        }
+      }
+    } else if (warp == 10) {
+      // -------------------------------------------------------------- TMA producer: the V ring (own warp: QK runs
+      // up to four tiles ahead of PV, so K refills must not queue behind V refills)
+      if (elect_one()) {
+        for (int j = 0; j < n_tiles; ++j) {
+          const int st = j % NST;
+          mbar_wait(&v_empty[st], ((j / NST) & 1) ^ 1);
           mbar_expect_tx(&v_full[st], Cfg::KV_BYTES);
           tma_load_head_tile<HD>(sV + st * Cfg::KV_BYTES, &tmKV, &v_full[st], Cfg::BN, 2 * D + h * HD, j * Cfg::BN, b);
         }
@@ -431,7 +438,6 @@ attn_fwd2_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ T
       // One warp consumes the K ring (QK_0, QK_1, QK_2, ...) and the V ring (PV_0, PV_1, ...) strictly in tile
       // order, so every parity wait on a ring stage follows the wait on that stage's previous fill.  (Two
       // issuers, one per stream, skip every other fill of a stage and their parity waits can pass vacuously.)
-      // The fixed order QK_{t+2}, PV_t also keeps the two streams half a period apart.
       constexpr uint32_t idesc_qk = make_idesc(128, Cfg::BN, false, false);
       const uint64_t pd0 = desc_kmajor<128>(smem_u32(sP));
       mbar_wait(q_full, 0);
@@ -447,26 +453,36 @@ attn_fwd2_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ T
         }
         __syncwarp();
       };
-      issue_qk(0);
-      if (n_tiles > 1) issue_qk(1);
-      for (int t = 0; t < n_tiles; ++t) {
-        const int g = t & 1, jl = t >> 1;
-        if (t + 2 < n_tiles) {                   // S buffer g is free once the stream holds S_t in registers
-          mbar_wait(&s_free[g], jl & 1);
-          issue_qk(t + 2);
-        }
-        const int st = t % NST;
-        mbar_wait(&v_full[st], (t / NST) & 1);
-        mbar_wait(&p_full[g], jl & 1);
+      auto issue_pv = [&](int t) {
+        const int g = t & 1, st = t % NST;
         tc_fence_after();
         if (elect_one()) {
           const uint64_t pd = desc_advance(pd0, g * Cfg::P_BYTES);
           mma_into_hd<HD, false, Cfg::BN>(tmem_base + Cfg::O_COL + g * HD, [&](int k) { return desc_advance(pd, k * 32); },
-                                          smem_u32(sV + st * Cfg::KV_BYTES), jl != 0);
+                                          smem_u32(sV + st * Cfg::KV_BYTES), t >= 2);
           umma_commit(&v_empty[st]);
           umma_commit(&pv_done[g]);
         }
         __syncwarp();
+      };
+      // Issue order = the order in which the events occur when the two streams run half a period apart:
+      //   QK_0 QK_1 | s_free(0): QK_2 | s_free(1): QK_3 | p_full(0): PV_0 | s_free(2): QK_4 | p_full(1): PV_1 | ...
+      // so S_{t+4} is requested as soon as its buffer has been drained, a full tile before the stream needs it.
+      auto qk_after_drain = [&](int t) {        // QK_t overwrites the S buffer that held S_{t-2}
+        if (t < n_tiles) {
+          mbar_wait(&s_free[t & 1], ((t - 2) >> 1) & 1);
+          issue_qk(t);
+        }
+      };
+      issue_qk(0);
+      if (n_tiles > 1) issue_qk(1);
+      qk_after_drain(2);
+      qk_after_drain(3);
+      for (int t = 0; t < n_tiles; ++t) {
+        mbar_wait(&v_full[t % NST], (t / NST) & 1);
+        mbar_wait(&p_full[t & 1], (t >> 1) & 1);
+        issue_pv(t);
+        qk_after_drain(t + 4);
       }
     }
   } else {

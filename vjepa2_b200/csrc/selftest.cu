@@ -487,6 +487,7 @@ int main(int argc, char** argv) {
     }
   }
   if (!strcmp(what, "benchattn")) {
+    bench_attn(6, 8192, 22, 64, false);
     bench_attn(24, 2048, 22, 64, false);
     bench_attn(24, 2048, 12, 32, false);
     bench_attn(24, 504, 22, 64, true);
