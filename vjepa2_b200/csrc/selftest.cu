@@ -404,6 +404,10 @@ static void bench_attn(int B, int S, int H, int hd, bool bwd) {
            " + exp/pack/store %.0f + fence/arrive %.0f\n",
            ap[0] / n / tiles, ap[1] / n / tiles, ap[2] / n / tiles, ap[3] / n / tiles, ap[4] / n / tiles, ap[5] / n / tiles,
            ap[6] / n / tiles);
+    const double nt = n * (double)((S + 63) / 64);
+    printf("      QK warp, per KV tile (cycles): total %.0f = wait K %.0f + wait Q %.0f + wait S-drain %.0f + issue/other | PV warp: total %.0f"
+           " = wait P %.0f + wait V %.0f + wait O-drain %.0f + issue/other\n",
+           ap[10] / nt, ap[8] / nt, ap[11] / nt, ap[12] / nt, ap[15] / nt, ap[7] / nt, ap[13] / nt, ap[14] / nt);
   }
 #endif
   if (bwd) {
@@ -452,6 +456,8 @@ int main(int argc, char** argv) {
     test_attn(1, 700, 3, 32, false);
     test_attn(2, 200, 2, 80, false);
     test_attn(1, 1000, 3, 80, false);
+    test_attn(5, 330, 24, 64, false);    // 360 work items (> 2 per SM): persistent CTAs walk several items, odd tile count
+    test_attn(7, 64, 50, 32, false);     // single-tile items, 350 of them
   }
   if (all || !strcmp(what, "attnbwd")) {
     test_attn(1, 128, 1, 64, true);
