@@ -23,6 +23,18 @@
 
 namespace vj {
 
+// Optional in-kernel cycle accounting (-DVJ_ATTN_PROFILE), compute warp 0 of every CTA:
+//  [0] CTA total [1] until first S^T/dP^T (prologue) [2] wait sdp [3] tmem ld [4] math [5] wait dq_full
+//  [6] stage dQ [7] P/dS store+fence [8] barriers [9] CTAs [10] epilogue (last drain + dK/dV)
+#ifdef VJ_ATTN_PROFILE
+__device__ unsigned long long g_attn_bwd_prof[16];
+#define BP_T0(v) const long long v = clock64()
+#define BP_ADD(acc, v) acc += clock64() - v
+#else
+#define BP_T0(v)
+#define BP_ADD(acc, v)
+#endif
+
 template <int HD>
 struct AttnBwdCfg {
   static constexpr int BT = 128;                       // keys per CTA == queries per iteration
@@ -351,6 +363,354 @@ attn_bwd_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__ 
   if (warp == 8) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Pipelined variant (head_dim 64 / 32).  The kernel above runs each query tile as one dependent chain
+//   S^T,dP^T (MMA) -> P^T,dS^T (compute) -> dV,dK,dQ (MMA) -> dQ drain (compute)
+// and the tensor pipe idles through both compute phases (17 % active in ncu).  With one CTA per SM there are
+// 200 registers per thread to spend, so here a compute thread copies its 64 S^T and 64 dP^T values out of TMEM
+// at once and releases the TMEM tiles (sdp_free): the MMA warp computes S^T,dP^T of tile i+1 while the
+// compute warps are still busy with tile i, and dV,dK,dQ of tile i while they start on tile i+1.  The dQ drain of
+// tile i-1 is folded into tile i (after the exp math, when dq_full(i-1) has long fired), with its own fp32
+// staging buffer so the TMA reduce-add overlaps the next tile.  Per element: one FFMA2 + MUFU.EX2 for P, one
+// FFMA2 + FMUL2 for dS (the 1/sqrt(d) factor of dQ and dK is folded into dS), per-column -lse / -delta*scale
+// come from smem as 128-bit broadcast loads.
+template <int HD>
+struct AttnBwd2Cfg {
+  static constexpr int BT = 128;
+  static constexpr int TILE_BYTES = BT * HD * 2;
+  static constexpr int PT_BYTES = BT * BT * 2;
+  static constexpr int DQ_BYTES = BT * HD * 4;
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + TILE_BYTES;
+  static constexpr int QDO_STAGES = 3;                   // Q_i / dO_i ring: tile i+1 must already be in flight while
+                                                         // the MMAs of tile i-1 still read theirs
+  static constexpr int OFF_Q = OFF_V + TILE_BYTES;
+  static constexpr int OFF_DO = OFF_Q + QDO_STAGES * TILE_BYTES;
+  static constexpr int OFF_PT = OFF_DO + QDO_STAGES * TILE_BYTES;
+  static constexpr int OFF_DS = OFF_PT + PT_BYTES;
+  static constexpr int OFF_DQ = OFF_DS + PT_BYTES;       // fp32 dQ staging: [HD/32 atoms][128 rows][128 B]
+  static constexpr int OFF_LSE = OFF_DQ + DQ_BYTES;      // [tile parity][-lse | -delta*scale][128] floats
+  static constexpr int OFF_BAR = OFF_LSE + 2 * 2 * 128 * 4;
+  // no alignment slack: the dynamic window starts 1024-B aligned (checked at kernel entry), and at head_dim 64
+  // the layout needs all but 768 bytes of the 227 KB
+  static constexpr int SMEM_BYTES = OFF_BAR + 256;
+  static constexpr int COL_ST = 0, COL_DPT = 128, COL_DV = 256, COL_DK = 256 + HD, COL_DQ = 256 + 2 * HD;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(HD == 64 || HD == 32, "pipelined backward: head_dim 64 or 32");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(320, 1)
+attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__ TMapPair tmDO,
+                 const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse,
+                 const float* __restrict__ delta, bf16* __restrict__ dqkv, const __half* __restrict__ rope, int S, int H,
+                 int D, float scale, float scale_log2) {
+  using Cfg = AttnBwd2Cfg<HD>;
+  constexpr int HO = HD / 2;                               // output columns per compute thread
+  constexpr int NST = Cfg::QDO_STAGES;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) {                    // swizzled tiles need 1024-B aligned bases
+    if (threadIdx.x == 0) printf("vjepa2_b200: attn_bwd2: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint8_t* sK = smem + Cfg::OFF_K;
+  uint8_t* sV = smem + Cfg::OFF_V;
+  uint8_t* sQ = smem + Cfg::OFF_Q;
+  uint8_t* sDO = smem + Cfg::OFF_DO;
+  uint8_t* sPT = smem + Cfg::OFF_PT;
+  uint8_t* sDS = smem + Cfg::OFF_DS;
+  uint8_t* sDQ = smem + Cfg::OFF_DQ;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* kv_full = bars;                  // 1
+  uint64_t* qdo_full = bars + 1;             // NST
+  uint64_t* qdo_empty = qdo_full + NST;      // NST
+  uint64_t* sdp_full = qdo_empty + NST;      // 1: S^T, dP^T of tile i are in TMEM
+  uint64_t* sdp_free = sdp_full + 1;         // 1 (8 warp arrivals): ... and have been copied to registers
+  uint64_t* pds_full = sdp_free + 1;         // 1 (8 warp arrivals): P^T, dS^T of tile i are in smem
+  uint64_t* dq_full = pds_full + 1;          // 1: dV, dK, dQ MMAs of tile i retired (P^T/dS^T smem free, dQ_i in TMEM)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int k0 = blockIdx.x * Cfg::BT;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_q = (S + Cfg::BT - 1) / Cfg::BT;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < NST; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(sdp_free, 8);
+    mbar_init(pds_full, 8);
+    mbar_init(dq_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      tma_prefetch_desc(&tmQKV.m[0]);
+      tma_prefetch_desc(&tmDO.m[0]);
+      mbar_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
+      tma_load_head_tile<HD>(sK, &tmQKV, kv_full, Cfg::BT, D + h * HD, k0, b);
+      tma_load_head_tile<HD>(sV, &tmQKV, kv_full, Cfg::BT, 2 * D + h * HD, k0, b);
+      for (int i = 0; i < n_q; ++i) {
+        const int st = i % NST;
+        mbar_wait(&qdo_empty[st], ((i / NST) & 1) ^ 1);
+        mbar_expect_tx(&qdo_full[st], 2 * Cfg::TILE_BYTES);
+        tma_load_head_tile<HD>(sQ + st * Cfg::TILE_BYTES, &tmQKV, &qdo_full[st], Cfg::BT, h * HD, i * Cfg::BT, b);
+        tma_load_head_tile<HD>(sDO + st * Cfg::TILE_BYTES, &tmDO, &qdo_full[st], Cfg::BT, h * HD, i * Cfg::BT, b);
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------------------------------------------------------- MMA issuer
+    //   S,dP(0) | sdp_free(0): S,dP(1) | pds_full(0): dV,dK,dQ(0) | sdp_free(1): S,dP(2) | pds_full(1): dV,dK,dQ(1) ...
+    constexpr uint32_t id_s = make_idesc(128, 128, false, false);
+    const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+    const uint64_t pt_k = desc_kmajor<128>(smem_u32(sPT));
+    const uint64_t ds_k = desc_kmajor<128>(smem_u32(sDS));
+    const uint64_t ds_mn = desc_mnmajor<128>(smem_u32(sDS), 16384);
+    auto issue_sdp = [&](int i) {
+      const int st = i % NST;
+      mbar_wait(&qdo_full[st], (i / NST) & 1);
+      if (i > 0) mbar_wait(sdp_free, (i - 1) & 1);          // tile i-1 left TMEM for the compute warps' registers
+      tc_fence_after();
+      if (elect_one()) {
+        mma_over_hd<HD>(tmem_base + Cfg::COL_ST, k_addr, Cfg::BT, smem_u32(sQ + st * Cfg::TILE_BYTES), Cfg::BT, id_s);
+        mma_over_hd<HD>(tmem_base + Cfg::COL_DPT, v_addr, Cfg::BT, smem_u32(sDO + st * Cfg::TILE_BYTES), Cfg::BT, id_s);
+        umma_commit(sdp_full);
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    issue_sdp(0);
+    for (int i = 0; i < n_q; ++i) {
+      const int st = i % NST;
+      if (i + 1 < n_q) issue_sdp(i + 1);
+      mbar_wait(pds_full, i & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
+        const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
+        // dV += P^T dO ; dK += dS^T Q   (A: K-major 2-atom tiles, k-step k lives in atom k/4)
+        mma_into_hd<HD, false, Cfg::BT>(tmem_base + Cfg::COL_DV,
+                                        [&](int k) { return desc_advance(pt_k, (k >> 2) * 16384 + (k & 3) * 32); },
+                                        do_addr, i != 0);
+        mma_into_hd<HD, false, Cfg::BT>(tmem_base + Cfg::COL_DK,
+                                        [&](int k) { return desc_advance(ds_k, (k >> 2) * 16384 + (k & 3) * 32); },
+                                        q_addr, i != 0);
+        // dQ_i = dS K   (A: the same dS^T buffer read MN-major)
+        mma_into_hd<HD, true, Cfg::BT>(tmem_base + Cfg::COL_DQ, [&](int k) { return desc_advance(ds_mn, k * 2048); },
+                                       k_addr, false);
+        umma_commit(&qdo_empty[st]);
+        umma_commit(dq_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------------------------------------------------------- compute warps
+    const int r = threadIdx.x & 127;                        // key row == TMEM lane
+    const int half = threadIdx.x >> 7;                      // query columns [64*half, 64*half + 64)
+    const int lane = threadIdx.x & 31;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const float* lse_bh = lse + ((long long)b * H + h) * S;
+    const float* delta_bh = delta + ((long long)b * H + h) * S;
+    const uint32_t s_col = smem_u32(smem + Cfg::OFF_LSE);
+    const uint32_t pt_row = smem_u32(sPT) + half * 16384 + r * 128;     // this thread's 64 columns = atom `half`
+    const uint32_t ds_row = smem_u32(sDS) + half * 16384 + r * 128;
+    const int swz = r & 7;
+    const uint64_t sc2 = f32x2_pack(scale_log2, scale_log2), s2 = f32x2_pack(scale, scale);
+
+    // dQ_j (TMEM) -> fp32 staging tile; lane r == query row r of tile j
+    auto stage_dq = [&]() {
+      uint32_t o[HO];
+      tmem_ld_n<HO>(lane_addr + Cfg::COL_DQ + half * HO, o);
+      tmem_ld_wait();
+      // 128-byte swizzled atoms of 32 fp32: HD = 64 -> atom = half (8 chunks); HD = 32 -> one atom, 4 chunks each
+      const uint32_t rowp = smem_u32(sDQ) + (HO == 32 ? half * 16384 : 0) + r * 128;
+      const int cbase = HO == 32 ? 0 : half * 4;
+#pragma unroll
+      for (int u = 0; u < HO / 4; ++u)
+        st_shared_v4(rowp + (((cbase + u) ^ swz) << 4), o[u * 4], o[u * 4 + 1], o[u * 4 + 2], o[u * 4 + 3]);
+    };
+    auto reduce_dq = [&](int j) {                           // one thread: TMA reduce-add the staged tile into dq_acc
+#pragma unroll
+      for (int a = 0; a < HD / 32; ++a) tma_reduce_add_3d(&tmDQ, sDQ + a * 16384, h * HD + a * 32, j * Cfg::BT, b);
+      bulk_commit_bwd();
+    };
+
+    long long bp2 = 0, bp3 = 0, bp4 = 0, bp5 = 0, bp6 = 0, bp7 = 0, bp8 = 0, bp1 = 0;
+    (void)bp1; (void)bp2; (void)bp3; (void)bp4; (void)bp5; (void)bp6; (void)bp7; (void)bp8;
+    BP_T0(bp_all);
+    // per-column -lse and -delta*scale of query tile j -> smem (parity j & 1); written one tile ahead, published by
+    // the barrier that closes the previous tile
+    auto load_cols = [&](int j) {
+      if (half == 0 && j < n_q) {
+        const uint32_t dst = s_col + (j & 1) * 1024;
+        const int q = j * Cfg::BT + r;
+        st_shared_f32(dst + r * 4, q < S ? -lse_bh[q] : -INFINITY);
+        st_shared_f32(dst + 512 + r * 4, q < S ? -delta_bh[q] * scale : 0.f);
+      }
+    };
+    load_cols(0);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    for (int i = 0; i < n_q; ++i) {
+      const uint32_t s_par = s_col + (i & 1) * 1024;
+      load_cols(i + 1);
+      BP_T0(c2);
+      mbar_wait(sdp_full, i & 1);
+      if (i == 0) { BP_ADD(bp1, bp_all); } else { BP_ADD(bp2, c2); }
+      tc_fence_after();
+      BP_T0(c3);
+      uint32_t sv[64], dv[64];
+      tmem_ld32(lane_addr + Cfg::COL_ST + half * 64, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
+      tmem_ld32(lane_addr + Cfg::COL_ST + half * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
+      tmem_ld32(lane_addr + Cfg::COL_DPT + half * 64, reinterpret_cast<uint32_t(&)[32]>(dv[0]));
+      tmem_ld32(lane_addr + Cfg::COL_DPT + half * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(dv[32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_free);                 // S^T, dP^T of tile i+1 may be computed now
+      BP_ADD(bp3, c3);
+      BP_T0(c4);
+      // P = exp2(s*scale*log2e - lse), dS = P * (dP - delta) * scale, on packed fp32 pairs.  Rows of keys >= S and
+      // columns of queries >= S need no masking: their K / V / Q / dO rows are TMA zero-fill and lse = +inf there,
+      // so every product they reach is an exact zero or lands in a dK / dV row that is never stored.
+      uint32_t pp[32], dd[32];
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        uint32_t nl[4], nd[4];
+        ld_shared_v4(s_par + (half * 64 + j) * 4, nl);
+        ld_shared_v4(s_par + 512 + (half * 64 + j) * 4, nd);
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+          const uint64_t x = f32x2_fma(f32x2_pack(__uint_as_float(sv[j + e]), __uint_as_float(sv[j + e + 1])), sc2,
+                                       f32x2_pack(__uint_as_float(nl[e]), __uint_as_float(nl[e + 1])));
+          float x0, x1;
+          f32x2_unpack(x, x0, x1);
+          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+          const uint64_t t = f32x2_fma(f32x2_pack(__uint_as_float(dv[j + e]), __uint_as_float(dv[j + e + 1])), s2,
+                                       f32x2_pack(__uint_as_float(nd[e]), __uint_as_float(nd[e + 1])));
+          const uint64_t d = f32x2_mul(f32x2_pack(p0, p1), t);
+          float d0, d1;
+          f32x2_unpack(d, d0, d1);
+          pp[(j + e) >> 1] = pack_bf16x2(p0, p1);
+          dd[(j + e) >> 1] = pack_bf16x2(d0, d1);
+        }
+      }
+      BP_ADD(bp4, c4);
+      {
+        // the staging tile is free once the TMA has read dQ_{i-2} out of it (issued a whole tile ago); this
+        // barrier also publishes the column constants of tile i+1
+        BP_T0(c8);
+        if (threadIdx.x == 128 && i > 1) bulk_wait_read0_bwd();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        BP_ADD(bp8, c8);
+      }
+      if (i > 0) {
+        // MMAs of tile i-1 retired: P^T / dS^T smem may be overwritten, dQ_{i-1} waits in TMEM
+        BP_T0(c5);
+        mbar_wait(dq_full, (i - 1) & 1);
+        BP_ADD(bp5, c5);
+        tc_fence_after();
+        BP_T0(c6);
+        stage_dq();
+        BP_ADD(bp6, c6);
+      }
+      BP_T0(c7);
+      // 8 x 16-byte chunks per buffer: chunk u of this thread's 128-byte row lands at u ^ (r & 7)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        st_shared_v4(pt_row + ((u ^ swz) << 4), pp[u * 4], pp[u * 4 + 1], pp[u * 4 + 2], pp[u * 4 + 3]);
+        st_shared_v4(ds_row + ((u ^ swz) << 4), dd[u * 4], dd[u * 4 + 1], dd[u * 4 + 2], dd[u * 4 + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+      BP_ADD(bp7, c7);
+      if (i > 0) {
+        BP_T0(c9);
+        asm volatile("bar.sync 2, 256;" ::: "memory");     // every thread's part of the staged dQ_{i-1} is fenced
+        if (threadIdx.x == 128) reduce_dq(i - 1);          // (the thread that waits on the bulk group above)
+        BP_ADD(bp8, c9);
+      }
+    }
+    BP_T0(c10);
+    // drain the last dQ tile
+    mbar_wait(dq_full, (n_q - 1) & 1);
+    tc_fence_after();
+    if (threadIdx.x == 128 && n_q > 1) bulk_wait_read0_bwd();
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    stage_dq();
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 2, 256;" ::: "memory");
+    if (threadIdx.x == 128) {
+      reduce_dq(n_q - 1);
+      bulk_wait_all0_bwd();
+    }
+    // dK / dV epilogue (all MMAs retired); the 1/sqrt(d) factor is already in dS
+    const int key = k0 + r;
+    bf16* dk_row = dqkv + ((long long)b * S + key) * 3 * D + D + h * HD + half * HO;
+    bf16* dv_row = dk_row + D;
+    constexpr int NV = HO / 8;
+    uint32_t a[HO], c[HO];
+    tmem_ld_n<HO>(lane_addr + Cfg::COL_DK + half * HO, a);
+    tmem_ld_n<HO>(lane_addr + Cfg::COL_DV + half * HO, c);
+    tmem_ld_wait();
+    if (key < S) {
+      const __half* tr = rope ? rope + ((long long)b * S + key) * 2 * HD + half * HO : nullptr;
+#pragma unroll
+      for (int jj = 0; jj < NV; ++jj) {
+        const int j = jj * 8;
+        uint4 u, w;
+        float gk[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gk[e] = __uint_as_float(a[j + e]);
+        if (rope) rope_adjoint8(gk, *reinterpret_cast<const uint4*>(tr + j), *reinterpret_cast<const uint4*>(tr + HD + j));
+        u.x = pack_bf16x2(gk[0], gk[1]);
+        u.y = pack_bf16x2(gk[2], gk[3]);
+        u.z = pack_bf16x2(gk[4], gk[5]);
+        u.w = pack_bf16x2(gk[6], gk[7]);
+        w.x = pack_bf16x2(__uint_as_float(c[j]), __uint_as_float(c[j + 1]));
+        w.y = pack_bf16x2(__uint_as_float(c[j + 2]), __uint_as_float(c[j + 3]));
+        w.z = pack_bf16x2(__uint_as_float(c[j + 4]), __uint_as_float(c[j + 5]));
+        w.w = pack_bf16x2(__uint_as_float(c[j + 6]), __uint_as_float(c[j + 7]));
+        *reinterpret_cast<uint4*>(dk_row + j) = u;
+        *reinterpret_cast<uint4*>(dv_row + j) = w;
+      }
+    }
+#ifdef VJ_ATTN_PROFILE
+    if (threadIdx.x == 0) {
+      atomicAdd(&g_attn_bwd_prof[0], (unsigned long long)(clock64() - bp_all));
+      atomicAdd(&g_attn_bwd_prof[1], (unsigned long long)bp1);
+      atomicAdd(&g_attn_bwd_prof[2], (unsigned long long)bp2);
+      atomicAdd(&g_attn_bwd_prof[3], (unsigned long long)bp3);
+      atomicAdd(&g_attn_bwd_prof[4], (unsigned long long)bp4);
+      atomicAdd(&g_attn_bwd_prof[5], (unsigned long long)bp5);
+      atomicAdd(&g_attn_bwd_prof[6], (unsigned long long)bp6);
+      atomicAdd(&g_attn_bwd_prof[7], (unsigned long long)bp7);
+      atomicAdd(&g_attn_bwd_prof[8], (unsigned long long)bp8);
+      atomicAdd(&g_attn_bwd_prof[9], 1ull);
+      atomicAdd(&g_attn_bwd_prof[10], (unsigned long long)(clock64() - c10));
+    }
+#endif
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
 template <int HD>
 static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, const float* lse, void* dqkv,
                            void* scratch, const void* rope, int B, int S, int H, cudaStream_t stream) {
@@ -380,17 +740,30 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
     int r = make_tmap(&tmDQ, dq_acc, VJ_F32, 3, dims, strides, box, Cfg::DQ_DENSE ? 0 : 128);
     if (r) return r;
   }
-  auto kern = attn_bwd_kernel<HD>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
   dim3 grid((S + Cfg::BT - 1) / Cfg::BT, H, B);
   const float scale = 1.0f / sqrtf((float)HD);
-  kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, reinterpret_cast<bf16*>(dqkv),
-                                              reinterpret_cast<const __half*>(rope), S, H, D, scale,
-                                              scale * 1.4426950408889634f);
+  if constexpr (HD == 80) {
+    auto kern = attn_bwd_kernel<HD>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+      attr_set = true;
+    }
+    kern<<<grid, 320, Cfg::SMEM_BYTES, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, reinterpret_cast<bf16*>(dqkv),
+                                                reinterpret_cast<const __half*>(rope), S, H, D, scale,
+                                                scale * 1.4426950408889634f);
+  } else {
+    using Cfg2 = AttnBwd2Cfg<HD>;
+    auto kern = attn_bwd2_kernel<HD>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
+      attr_set = true;
+    }
+    kern<<<grid, 320, Cfg2::SMEM_BYTES, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, reinterpret_cast<bf16*>(dqkv),
+                                                 reinterpret_cast<const __half*>(rope), S, H, D, scale,
+                                                 scale * 1.4426950408889634f);
+  }
   VJ_LAUNCH_CHECK();
   {
     const long long n = (long long)B * S * (D / 8);
@@ -402,6 +775,18 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
 }
 
 }  // namespace vj
+
+#ifdef VJ_ATTN_PROFILE
+extern "C" int vj_attn_bwd_prof_read(unsigned long long* out16, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, vj::g_attn_bwd_prof, 16 * sizeof(unsigned long long));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(vj::g_attn_bwd_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 extern "C" size_t vj_attn_bwd_scratch(int B, int S, int H, int head_dim) {
   return ((size_t)B * S * H * head_dim + (size_t)B * H * S) * sizeof(float);

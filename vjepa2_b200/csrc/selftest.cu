@@ -365,6 +365,7 @@ static void bench_gemm(const char* name, long long M, long long N, long long K, 
 
 #ifdef VJ_ATTN_PROFILE
 extern "C" int vj_attn_prof_read(unsigned long long* out16, int reset);
+extern "C" int vj_attn_bwd_prof_read(unsigned long long* out16, int reset);
 #endif
 
 static void bench_attn(int B, int S, int H, int hd, bool bwd) {
@@ -413,6 +414,9 @@ static void bench_attn(int B, int S, int H, int hd, bool bwd) {
   if (bwd) {
     for (int i = 0; i < 2; ++i) VJ(vj_attn_bwd(qkv, out, dout, lse, dqkv, scratch, nullptr, B, S, H, hd, 0));
     CK(cudaDeviceSynchronize());
+#ifdef VJ_ATTN_PROFILE
+    { unsigned long long z[16]; vj_attn_bwd_prof_read(z, 1); }
+#endif
     cudaEventRecord(e0);
     for (int i = 0; i < iters; ++i) VJ(vj_attn_bwd(qkv, out, dout, lse, dqkv, scratch, nullptr, B, S, H, hd, 0));
     cudaEventRecord(e1);
@@ -421,6 +425,18 @@ static void bench_attn(int B, int S, int H, int hd, bool bwd) {
     ms /= iters;
     printf("[bench attn bwd] B=%d S=%d H=%d hd=%d  %.3f ms  %.1f TFLOP/s (2.5x fwd flops)\n", B, S, H, hd, ms,
            2.5 * fl / ms * 1e-9);
+#ifdef VJ_ATTN_PROFILE
+    {
+      unsigned long long bp[16];
+      vj_attn_bwd_prof_read(bp, 1);
+      const double n = (double)bp[9], it = (double)((S + 127) / 128);
+      if (n > 0)
+        printf("      per CTA (cycles): total %.0f = prologue %.0f + %d x [barriers %.0f + wait S/dP %.0f + tmem ld %.0f + math %.0f"
+               " + wait dQ %.0f + stage dQ %.0f + P/dS store %.0f] + epilogue %.0f\n",
+               bp[0] / n, bp[1] / n, (int)it, bp[8] / n / it, bp[2] / n / it, bp[3] / n / it, bp[4] / n / it, bp[5] / n / it,
+               bp[6] / n / it, bp[7] / n / it, bp[10] / n);
+    }
+#endif
   }
   cudaFree(qkv); cudaFree(out); cudaFree(dout); cudaFree(dqkv); cudaFree(lse); cudaFree(scratch);
 }
