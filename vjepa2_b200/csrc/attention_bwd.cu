@@ -364,7 +364,7 @@ attn_bwd_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Pipelined variant (head_dim 64 / 32).  The kernel above runs each query tile as one dependent chain
+// Pipelined persistent variant (head_dim 64 / 32).  The kernel above runs each query tile as one dependent chain
 //   S^T,dP^T (MMA) -> P^T,dS^T (compute) -> dV,dK,dQ (MMA) -> dQ drain (compute)
 // and the tensor pipe idles through both compute phases (17 % active in ncu).  With one CTA per SM there are
 // 200 registers per thread to spend, so here a compute thread copies its 64 S^T and 64 dP^T values out of TMEM
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(320, 1)
 attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__ TMapPair tmDO,
                  const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse,
                  const float* __restrict__ delta, bf16* __restrict__ dqkv, const __half* __restrict__ rope, int S, int H,
-                 int D, float scale, float scale_log2) {
+                 int D, float scale, float scale_log2, int n_kt, int n_items) {
   using Cfg = AttnBwd2Cfg<HD>;
   constexpr int HO = HD / 2;                               // output columns per compute thread
   constexpr int NST = Cfg::QDO_STAGES;
@@ -423,22 +423,25 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
   uint8_t* sDS = smem + Cfg::OFF_DS;
   uint8_t* sDQ = smem + Cfg::OFF_DQ;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* kv_full = bars;                  // 1
-  uint64_t* qdo_full = bars + 1;             // NST
+  uint64_t* kv_full = bars;                  // 1: K, V of the work item landed
+  uint64_t* kv_empty = bars + 1;             // 1: the item's last MMAs retired (K, V smem free)
+  uint64_t* qdo_full = bars + 2;             // NST
   uint64_t* qdo_empty = qdo_full + NST;      // NST
-  uint64_t* sdp_full = qdo_empty + NST;      // 1: S^T, dP^T of tile i are in TMEM
+  uint64_t* sdp_full = qdo_empty + NST;      // 1: S^T, dP^T of tile G are in TMEM
   uint64_t* sdp_free = sdp_full + 1;         // 1 (8 warp arrivals): ... and have been copied to registers
-  uint64_t* pds_full = sdp_free + 1;         // 1 (8 warp arrivals): P^T, dS^T of tile i are in smem
-  uint64_t* dq_full = pds_full + 1;          // 1: dV, dK, dQ MMAs of tile i retired (P^T/dS^T smem free, dQ_i in TMEM)
+  uint64_t* pds_full = sdp_free + 1;         // 1 (8 warp arrivals): P^T, dS^T of tile G are in smem
+  uint64_t* dq_full = pds_full + 1;          // 1: dV, dK, dQ MMAs of tile G retired (P^T/dS^T smem free, dQ_G in TMEM)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dq_full + 1);
 
+  // Persistent CTA: work items (key tile, head, sample) = blockIdx.x, +gridDim.x, ...; the query tiles of all its
+  // items are numbered G = 0, 1, 2, ... and ring stages / barrier phases follow G straight through item boundaries.
   const int warp = threadIdx.x >> 5;
-  const int k0 = blockIdx.x * Cfg::BT;
-  const int h = blockIdx.y, b = blockIdx.z;
   const int n_q = (S + Cfg::BT - 1) / Cfg::BT;
+  const int n_my = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
     for (int i = 0; i < NST; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(sdp_full, 1);
     mbar_init(sdp_free, 8);
@@ -460,29 +463,38 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
     if (elect_one()) {
       tma_prefetch_desc(&tmQKV.m[0]);
       tma_prefetch_desc(&tmDO.m[0]);
-      mbar_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
-      tma_load_head_tile<HD>(sK, &tmQKV, kv_full, Cfg::BT, D + h * HD, k0, b);
-      tma_load_head_tile<HD>(sV, &tmQKV, kv_full, Cfg::BT, 2 * D + h * HD, k0, b);
-      for (int i = 0; i < n_q; ++i) {
-        const int st = i % NST;
-        mbar_wait(&qdo_empty[st], ((i / NST) & 1) ^ 1);
-        mbar_expect_tx(&qdo_full[st], 2 * Cfg::TILE_BYTES);
-        tma_load_head_tile<HD>(sQ + st * Cfg::TILE_BYTES, &tmQKV, &qdo_full[st], Cfg::BT, h * HD, i * Cfg::BT, b);
-        tma_load_head_tile<HD>(sDO + st * Cfg::TILE_BYTES, &tmDO, &qdo_full[st], Cfg::BT, h * HD, i * Cfg::BT, b);
+      int G = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int k0 = (item % n_kt) * Cfg::BT, h = (item / n_kt) % H, b = item / (n_kt * H);
+        mbar_wait(kv_empty, (it & 1) ^ 1);
+        mbar_expect_tx(kv_full, 2 * Cfg::TILE_BYTES);
+        tma_load_head_tile<HD>(sK, &tmQKV, kv_full, Cfg::BT, D + h * HD, k0, b);
+        tma_load_head_tile<HD>(sV, &tmQKV, kv_full, Cfg::BT, 2 * D + h * HD, k0, b);
+        for (int i = 0; i < n_q; ++i, ++G) {
+          const int st = G % NST;
+          mbar_wait(&qdo_empty[st], ((G / NST) & 1) ^ 1);
+          mbar_expect_tx(&qdo_full[st], 2 * Cfg::TILE_BYTES);
+          tma_load_head_tile<HD>(sQ + st * Cfg::TILE_BYTES, &tmQKV, &qdo_full[st], Cfg::BT, h * HD, i * Cfg::BT, b);
+          tma_load_head_tile<HD>(sDO + st * Cfg::TILE_BYTES, &tmDO, &qdo_full[st], Cfg::BT, h * HD, i * Cfg::BT, b);
+        }
       }
     }
   } else if (warp == 9) {
     // ---------------------------------------------------------------- MMA issuer
     //   S,dP(0) | sdp_free(0): S,dP(1) | pds_full(0): dV,dK,dQ(0) | sdp_free(1): S,dP(2) | pds_full(1): dV,dK,dQ(1) ...
+    // (at the last tile of an item the order flips: the next item's S,dP need its K, V, whose smem is only
+    //  released by this item's last dV,dK,dQ)
     constexpr uint32_t id_s = make_idesc(128, 128, false, false);
     const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
     const uint64_t pt_k = desc_kmajor<128>(smem_u32(sPT));
     const uint64_t ds_k = desc_kmajor<128>(smem_u32(sDS));
     const uint64_t ds_mn = desc_mnmajor<128>(smem_u32(sDS), 16384);
-    auto issue_sdp = [&](int i) {
-      const int st = i % NST;
-      mbar_wait(&qdo_full[st], (i / NST) & 1);
-      if (i > 0) mbar_wait(sdp_free, (i - 1) & 1);          // tile i-1 left TMEM for the compute warps' registers
+    auto issue_sdp = [&](int G, bool first_of_item, int it) {
+      const int st = G % NST;
+      if (first_of_item) mbar_wait(kv_full, it & 1);
+      mbar_wait(&qdo_full[st], (G / NST) & 1);
+      if (G > 0) mbar_wait(sdp_free, (G - 1) & 1);          // tile G-1 left TMEM for the compute warps' registers
       tc_fence_after();
       if (elect_one()) {
         mma_over_hd<HD>(tmem_base + Cfg::COL_ST, k_addr, Cfg::BT, smem_u32(sQ + st * Cfg::TILE_BYTES), Cfg::BT, id_s);
@@ -491,30 +503,35 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
       }
       __syncwarp();
     };
-    mbar_wait(kv_full, 0);
-    issue_sdp(0);
-    for (int i = 0; i < n_q; ++i) {
-      const int st = i % NST;
-      if (i + 1 < n_q) issue_sdp(i + 1);
-      mbar_wait(pds_full, i & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
-        const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
-        // dV += P^T dO ; dK += dS^T Q   (A: K-major 2-atom tiles, k-step k lives in atom k/4)
-        mma_into_hd<HD, false, Cfg::BT>(tmem_base + Cfg::COL_DV,
-                                        [&](int k) { return desc_advance(pt_k, (k >> 2) * 16384 + (k & 3) * 32); },
-                                        do_addr, i != 0);
-        mma_into_hd<HD, false, Cfg::BT>(tmem_base + Cfg::COL_DK,
-                                        [&](int k) { return desc_advance(ds_k, (k >> 2) * 16384 + (k & 3) * 32); },
-                                        q_addr, i != 0);
-        // dQ_i = dS K   (A: the same dS^T buffer read MN-major)
-        mma_into_hd<HD, true, Cfg::BT>(tmem_base + Cfg::COL_DQ, [&](int k) { return desc_advance(ds_mn, k * 2048); },
-                                       k_addr, false);
-        umma_commit(&qdo_empty[st]);
-        umma_commit(dq_full);
+    int G = 0;
+    for (int it = 0; it < n_my; ++it) {
+      if (it == 0) issue_sdp(0, true, 0);
+      for (int i = 0; i < n_q; ++i, ++G) {
+        const int st = G % NST;
+        const bool last = (i == n_q - 1);
+        if (!last) issue_sdp(G + 1, false, it);
+        mbar_wait(pds_full, G & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t q_addr = smem_u32(sQ + st * Cfg::TILE_BYTES);
+          const uint32_t do_addr = smem_u32(sDO + st * Cfg::TILE_BYTES);
+          // dV += P^T dO ; dK += dS^T Q   (A: K-major 2-atom tiles, k-step k lives in atom k/4)
+          mma_into_hd<HD, false, Cfg::BT>(tmem_base + Cfg::COL_DV,
+                                          [&](int k) { return desc_advance(pt_k, (k >> 2) * 16384 + (k & 3) * 32); },
+                                          do_addr, i != 0);
+          mma_into_hd<HD, false, Cfg::BT>(tmem_base + Cfg::COL_DK,
+                                          [&](int k) { return desc_advance(ds_k, (k >> 2) * 16384 + (k & 3) * 32); },
+                                          q_addr, i != 0);
+          // dQ_i = dS K   (A: the same dS^T buffer read MN-major)
+          mma_into_hd<HD, true, Cfg::BT>(tmem_base + Cfg::COL_DQ, [&](int k) { return desc_advance(ds_mn, k * 2048); },
+                                         k_addr, false);
+          umma_commit(&qdo_empty[st]);
+          umma_commit(dq_full);
+          if (last) umma_commit(kv_empty);
+        }
+        __syncwarp();
+        if (last && it + 1 < n_my) issue_sdp(G + 1, true, it + 1);
       }
-      __syncwarp();
     }
   } else {
     // ---------------------------------------------------------------- compute warps
@@ -522,15 +539,17 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
     const int half = threadIdx.x >> 7;                      // query columns [64*half, 64*half + 64)
     const int lane = threadIdx.x & 31;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    const float* lse_bh = lse + ((long long)b * H + h) * S;
-    const float* delta_bh = delta + ((long long)b * H + h) * S;
     const uint32_t s_col = smem_u32(smem + Cfg::OFF_LSE);
     const uint32_t pt_row = smem_u32(sPT) + half * 16384 + r * 128;     // this thread's 64 columns = atom `half`
     const uint32_t ds_row = smem_u32(sDS) + half * 16384 + r * 128;
     const int swz = r & 7;
     const uint64_t sc2 = f32x2_pack(scale_log2, scale_log2), s2 = f32x2_pack(scale, scale);
+    long long bp2 = 0, bp3 = 0, bp4 = 0, bp5 = 0, bp6 = 0, bp7 = 0, bp8 = 0, bp1 = 0, bp10 = 0, bp11 = 0, bp12 = 0, bp13 = 0;
+    (void)bp1; (void)bp2; (void)bp3; (void)bp4; (void)bp5; (void)bp6; (void)bp7; (void)bp8; (void)bp10; (void)bp11;
+    (void)bp12; (void)bp13;
+    BP_T0(bp_all);
 
-    // dQ_j (TMEM) -> fp32 staging tile; lane r == query row r of tile j
+    // dQ tile (TMEM) -> fp32 staging tile; lane r == query row r of the tile
     auto stage_dq = [&]() {
       uint32_t o[HO];
       tmem_ld_n<HO>(lane_addr + Cfg::COL_DQ + half * HO, o);
@@ -542,153 +561,181 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
       for (int u = 0; u < HO / 4; ++u)
         st_shared_v4(rowp + (((cbase + u) ^ swz) << 4), o[u * 4], o[u * 4 + 1], o[u * 4 + 2], o[u * 4 + 3]);
     };
-    auto reduce_dq = [&](int j) {                           // one thread: TMA reduce-add the staged tile into dq_acc
-#pragma unroll
-      for (int a = 0; a < HD / 32; ++a) tma_reduce_add_3d(&tmDQ, sDQ + a * 16384, h * HD + a * 32, j * Cfg::BT, b);
-      bulk_commit_bwd();
-    };
 
-    long long bp2 = 0, bp3 = 0, bp4 = 0, bp5 = 0, bp6 = 0, bp7 = 0, bp8 = 0, bp1 = 0;
-    (void)bp1; (void)bp2; (void)bp3; (void)bp4; (void)bp5; (void)bp6; (void)bp7; (void)bp8;
-    BP_T0(bp_all);
-    // per-column -lse and -delta*scale of query tile j -> smem (parity j & 1); written one tile ahead, published by
-    // the barrier that closes the previous tile
-    auto load_cols = [&](int j) {
-      if (half == 0 && j < n_q) {
-        const uint32_t dst = s_col + (j & 1) * 1024;
-        const int q = j * Cfg::BT + r;
-        st_shared_f32(dst + r * 4, q < S ? -lse_bh[q] : -INFINITY);
-        st_shared_f32(dst + 512 + r * 4, q < S ? -delta_bh[q] * scale : 0.f);
-      }
-    };
-    load_cols(0);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    for (int i = 0; i < n_q; ++i) {
-      const uint32_t s_par = s_col + (i & 1) * 1024;
-      load_cols(i + 1);
-      BP_T0(c2);
-      mbar_wait(sdp_full, i & 1);
-      if (i == 0) { BP_ADD(bp1, bp_all); } else { BP_ADD(bp2, c2); }
-      tc_fence_after();
-      BP_T0(c3);
-      uint32_t sv[64], dv[64];
-      tmem_ld32(lane_addr + Cfg::COL_ST + half * 64, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
-      tmem_ld32(lane_addr + Cfg::COL_ST + half * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
-      tmem_ld32(lane_addr + Cfg::COL_DPT + half * 64, reinterpret_cast<uint32_t(&)[32]>(dv[0]));
-      tmem_ld32(lane_addr + Cfg::COL_DPT + half * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(dv[32]));
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(sdp_free);                 // S^T, dP^T of tile i+1 may be computed now
-      BP_ADD(bp3, c3);
-      BP_T0(c4);
-      // P = exp2(s*scale*log2e - lse), dS = P * (dP - delta) * scale, on packed fp32 pairs.  Rows of keys >= S and
-      // columns of queries >= S need no masking: their K / V / Q / dO rows are TMA zero-fill and lse = +inf there,
-      // so every product they reach is an exact zero or lands in a dK / dV row that is never stored.
-      uint32_t pp[32], dd[32];
+    int G = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int k0 = (item % n_kt) * Cfg::BT, h = (item / n_kt) % H, b = item / (n_kt * H);
+      const float* lse_bh = lse + ((long long)b * H + h) * S;
+      const float* delta_bh = delta + ((long long)b * H + h) * S;
+      auto reduce_dq = [&](int j) {                         // one thread: TMA reduce-add the staged tile into dq_acc
 #pragma unroll
-      for (int j = 0; j < 64; j += 4) {
-        uint32_t nl[4], nd[4];
-        ld_shared_v4(s_par + (half * 64 + j) * 4, nl);
-        ld_shared_v4(s_par + 512 + (half * 64 + j) * 4, nd);
+        for (int a = 0; a < HD / 32; ++a) tma_reduce_add_3d(&tmDQ, sDQ + a * 16384, h * HD + a * 32, j * Cfg::BT, b);
+        bulk_commit_bwd();
+      };
+      // per-column -lse and -delta*scale of query tile j -> smem (parity of its global index); written one tile
+      // ahead, published by the barrier inside the previous tile
+      // (the global loads are issued a phase before their values are stored to smem, so their latency hides
+      // behind the TMEM loads and the exp math)
+      // (fetch only issues the loads -- no arithmetic on the values, an in-order warp would stall on it)
+      float col_l = 0.f, col_d = 0.f;
+      auto fetch_cols = [&](int j) {
+        if (half == 0 && j < n_q) {
+          const int q = j * Cfg::BT + r;
+          if (q < S) {
+            col_l = __ldg(lse_bh + q);
+            col_d = __ldg(delta_bh + q);
+          } else {
+            col_l = INFINITY;
+            col_d = 0.f;
+          }
+        }
+      };
+      auto put_cols = [&](int j, int Gj) {
+        if (half == 0 && j < n_q) {
+          const uint32_t dst = s_col + (Gj & 1) * 1024;
+          st_shared_f32(dst + r * 4, -col_l);
+          st_shared_f32(dst + 512 + r * 4, -col_d * scale);
+        }
+      };
+      BP_T0(c13);
+      fetch_cols(0);
+      put_cols(0, G);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      BP_ADD(bp13, c13);
+      for (int i = 0; i < n_q; ++i, ++G) {
+        const uint32_t s_par = s_col + (G & 1) * 1024;
+        fetch_cols(i + 1);
+        BP_T0(c2);
+        mbar_wait(sdp_full, G & 1);
+        if (i == 0) { BP_ADD(bp1, c2); } else { BP_ADD(bp2, c2); }
+        tc_fence_after();
+        BP_T0(c3);
+        uint32_t sv[64], dv[64];
+        tmem_ld32(lane_addr + Cfg::COL_ST + half * 64, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
+        tmem_ld32(lane_addr + Cfg::COL_ST + half * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
+        tmem_ld32(lane_addr + Cfg::COL_DPT + half * 64, reinterpret_cast<uint32_t(&)[32]>(dv[0]));
+        tmem_ld32(lane_addr + Cfg::COL_DPT + half * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(dv[32]));
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(sdp_free);               // S^T, dP^T of the next tile may be computed now
+        BP_ADD(bp3, c3);
+        BP_T0(c4);
+        // P = exp2(s*scale*log2e - lse), dS = P * (dP - delta) * scale, on packed fp32 pairs.  Rows of keys >= S
+        // and columns of queries >= S need no masking: their K / V / Q / dO rows are TMA zero-fill and lse = +inf
+        // there, so every product they reach is an exact zero or lands in a dK / dV row that is never stored.
+        uint32_t pp[32], dd[32];
 #pragma unroll
-        for (int e = 0; e < 4; e += 2) {
-          const uint64_t x = f32x2_fma(f32x2_pack(__uint_as_float(sv[j + e]), __uint_as_float(sv[j + e + 1])), sc2,
-                                       f32x2_pack(__uint_as_float(nl[e]), __uint_as_float(nl[e + 1])));
-          float x0, x1;
-          f32x2_unpack(x, x0, x1);
-          const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-          const uint64_t t = f32x2_fma(f32x2_pack(__uint_as_float(dv[j + e]), __uint_as_float(dv[j + e + 1])), s2,
-                                       f32x2_pack(__uint_as_float(nd[e]), __uint_as_float(nd[e + 1])));
-          const uint64_t d = f32x2_mul(f32x2_pack(p0, p1), t);
-          float d0, d1;
-          f32x2_unpack(d, d0, d1);
-          pp[(j + e) >> 1] = pack_bf16x2(p0, p1);
-          dd[(j + e) >> 1] = pack_bf16x2(d0, d1);
+        for (int j = 0; j < 64; j += 4) {
+          uint32_t nl[4], nd[4];
+          ld_shared_v4(s_par + (half * 64 + j) * 4, nl);
+          ld_shared_v4(s_par + 512 + (half * 64 + j) * 4, nd);
+#pragma unroll
+          for (int e = 0; e < 4; e += 2) {
+            const uint64_t x = f32x2_fma(f32x2_pack(__uint_as_float(sv[j + e]), __uint_as_float(sv[j + e + 1])), sc2,
+                                         f32x2_pack(__uint_as_float(nl[e]), __uint_as_float(nl[e + 1])));
+            float x0, x1;
+            f32x2_unpack(x, x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            const uint64_t t = f32x2_fma(f32x2_pack(__uint_as_float(dv[j + e]), __uint_as_float(dv[j + e + 1])), s2,
+                                         f32x2_pack(__uint_as_float(nd[e]), __uint_as_float(nd[e + 1])));
+            const uint64_t d = f32x2_mul(f32x2_pack(p0, p1), t);
+            float d0, d1;
+            f32x2_unpack(d, d0, d1);
+            pp[(j + e) >> 1] = pack_bf16x2(p0, p1);
+            dd[(j + e) >> 1] = pack_bf16x2(d0, d1);
+          }
+        }
+        BP_ADD(bp4, c4);
+        {
+          // the staging tile is free once the TMA has read the dQ tile staged a whole tile ago; this barrier also
+          // publishes the column constants of the next tile
+          BP_T0(c8);
+          put_cols(i + 1, G + 1);
+          if (threadIdx.x == 128) bulk_wait_read0_bwd();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          BP_ADD(bp8, c8);
+        }
+        if (i > 0) {
+          // MMAs of the previous tile retired: P^T / dS^T smem may be overwritten, its dQ waits in TMEM
+          BP_T0(c5);
+          mbar_wait(dq_full, (G - 1) & 1);
+          BP_ADD(bp5, c5);
+          tc_fence_after();
+          BP_T0(c6);
+          stage_dq();
+          BP_ADD(bp6, c6);
+        }
+        BP_T0(c7);
+        // 8 x 16-byte chunks per buffer: chunk u of this thread's 128-byte row lands at u ^ (r & 7)
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          st_shared_v4(pt_row + ((u ^ swz) << 4), pp[u * 4], pp[u * 4 + 1], pp[u * 4 + 2], pp[u * 4 + 3]);
+          st_shared_v4(ds_row + ((u ^ swz) << 4), dd[u * 4], dd[u * 4 + 1], dd[u * 4 + 2], dd[u * 4 + 3]);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_full);
+        BP_ADD(bp7, c7);
+        if (i > 0) {
+          BP_T0(c9);
+          asm volatile("bar.sync 2, 256;" ::: "memory");   // every thread's part of the staged dQ tile is fenced
+          if (threadIdx.x == 128) reduce_dq(i - 1);        // (the thread that waits on the bulk group above)
+          BP_ADD(bp8, c9);
         }
       }
-      BP_ADD(bp4, c4);
-      {
-        // the staging tile is free once the TMA has read dQ_{i-2} out of it (issued a whole tile ago); this
-        // barrier also publishes the column constants of tile i+1
-        BP_T0(c8);
-        if (threadIdx.x == 128 && i > 1) bulk_wait_read0_bwd();
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        BP_ADD(bp8, c8);
-      }
-      if (i > 0) {
-        // MMAs of tile i-1 retired: P^T / dS^T smem may be overwritten, dQ_{i-1} waits in TMEM
-        BP_T0(c5);
-        mbar_wait(dq_full, (i - 1) & 1);
-        BP_ADD(bp5, c5);
-        tc_fence_after();
-        BP_T0(c6);
-        stage_dq();
-        BP_ADD(bp6, c6);
-      }
-      BP_T0(c7);
-      // 8 x 16-byte chunks per buffer: chunk u of this thread's 128-byte row lands at u ^ (r & 7)
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        st_shared_v4(pt_row + ((u ^ swz) << 4), pp[u * 4], pp[u * 4 + 1], pp[u * 4 + 2], pp[u * 4 + 3]);
-        st_shared_v4(ds_row + ((u ^ swz) << 4), dd[u * 4], dd[u * 4 + 1], dd[u * 4 + 2], dd[u * 4 + 3]);
-      }
+      // ---- item epilogue: last dQ tile, then dK / dV (the 1/sqrt(d) factor is already in dS)
+      // (dK / dV are pulled out of TMEM first: the TMA is still reading the dQ tile staged a moment ago)
+      BP_T0(c10);
+      mbar_wait(dq_full, (G - 1) & 1);
+      BP_ADD(bp11, c10);
+      tc_fence_after();
+      constexpr int NV = HO / 8;
+      uint32_t a[HO], c[HO];
+      tmem_ld_n<HO>(lane_addr + Cfg::COL_DK + half * HO, a);
+      tmem_ld_n<HO>(lane_addr + Cfg::COL_DV + half * HO, c);
+      tmem_ld_wait();
+      BP_T0(c12);
+      if (threadIdx.x == 128) bulk_wait_read0_bwd();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      BP_ADD(bp12, c12);
+      stage_dq();
+      tc_fence_before();                                    // the next item's MMAs overwrite dQ / dK / dV in TMEM
+      // (fence + barrier come BEFORE the dK / dV global stores: the proxy fence is a full MEMBAR and would wait
+      //  for those stores to be acknowledged)
       fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-      BP_ADD(bp7, c7);
-      if (i > 0) {
-        BP_T0(c9);
-        asm volatile("bar.sync 2, 256;" ::: "memory");     // every thread's part of the staged dQ_{i-1} is fenced
-        if (threadIdx.x == 128) reduce_dq(i - 1);          // (the thread that waits on the bulk group above)
-        BP_ADD(bp8, c9);
-      }
-    }
-    BP_T0(c10);
-    // drain the last dQ tile
-    mbar_wait(dq_full, (n_q - 1) & 1);
-    tc_fence_after();
-    if (threadIdx.x == 128 && n_q > 1) bulk_wait_read0_bwd();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    stage_dq();
-    fence_proxy_async_smem();
-    asm volatile("bar.sync 2, 256;" ::: "memory");
-    if (threadIdx.x == 128) {
-      reduce_dq(n_q - 1);
-      bulk_wait_all0_bwd();
-    }
-    // dK / dV epilogue (all MMAs retired); the 1/sqrt(d) factor is already in dS
-    const int key = k0 + r;
-    bf16* dk_row = dqkv + ((long long)b * S + key) * 3 * D + D + h * HD + half * HO;
-    bf16* dv_row = dk_row + D;
-    constexpr int NV = HO / 8;
-    uint32_t a[HO], c[HO];
-    tmem_ld_n<HO>(lane_addr + Cfg::COL_DK + half * HO, a);
-    tmem_ld_n<HO>(lane_addr + Cfg::COL_DV + half * HO, c);
-    tmem_ld_wait();
-    if (key < S) {
-      const __half* tr = rope ? rope + ((long long)b * S + key) * 2 * HD + half * HO : nullptr;
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (threadIdx.x == 128) reduce_dq(n_q - 1);
+      const int key = k0 + r;
+      if (key < S) {
+        bf16* dk_row = dqkv + ((long long)b * S + key) * 3 * D + D + h * HD + half * HO;
+        bf16* dv_row = dk_row + D;
+        const __half* tr = rope ? rope + ((long long)b * S + key) * 2 * HD + half * HO : nullptr;
 #pragma unroll
-      for (int jj = 0; jj < NV; ++jj) {
-        const int j = jj * 8;
-        uint4 u, w;
-        float gk[8];
+        for (int jj = 0; jj < NV; ++jj) {
+          const int j = jj * 8;
+          uint4 u, w;
+          float gk[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) gk[e] = __uint_as_float(a[j + e]);
-        if (rope) rope_adjoint8(gk, *reinterpret_cast<const uint4*>(tr + j), *reinterpret_cast<const uint4*>(tr + HD + j));
-        u.x = pack_bf16x2(gk[0], gk[1]);
-        u.y = pack_bf16x2(gk[2], gk[3]);
-        u.z = pack_bf16x2(gk[4], gk[5]);
-        u.w = pack_bf16x2(gk[6], gk[7]);
-        w.x = pack_bf16x2(__uint_as_float(c[j]), __uint_as_float(c[j + 1]));
-        w.y = pack_bf16x2(__uint_as_float(c[j + 2]), __uint_as_float(c[j + 3]));
-        w.z = pack_bf16x2(__uint_as_float(c[j + 4]), __uint_as_float(c[j + 5]));
-        w.w = pack_bf16x2(__uint_as_float(c[j + 6]), __uint_as_float(c[j + 7]));
-        *reinterpret_cast<uint4*>(dk_row + j) = u;
-        *reinterpret_cast<uint4*>(dv_row + j) = w;
+          for (int e = 0; e < 8; ++e) gk[e] = __uint_as_float(a[j + e]);
+          if (rope) rope_adjoint8(gk, *reinterpret_cast<const uint4*>(tr + j), *reinterpret_cast<const uint4*>(tr + HD + j));
+          u.x = pack_bf16x2(gk[0], gk[1]);
+          u.y = pack_bf16x2(gk[2], gk[3]);
+          u.z = pack_bf16x2(gk[4], gk[5]);
+          u.w = pack_bf16x2(gk[6], gk[7]);
+          w.x = pack_bf16x2(__uint_as_float(c[j]), __uint_as_float(c[j + 1]));
+          w.y = pack_bf16x2(__uint_as_float(c[j + 2]), __uint_as_float(c[j + 3]));
+          w.z = pack_bf16x2(__uint_as_float(c[j + 4]), __uint_as_float(c[j + 5]));
+          w.w = pack_bf16x2(__uint_as_float(c[j + 6]), __uint_as_float(c[j + 7]));
+          *reinterpret_cast<uint4*>(dk_row + j) = u;
+          *reinterpret_cast<uint4*>(dv_row + j) = w;
+        }
       }
+      BP_ADD(bp10, c10);
     }
+    if (threadIdx.x == 128) bulk_wait_all0_bwd();           // all reduce-adds have landed before the kernel ends
 #ifdef VJ_ATTN_PROFILE
     if (threadIdx.x == 0) {
       atomicAdd(&g_attn_bwd_prof[0], (unsigned long long)(clock64() - bp_all));
@@ -700,8 +747,11 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
       atomicAdd(&g_attn_bwd_prof[6], (unsigned long long)bp6);
       atomicAdd(&g_attn_bwd_prof[7], (unsigned long long)bp7);
       atomicAdd(&g_attn_bwd_prof[8], (unsigned long long)bp8);
-      atomicAdd(&g_attn_bwd_prof[9], 1ull);
-      atomicAdd(&g_attn_bwd_prof[10], (unsigned long long)(clock64() - c10));
+      atomicAdd(&g_attn_bwd_prof[9], (unsigned long long)n_my);
+      atomicAdd(&g_attn_bwd_prof[10], (unsigned long long)bp10);
+      atomicAdd(&g_attn_bwd_prof[11], (unsigned long long)bp11);
+      atomicAdd(&g_attn_bwd_prof[12], (unsigned long long)bp12);
+      atomicAdd(&g_attn_bwd_prof[13], (unsigned long long)bp13);
     }
 #endif
   }
@@ -760,9 +810,13 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
       VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
       attr_set = true;
     }
-    kern<<<grid, 320, Cfg2::SMEM_BYTES, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, reinterpret_cast<bf16*>(dqkv),
-                                                 reinterpret_cast<const __half*>(rope), S, H, D, scale,
-                                                 scale * 1.4426950408889634f);
+    const int n_kt = (S + Cfg2::BT - 1) / Cfg2::BT;
+    const long long n_items = (long long)n_kt * H * B;
+    VJ_CHECK(n_items < (1ll << 30), "vj_attn_bwd: too many (key tile, head, sample) work items");
+    const int pgrid = (int)(n_items < sm_count() ? n_items : sm_count());      // persistent: one CTA per SM
+    kern<<<pgrid, 320, Cfg2::SMEM_BYTES, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, reinterpret_cast<bf16*>(dqkv),
+                                                  reinterpret_cast<const __half*>(rope), S, H, D, scale,
+                                                  scale * 1.4426950408889634f, n_kt, (int)n_items);
   }
   VJ_LAUNCH_CHECK();
   {

@@ -431,10 +431,13 @@ static void bench_attn(int B, int S, int H, int hd, bool bwd) {
       vj_attn_bwd_prof_read(bp, 1);
       const double n = (double)bp[9], it = (double)((S + 127) / 128);
       if (n > 0)
-        printf("      per CTA (cycles): total %.0f = prologue %.0f + %d x [barriers %.0f + wait S/dP %.0f + tmem ld %.0f + math %.0f"
+        printf("      per work item (cycles): total %.0f = first S/dP wait %.0f + %d x [barriers %.0f + wait S/dP %.0f + tmem ld %.0f + math %.0f"
                " + wait dQ %.0f + stage dQ %.0f + P/dS store %.0f] + epilogue %.0f\n",
                bp[0] / n, bp[1] / n, (int)it, bp[8] / n / it, bp[2] / n / it, bp[3] / n / it, bp[4] / n / it, bp[5] / n / it,
                bp[6] / n / it, bp[7] / n / it, bp[10] / n);
+      if (n > 0)
+        printf("      epilogue: wait last MMAs %.0f, wait staging TMA + barrier %.0f; item start (column constants + barrier) %.0f\n",
+               bp[11] / n, bp[12] / n, bp[13] / n);
     }
 #endif
   }
@@ -483,6 +486,8 @@ int main(int argc, char** argv) {
     test_attn(1, 700, 3, 32, true);
     test_attn(2, 200, 2, 80, true);
     test_attn(1, 520, 3, 80, true);
+    test_attn(4, 330, 20, 64, true);     // 240 work items on 148 persistent CTAs, 3 query tiles each
+    test_attn(6, 100, 40, 32, true);     // single-tile items
   }
   if (all || !strcmp(what, "bench")) {
     bench_gemm("qkv fwd (ViT-g target)", 49152, 4224, 1408, 0, 0, VJ_EPI_BIAS);
