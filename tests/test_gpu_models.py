@@ -103,6 +103,28 @@ def test_predictor_forward_vs_reference_golden(dev, golden):
     assert relerr(out1, golden["pred.out_idx1"]) < 1e-2
 
 
+def test_multi_mask_pass_equals_per_mask_passes(dev):
+    """The fused step pushes all masks of a group through one set of launches (row blocks of one token matrix);
+    the reference loops over the masks (wrappers.py:15-43).  Row-wise kernels + per-mask attention launches make
+    the two bit-identical in the forward direction."""
+    from vjepa2_b200 import engine
+    enc, pred, _, _ = build_models(dev)
+    clips = tiny_clips(2).to(dev)
+    me, mp = step_masks()
+    me = [m.to(dev).contiguous() for m in me]
+    mp = [m.to(dev).contiguous() for m in mp]
+    assert me[0].shape[1] != me[1].shape[1] and mp[0].shape[1] != mp[1].shape[1]   # ragged on purpose
+    ert, prt = enc.runtime(), pred.runtime()
+    grid = (GRID, GRID)
+    zs, _ = engine.encoder_forward(ert, clips, me, grid, save=False)
+    ps, _ = engine.predictor_forward(prt, zs, me, mp, 0, save=False)
+    for j in range(2):
+        z1, _ = engine.encoder_forward(ert, clips, me[j], grid, save=False)
+        assert torch.equal(zs[j], z1), j
+        p1, _ = engine.predictor_forward(prt, z1, me[j], mp[j], 0, save=False)
+        assert torch.equal(ps[j], p1), j
+
+
 def _oracle_state():
     import vjepa_oracle as O
     w_enc, w_pred = tiny_weights()

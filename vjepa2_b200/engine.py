@@ -57,10 +57,43 @@ class BlockG:
 # ------------------------------------------------------------------------------------------------
 # one transformer block
 # ------------------------------------------------------------------------------------------------
+def _segs(B, S):
+    """Normalise the sequence layout of a token matrix: a list of (samples, tokens per sample) segments whose
+    rows follow each other.  Everything but attention is row-wise, so differently masked copies of a batch
+    (different kept-token counts) run through ONE set of LayerNorm / GEMM launches; only attention is launched
+    per segment."""
+    if isinstance(B, (list, tuple)):
+        return list(B)
+    return [(B, S)]
+
+
+def _attn_fwd_segs(qkv, att, lse, segs, heads, hd, st):
+    r0 = l0 = 0
+    for (b, s) in segs:
+        n, nl = b * s, b * heads * s
+        ops.attn_fwd(qkv[r0:r0 + n], att[r0:r0 + n], lse[l0:l0 + nl], b, s, heads, hd, st)
+        r0 += n
+        l0 += nl
+
+
+def _attn_bwd_segs(qkv, att, datt, lse, dqkv, segs, heads, hd, st, ws, rope):
+    r0 = l0 = 0
+    for (b, s) in segs:
+        n, nl = b * s, b * heads * s
+        mk = ws.mark()
+        ops.attn_bwd(qkv[r0:r0 + n], att[r0:r0 + n], datt[r0:r0 + n], lse[l0:l0 + nl], dqkv[r0:r0 + n], b, s, heads, hd,
+                     st, ws.tmp, rope[r0:r0 + n] if rope is not None else None)
+        ws.release(mk)                          # one segment's attention scratch is dead once the call is enqueued
+        r0 += n
+        l0 += nl
+
+
 def block_forward(h: BlockH, x, x_out, B, S, heads, hd, rope, save, st, ws):
-    """x: residual stream [B*S, D] (bf16 encoder / fp32 predictor); x_out: where the block output goes.
+    """x: residual stream [sum(B_i*S_i), D] (bf16 encoder / fp32 predictor); x_out: where the block output goes.
+    B, S: samples and tokens per sample, or B = list of (B_i, S_i) segments (see _segs) and S ignored.
     save=True keeps everything backward needs in ws.act; otherwise temporaries live in ws.tmp (caller
     brackets the call with mark/release).  Returns saved tuple or None."""
+    segs = _segs(B, S)
     M, D = x.shape
     Hm = h.hidden
     A = ws.act if save else ws.tmp
@@ -74,8 +107,8 @@ def block_forward(h: BlockH, x, x_out, B, S, heads, hd, rope, save, st, ws):
     qkv = A((M, 3 * D), BF16)
     ops.gemm(ln1, h.qkv_w, qkv, M, 3 * D, D, bias=h.qkv_b, rope=(rope, hd, D), st=st)     # qkv + fused 3-axis RoPE
     att = A((M, D), BF16)
-    lse = A((B * heads * S,), F32)
-    ops.attn_fwd(qkv, att, lse, B, S, heads, hd, st)
+    lse = A((sum(b * s for b, s in segs) * heads,), F32)
+    _attn_fwd_segs(qkv, att, lse, segs, heads, hd, st)
     x1 = A((M, D), x.dtype)
     ops.gemm(att, h.proj_w, x1, M, D, D, bias=h.proj_b, residual=x, round_bf16=True, st=st)
     ln2 = A((M, D), BF16)
@@ -99,6 +132,7 @@ def block_backward(h: BlockH, g: BlockG, saved, dx2, dx0, B, S, heads, hd, rope,
     the gradient w.r.t. the block input (may not alias dx2).  Parameter gradients are ACCUMULATED into g
     (fp32).  Temporaries come from ws.tmp and are released before returning."""
     x, mean1, rstd1, ln1, qkv, att, lse, x1, mean2, rstd2, ln2, hpre, act = saved
+    segs = _segs(B, S)
     M, D = x.shape
     Hm = h.hidden
     T = ws.tmp
@@ -122,7 +156,7 @@ def block_backward(h: BlockH, g: BlockG, saved, dx2, dx0, B, S, heads, hd, rope,
     ops.gemm(d1, att, g.proj_w, D, D, M, a_mn=True, b_mn=True, residual=g.proj_w, st=st)
     ops.colsum(d1, g.proj_b, True, st, T)
     dqkv = T((M, 3 * D), BF16)
-    ops.attn_bwd(qkv, att, datt, lse, dqkv, B, S, heads, hd, st, T, rope)                  # + fused adjoint RoPE
+    _attn_bwd_segs(qkv, att, datt, lse, dqkv, segs, heads, hd, st, ws, rope)              # + fused adjoint RoPE
     dln1 = T((M, D), BF16)
     ops.gemm(dqkv, h.qkv_w, dln1, M, D, 3 * D, b_mn=True, st=st)
     ops.gemm(dqkv, ln1, g.qkv_w, 3 * D, D, M, a_mn=True, b_mn=True, residual=g.qkv_w, st=st)
@@ -198,8 +232,10 @@ class EncoderRT:
 
 
 def encoder_forward(rt: EncoderRT, clips, ids, grid_hw, save, ws=None, out_layers=None):
-    """clips fp32 [B,C,T,H,W]; ids None or int64 [B*reps, K] kept-token ids.
-    Returns (out fp32 [B*reps, S, D], saved) -- or the list of normed intermediate outputs if out_layers.
+    """clips fp32 [B,C,T,H,W]; ids: None, int64 [B*reps, K] kept-token ids, or a LIST of int64 [B, K_i] (one entry
+    per mask; the masked copies share every LayerNorm / GEMM launch, see _segs).
+    Returns (out, saved): out fp32 [B*reps, S, D], or a list of [B, K_i, D] views for a list of ids -- or the list
+    of normed intermediate outputs if out_layers.
     With an Arena `ws`, the output lives in ws.act (save) / ws.tmp and is only valid until the arena is reset."""
     st = ops.stream()
     B = clips.shape[0]
@@ -209,15 +245,30 @@ def encoder_forward(rt: EncoderRT, clips, ids, grid_hw, save, ws=None, out_layer
     Hp, Wp = grid_hw
     D, heads, hd = rt.D, rt.heads, rt.hd
     A = ws.act if save else ws.tmp
-    cols = ops.im2col_tubelets(clips, ids, rt.tubelet, rt.patch, st, A)
-    M = cols.shape[0]
-    if ids is not None:
-        Bp, S = ids.shape
+    multi = isinstance(ids, (list, tuple))
+    if multi:
+        if out_layers is not None:
+            raise NotImplementedError("vjepa2_b200: out_layers with a list of masks")
+        segs = [(B, int(m.shape[1])) for m in ids]
+        M = sum(b * s for b, s in segs)
+        cols = A((M, rt.pe_k), BF16)
+        rope = A((M, 2, hd), torch.float16)
+        r0 = 0
+        for m, (b, s) in zip(ids, segs):
+            ops.im2col_tubelets(clips, m, rt.tubelet, rt.patch, st, out=cols[r0:r0 + b * s])
+            ops.rope_table(m, b * s, s, Hp, Wp, hd, dev, st, out=rope[r0:r0 + b * s])
+            r0 += b * s
+        Bp, S = segs, None
     else:
-        Bp, S = B, M // B
+        cols = ops.im2col_tubelets(clips, ids, rt.tubelet, rt.patch, st, A)
+        M = cols.shape[0]
+        if ids is not None:
+            Bp, S = ids.shape
+        else:
+            Bp, S = B, M // B
+        rope = ops.rope_table(ids, M, S, Hp, Wp, hd, dev, st, A)
     x = A((M, D), BF16)
     ops.gemm(cols, rt.pe_w, x, M, D, rt.pe_k, bias=rt.pe_b, st=st)
-    rope = ops.rope_table(ids, M, S, Hp, Wp, hd, dev, st, A)
     outs = []
 
     def collect(i, xi):
@@ -237,16 +288,22 @@ def encoder_forward(rt: EncoderRT, clips, ids, grid_hw, save, ws=None, out_layer
         rstd = A((M,), F32)
     ops.layernorm_fwd(x, rt.norm_w, rt.norm_b, out, mean, rstd, 1e-6, st)
     saved = (cols, rope, blocks_saved, x, mean, rstd, Bp, S) if save else None
+    if multi:
+        views, r0 = [], 0
+        for (b, s) in segs:
+            views.append(out[r0:r0 + b * s].view(b, s, D))
+            r0 += b * s
+        return views, saved
     return out.view(Bp, S, D), saved
 
 
 def encoder_backward(rt: EncoderRT, saved, dout, gbuf, ws=None, on_block_done=None):
-    """dout: gradient w.r.t. the encoder output [B', S, D] (bf16 or fp32).  Accumulates parameter
-    gradients into gbuf (flat fp32).  The input clip needs no gradient."""
+    """dout: gradient w.r.t. the encoder output, [B', S, D] or the row-concatenated [M, D] of a multi-mask
+    forward (bf16 or fp32).  Accumulates parameter gradients into gbuf (flat fp32).  The clip needs no gradient."""
     st = ops.stream()
     cols, rope, blocks_saved, x_last, mean, rstd, Bp, S = saved
     D, heads, hd = rt.D, rt.heads, rt.hd
-    M = Bp * S
+    M = x_last.shape[0]
     if ws is None:
         ws = TorchAlloc(dout.device)
     g = rt.grads(gbuf)
@@ -312,89 +369,137 @@ class PredictorRT:
 
 
 def predictor_forward(rt: PredictorRT, z, masks_x, masks_y, mask_index, save, ws=None):
-    """z: context-encoder output [B, Kc, D_in] (fp32 or bf16); masks_x [B,Kc], masks_y [B,Kp] int64.
-    Returns (pred bf16 [B, Kp, D_in], saved)."""
+    """z: context-encoder output [B, Kc, D_in] (fp32 or bf16); masks_x [B,Kc], masks_y [B,Kp] int64 -- or three
+    equally long LISTS of those (one entry per mask; the entries of z must be consecutive row blocks of one
+    matrix, as encoder_forward returns them).  Returns (pred bf16 [B, Kp, D_in] or a list of such views, saved)."""
     st = ops.stream()
-    dev = z.device
+    multi = isinstance(z, (list, tuple))
+    zs = list(z) if multi else [z]
+    mxs = list(masks_x) if multi else [masks_x]
+    mys = list(masks_y) if multi else [masks_y]
+    dev = zs[0].device
     if ws is None:
         ws = TorchAlloc(dev)
-    B, Kc, Din = z.shape
-    Kp = masks_y.shape[1]
-    S = Kc + Kp
+    B, Din = zs[0].shape[0], zs[0].shape[2]
+    Kcs = [int(t.shape[1]) for t in zs]
+    Kps = [int(t.shape[1]) for t in mys]
+    Mc, Mp = B * sum(Kcs), B * sum(Kps)
+    segs = [(B, kc + kp) for kc, kp in zip(Kcs, Kps)]
+    Ms = sum(b * s for b, s in segs)
     D, heads, hd = rt.D, rt.heads, rt.hd
     A = ws.act if save else ws.tmp
-    z2 = z.reshape(B * Kc, Din)
+    if len(zs) == 1:
+        z2 = zs[0].reshape(Mc, Din)
+    else:
+        step = zs[0].element_size() * Din
+        p0 = zs[0].data_ptr()
+        for t, kc_prev in zip(zs[1:], Kcs[:-1]):
+            p0 += B * kc_prev * step
+            if t.data_ptr() != p0 or not t.is_contiguous():
+                raise ValueError("vjepa2_b200: predictor_forward expects the z entries to be consecutive row blocks")
+        z2 = torch.as_strided(zs[0], (Mc, Din), (Din, 1))
     if z2.dtype == BF16:
         z16 = z2
     else:
-        z16 = A((B * Kc, Din), BF16)
+        z16 = A((Mc, Din), BF16)
         ops.cast_f32_bf16(z2, z16, st)
-    emb = A((B * Kc, D), BF16)
-    ops.gemm(z16, rt.embed_w, emb, B * Kc, D, Din, bias=rt.embed_b, st=st)
-    ids_sorted, asm_idx, tgt_pos, ctx_pos, seq_to_tgt = ops.pred_indices(masks_x, masks_y, st, A)
+    emb = A((Mc, D), BF16)
+    ops.gemm(z16, rt.embed_w, emb, Mc, D, Din, bias=rt.embed_b, st=st)
     mi = mask_index % len(rt.mask_tokens)
-    x = A((B * S, D), F32)
-    ops.gather_rows(emb, x, asm_idx, fill=rt.mask_tokens[mi], st=st)
-    rope = ops.rope_table(ids_sorted, B * S, S, rt.grid, rt.grid, hd, dev, st, A)
-    x, blocks_saved = _run_blocks_forward(rt.blocks, x, B, S, heads, hd, rope, save, st, ws)
+    x = A((Ms, D), F32)
+    rope = A((Ms, 2, hd), torch.float16)
+    idx = []
+    c0 = s0 = 0
+    for mx, my, kc, kp, (b, sq) in zip(mxs, mys, Kcs, Kps, segs):
+        ids_sorted, asm_idx, tgt_pos, ctx_pos, seq_to_tgt = ops.pred_indices(mx, my, st, A)
+        ops.gather_rows(emb[c0:c0 + b * kc], x[s0:s0 + b * sq], asm_idx, fill=rt.mask_tokens[mi], st=st)
+        ops.rope_table(ids_sorted, b * sq, sq, rt.grid, rt.grid, hd, dev, st, out=rope[s0:s0 + b * sq])
+        idx.append((tgt_pos, ctx_pos, seq_to_tgt))
+        c0 += b * kc
+        s0 += b * sq
+    x, blocks_saved = _run_blocks_forward(rt.blocks, x, segs, None, heads, hd, rope, save, st, ws)
     # LayerNorm is row-wise, so norm(x)[targets] == norm(x[targets]) (predictor.py:233,240-242)
-    xg = A((B * Kp, D), F32)
-    ops.gather_rows(x, xg, tgt_pos, st=st)
-    y16 = A((B * Kp, D), BF16)
+    xg = A((Mp, D), F32)
+    s0 = t0 = 0
+    for (tgt_pos, _, _), kp, (b, sq) in zip(idx, Kps, segs):
+        ops.gather_rows(x[s0:s0 + b * sq], xg[t0:t0 + b * kp], tgt_pos, st=st)
+        s0 += b * sq
+        t0 += b * kp
+    y16 = A((Mp, D), BF16)
     mean = rstd = None
     if save:
-        mean = A((B * Kp,), F32)
-        rstd = A((B * Kp,), F32)
+        mean = A((Mp,), F32)
+        rstd = A((Mp,), F32)
     ops.layernorm_fwd(xg, rt.norm_w, rt.norm_b, y16, mean, rstd, 1e-6, st)
-    out = A((B * Kp, Din), BF16)
-    ops.gemm(y16, rt.proj_w, out, B * Kp, Din, D, bias=rt.proj_b, st=st)
+    out = A((Mp, Din), BF16)
+    ops.gemm(y16, rt.proj_w, out, Mp, Din, D, bias=rt.proj_b, st=st)
     saved = None
     if save:
-        saved = (z16, rope, blocks_saved, xg, mean, rstd, y16, tgt_pos, ctx_pos, seq_to_tgt, mi, B, Kc, Kp)
-    return out.view(B, Kp, Din), saved
+        saved = (z16, rope, blocks_saved, xg, mean, rstd, y16, idx, mi, B, Kcs, Kps)
+    if multi:
+        views, t0 = [], 0
+        for kp in Kps:
+            views.append(out[t0:t0 + B * kp].view(B, kp, Din))
+            t0 += B * kp
+        return views, saved
+    return out.view(B, Kps[0], Din), saved
 
 
 def predictor_backward(rt: PredictorRT, saved, dout, gbuf, ws=None, dz_out=None):
-    """dout bf16 [B, Kp, D_in].  Accumulates parameter grads into gbuf; returns d(z) bf16 [B, Kc, D_in]
-    (written to dz_out if given, else allocated from ws.act so it outlives this call's temporaries)."""
+    """dout bf16 [B, Kp, D_in] (or the row-concatenated [sum B*Kp_i, D_in] of a multi-mask forward).
+    Accumulates parameter grads into gbuf; returns d(z) bf16 [B, Kc, D_in] ([sum B*Kc_i, D_in] for multi-mask),
+    written to dz_out if given, else allocated from ws.act so it outlives this call's temporaries."""
     st = ops.stream()
-    z16, rope, blocks_saved, xg, mean, rstd, y16, tgt_pos, ctx_pos, seq_to_tgt, mi, B, Kc, Kp = saved
+    z16, rope, blocks_saved, xg, mean, rstd, y16, idx, mi, B, Kcs, Kps = saved
     dev = z16.device
     if ws is None:
         ws = TorchAlloc(dev)
-    S = Kc + Kp
+    segs = [(B, kc + kp) for kc, kp in zip(Kcs, Kps)]
+    Mc, Mp = B * sum(Kcs), B * sum(Kps)
+    Ms = sum(b * s for b, s in segs)
     D, heads, hd, Din = rt.D, rt.heads, rt.hd, rt.D_in
     g = rt.grads(gbuf)
-    dz = dz_out if dz_out is not None else ws.act((B * Kc, Din), BF16)
+    dz = dz_out if dz_out is not None else ws.act((Mc, Din), BF16)
     T = ws.tmp
     outer = ws.mark()
-    do = _as_bf16(dout.reshape(B * Kp, Din), st, ws)
+    do = _as_bf16(dout.reshape(Mp, Din), st, ws)
     # predictor_proj
-    dy16 = T((B * Kp, D), BF16)
-    ops.gemm(do, rt.proj_w, dy16, B * Kp, D, Din, b_mn=True, st=st)
-    ops.gemm(do, y16, g["proj_w"], Din, D, B * Kp, a_mn=True, b_mn=True, residual=g["proj_w"], st=st)
+    dy16 = T((Mp, D), BF16)
+    ops.gemm(do, rt.proj_w, dy16, Mp, D, Din, b_mn=True, st=st)
+    ops.gemm(do, y16, g["proj_w"], Din, D, Mp, a_mn=True, b_mn=True, residual=g["proj_w"], st=st)
     ops.colsum(do, g["proj_b"], True, st, T)
     # predictor_norm on the target rows, then scatter back into the sorted sequence
-    dxg = T((B * Kp, D), F32)
+    dxg = T((Mp, D), F32)
     ops.layernorm_bwd(dy16, xg, rt.norm_w, mean, rstd, dxg, dres=None, dgamma=g["norm_w"], dbeta=g["norm_b"], st=st,
                       alloc=T)
-    pp = (T((B * S, D), F32), T((B * S, D), F32))
+    pp = (T((Ms, D), F32), T((Ms, D), F32))
     dx = pp[0]
-    ops.gather_rows(dxg, dx, seq_to_tgt, fill=None, st=st)          # context rows get zeros
+    s0 = t0 = 0
+    for (_, _, seq_to_tgt), kp, (b, sq) in zip(idx, Kps, segs):
+        ops.gather_rows(dxg[t0:t0 + b * kp], dx[s0:s0 + b * sq], seq_to_tgt, fill=None, st=st)   # context rows get zeros
+        s0 += b * sq
+        t0 += b * kp
     k = 0
     for i in range(len(rt.blocks) - 1, -1, -1):
         k ^= 1
-        dx = block_backward(rt.blocks[i], g["blocks"][i], blocks_saved[i], dx, pp[k], B, S, heads, hd, rope, st, ws)
+        dx = block_backward(rt.blocks[i], g["blocks"][i], blocks_saved[i], dx, pp[k], segs, None, heads, hd, rope, st, ws)
         blocks_saved[i] = None
-    # mask token: sum of the gradients of every target slot (predictor.py:195-197)
-    dtg = T((B * Kp, D), F32)
-    ops.gather_rows(dx, dtg, tgt_pos, st=st)
+    # mask token: sum of the gradients of every target slot (predictor.py:195-197); predictor_embed inputs
+    dtg = T((Mp, D), F32)
+    demb = T((Mc, D), BF16)
+    s0 = t0 = c0 = 0
+    for (tgt_pos, ctx_pos, _), kc, kp, (b, sq) in zip(idx, Kcs, Kps, segs):
+        ops.gather_rows(dx[s0:s0 + b * sq], dtg[t0:t0 + b * kp], tgt_pos, st=st)
+        ops.gather_rows(dx[s0:s0 + b * sq], demb[c0:c0 + b * kc], ctx_pos, st=st)
+        s0 += b * sq
+        t0 += b * kp
+        c0 += b * kc
     ops.colsum(dtg, g["mask_tokens"][mi], True, st, T)
     # predictor_embed
-    demb = T((B * Kc, D), BF16)
-    ops.gather_rows(dx, demb, ctx_pos, st=st)
-    ops.gemm(demb, rt.embed_w, dz, B * Kc, Din, D, b_mn=True, st=st)
-    ops.gemm(demb, z16, g["embed_w"], D, Din, B * Kc, a_mn=True, b_mn=True, residual=g["embed_w"], st=st)
+    ops.gemm(demb, rt.embed_w, dz, Mc, Din, D, b_mn=True, st=st)
+    ops.gemm(demb, z16, g["embed_w"], D, Din, Mc, a_mn=True, b_mn=True, residual=g["embed_w"], st=st)
     ops.colsum(demb, g["embed_b"], True, st, T)
     ws.release(outer)
-    return dz.view(B, Kc, Din)
+    if len(Kcs) == 1:
+        return dz.view(B, Kcs[0], Din)
+    return dz.view(Mc, Din)

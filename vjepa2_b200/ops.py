@@ -128,11 +128,14 @@ def rope_seg(head_dim: int) -> int:
     return 2 * ((head_dim // 3) // 2)
 
 
-def rope_table(ids, n, period, Hp, Wp, head_dim, device, st=None, alloc=None):
+def rope_table(ids, n, period, Hp, Wp, head_dim, device, st=None, alloc=None, out=None):
     """ids: int64 [n] flattened token ids, or None for id(row) = row % period -> fp16 table [n, 2, head_dim]
-    (per-element cos then sin, see include/vjepa2_b200.h)."""
+    (per-element cos then sin, see include/vjepa2_b200.h).  out: optional pre-allocated table (rows of a larger one)."""
     shape = (n, 2, head_dim)
-    table = alloc(shape, torch.float16) if alloc is not None else torch.empty(shape, dtype=torch.float16, device=device)
+    if out is not None:
+        table = out
+    else:
+        table = alloc(shape, torch.float16) if alloc is not None else torch.empty(shape, dtype=torch.float16, device=device)
     _counting_check(C.load().vj_rope_table(_p(ids), n, period, Hp, Wp, head_dim, table.data_ptr(),
                                            st if st is not None else stream()), "vj_rope_table")
     return table
@@ -185,15 +188,19 @@ def mask_to_rows(masks, N, st=None):
     return out
 
 
-def im2col_tubelets(clips, ids, tubelet, patch, st=None, alloc=None):
-    """clips fp32 [B,C,T,H,W]; ids int64 [B,K] or None -> bf16 [B*K, C*tubelet*patch*patch]."""
+def im2col_tubelets(clips, ids, tubelet, patch, st=None, alloc=None, out=None):
+    """clips fp32 [B,C,T,H,W]; ids int64 [B,K] or None -> bf16 [B*K, C*tubelet*patch*patch].
+    out: optional pre-allocated destination (rows of a larger matrix)."""
     B, Cc, T, H, W = clips.shape
     if ids is not None:
         reps, K = ids.shape[0] // B, ids.shape[1]
     else:
         reps, K = 1, (T // tubelet) * (H // patch) * (W // patch)
     shape = (B * reps * K, Cc * tubelet * patch * patch)
-    cols = alloc(shape, BF16) if alloc is not None else torch.empty(shape, dtype=BF16, device=clips.device)
+    if out is not None:
+        cols = out
+    else:
+        cols = alloc(shape, BF16) if alloc is not None else torch.empty(shape, dtype=BF16, device=clips.device)
     _counting_check(C.load().vj_im2col_tubelets(clips.data_ptr(), _p(ids), cols.data_ptr(), B, Cc, T, H, W, tubelet, patch, K,
                                         reps, st if st is not None else stream()), "vj_im2col_tubelets")
     return cols

@@ -23,6 +23,7 @@ class _PredictorFn(torch.autograd.Function):
         rt = model.runtime()
         out, saved = engine.predictor_forward(rt, z, masks_x, masks_y, mask_index, save=True)
         ctx.rt, ctx.saved, ctx.z_dtype = rt, saved, z.dtype
+        ctx.mi = mask_index % len(rt.mask_tokens)
         return out
 
     @staticmethod
@@ -31,7 +32,7 @@ class _PredictorFn(torch.autograd.Function):
         fs = rt.fs
         gbuf = torch.zeros(fs.total, dtype=torch.float32, device=dout.device)
         dz = engine.predictor_backward(rt, ctx.saved, dout.contiguous(), gbuf)
-        mi = ctx.saved[10]
+        mi = ctx.mi
         ctx.saved = None
         used = {id(p) for p in fs.params} - {id(p) for k, p in enumerate(rt.model.mask_tokens) if k != mi}
         grads = tuple(fs.grad_view(gbuf, p) if (p.requires_grad and id(p) in used) else None for p in fs.params)

@@ -225,31 +225,39 @@ class JepaTrainStep:
             Bq, N, D = h.shape
             h2 = h.view(Bq * N, D)
             ops.layernorm_fwd(h2, None, None, h2, None, None, 1e-5, st)     # in place (row-local)
-            for j, (me, mp) in enumerate(zip(masks_enc[i], masks_pred[i])):
-                pair_no += 1
-                last = pair_no == n_pairs
-                me = me.contiguous()
-                mp = mp.contiguous()
-                # ---- context + predictor forward (train.py:420-423)
-                z, sv_e = engine.encoder_forward(enc_rt, c, me, grid, save=True, ws=ws)
-                pred, sv_p = engine.predictor_forward(pred_rt, z, me, mp, i, save=True, ws=ws)
-                # ---- loss (train.py:425-435) and its gradient, GradScaler-scaled (train.py:445)
-                dz = ws.act(tuple(pred.shape), pred.dtype)
-                inv = 1.0 / (n_pairs * pred.numel())
+            # ---- all masks of the group in ONE pass: the masked copies are row blocks of the same token matrix, so
+            #      every LayerNorm / GEMM / reduction launch covers them all (attention runs per mask); the reference
+            #      loops over the masks (wrappers.py:15-43), which is the same arithmetic row by row
+            mes = [m.contiguous() for m in masks_enc[i]]
+            mps = [m.contiguous() for m in masks_pred[i]]
+            pair_no += len(mes)
+            last = pair_no == n_pairs
+            # ---- context + predictor forward (train.py:420-423)
+            zs, sv_e = engine.encoder_forward(enc_rt, c, mes, grid, save=True, ws=ws)
+            preds, sv_p = engine.predictor_forward(pred_rt, zs, mes, mps, i, save=True, ws=ws)
+            # ---- loss (train.py:425-435) and its gradient, GradScaler-scaled (train.py:445)
+            Din = preds[0].shape[2]
+            rows = sum(pr.shape[0] * pr.shape[1] for pr in preds)
+            dz = ws.act((rows, Din), preds[0].dtype)
+            r0 = 0
+            for pr, mp in zip(preds, mps):
+                n = pr.shape[0] * pr.shape[1]
+                inv = 1.0 / (n_pairs * pr.numel())
                 mk = ws.mark()
-                ops.l1_loss(pred, h, mp, self.loss_accum, dz, inv, inv, self.scale, st, ws.tmp)
+                ops.l1_loss(pr, h, mp, self.loss_accum, dz[r0:r0 + n], inv, inv, self.scale, st, ws.tmp)
                 ws.release(mk)
-                # ---- backward
-                dzenc = engine.predictor_backward(pred_rt, sv_p, dz, pfs.g32, ws=ws)
-                del sv_p
-                if last and self.world > 1:
-                    self.bucketer.submit(pfs.g32, 0, pfs.total)
-                    hook = lambda b, efs=efs: self.bucketer.submit(efs.g32, *self._enc_ranges[b])  # noqa: E731
-                else:
-                    hook = None
-                engine.encoder_backward(enc_rt, sv_e, dzenc, efs.g32, ws=ws, on_block_done=hook)
-                del sv_e, z, pred, dz, dzenc
-                ws._act.reset()                                   # this pair's activations are dead
+                r0 += n
+            # ---- backward
+            dzenc = engine.predictor_backward(pred_rt, sv_p, dz, pfs.g32, ws=ws)
+            del sv_p
+            if last and self.world > 1:
+                self.bucketer.submit(pfs.g32, 0, pfs.total)
+                hook = lambda b, efs=efs: self.bucketer.submit(efs.g32, *self._enc_ranges[b])  # noqa: E731
+            else:
+                hook = None
+            engine.encoder_backward(enc_rt, sv_e, dzenc, efs.g32, ws=ws, on_block_done=hook)
+            del sv_e, zs, preds, dz, dzenc
+            ws._act.reset()                                       # this group's activations are dead
         self.bucketer.wait()
 
         # ---- unscale + inf check + AdamW (train.py:446-451; app/vjepa/utils.py:239), flat kernels
