@@ -366,7 +366,7 @@ def main():
         s.record()
         r = real_gemm(a, b, out, M, N, K, **kw)
         e.record()
-        recs.append((s, e, 2.0 * M * N * K))
+        recs.append((s, e, 2.0 * M * N * K, (M, N, K, bool(kw.get("gelu")), bool(kw.get("a_mn")), bool(kw.get("b_mn")))))
         return r
 
     if rank == 0:
@@ -380,14 +380,36 @@ def main():
     eng.ops.gemm = real_gemm
     roof = None
     if rank == 0:
-        g_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
-        g_fl = sum(f for _, _, f in recs)
-        achieved = g_fl / (g_ms / 1e3) / 1e12
-        roof = dict(bound="tensor", kernel="vj::gemm_kernel (tcgen05 GEMM, all fwd/dgrad/wgrad launches of one step)",
+        g_ms = sum(s.elapsed_time(e) for s, e, _, _ in recs)
+        g_fl = sum(f for _, _, f, _ in recs)
+        # the dominant launch: fc1 forward (+bias, +GELU) of the target encoder, the largest single share of the step
+        hid = MODELS[args.model][3]
+        dom = [(s, e, f, k) for s, e, f, k in recs if k[3] and not k[4] and not k[5] and k[1] == hid and k[0] == args.batch * NTOK]
+        if not dom:
+            dom = recs
+        d_ms = sum(s.elapsed_time(e) for s, e, _, _ in dom) / len(dom)
+        d_fl = sum(f for _, _, f, _ in dom) / len(dom)
+        Md, Nd, Kd = dom[0][3][:3]
+        achieved = d_fl / (d_ms / 1e3) / 1e12
+        traffic, traffic_src = None, None
+        try:        # dram__bytes_read.sum + dram__bytes_write.sum of ONE such launch, from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_ncu_traffic.json")))["fc1gelu"]
+            if (Md, Nd, Kd) == (49152, 6144, 1408):
+                traffic, traffic_src = tj["dram_bytes"], "profiles/r01b_ncu_full_summary.txt (ncu --set full, same shape and epilogue)"
+        except Exception:
+            pass
+        roof = dict(bound="tensor",
+                    kernel=f"vj::gemm_kernel<256,0,0,0> (tcgen05 GEMM): fc1 forward +bias +GELU of the target encoder, "
+                           f"M={Md} N={Nd} K={Kd}",
                     achieved=achieved, peak=peaks["sustained"], unit="TFLOP/s", frac=achieved / peaks["sustained"],
                     peak_source=f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)",
-                    traffic=None, launches=len(recs), gemm_ms_per_step=g_ms, step_ms_instrumented=evs.elapsed_time(eve),
-                    gemm_share_of_step=g_ms / evs.elapsed_time(eve))
+                    flops_per_launch=d_fl, ms_per_launch=d_ms, launches=len(dom),
+                    algorithmic_bytes_per_launch=2.0 * (Md * Kd + Nd * Kd + Md * Nd),
+                    traffic=traffic, traffic_source=traffic_src,
+                    all_gemms=dict(achieved=g_fl / (g_ms / 1e3) / 1e12, frac=g_fl / (g_ms / 1e3) / 1e12 / peaks["sustained"],
+                                   launches=len(recs), gemm_ms_per_step=g_ms,
+                                   step_ms_instrumented=evs.elapsed_time(eve),
+                                   gemm_share_of_step=g_ms / evs.elapsed_time(eve)))
     barrier()
 
     if args.profile_ops and rank == 0 and world == 1:
