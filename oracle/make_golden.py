@@ -87,6 +87,7 @@ def build_ref_models():
 def main():
     torch.set_num_threads(8)
     G = {}
+    G2 = {}     # second file (tests/golden/ref_golden_infer.pt): optimizer moments + encoder-only inference paths
 
     # 1. rotate_queries_or_keys (modules.py:26-50) fwd + autograd grad, fp64 and fp32
     g = torch.Generator().manual_seed(11)
@@ -194,6 +195,12 @@ def main():
         G["step.after.tgt." + k] = target.state_dict()[k].clone()
     for k in ["predictor_embed.weight", "mask_tokens.0", "mask_tokens.1", "predictor_proj.bias"]:
         G["step.after.pred." + k] = pred.state_dict()[k].clone()
+    # AdamW moments after the two steps (what a checkpoint's "opt" entry carries, train.py:320)
+    for k in ["blocks.0.attn.qkv.weight", "blocks.1.mlp.fc2.bias", "norm.weight"]:
+        st_ = optimizer.state[dict(enc.named_parameters())[k]]
+        G2["opt.enc.exp_avg." + k], G2["opt.enc.exp_avg_sq." + k] = st_["exp_avg"].clone(), st_["exp_avg_sq"].clone()
+        G2["opt.step"] = st_["step"].clone()
+    assert dict(pred.named_parameters())["mask_tokens.1"] not in optimizer.state
 
     # 7. ViT-H geometry in miniature: head_dim 80 (RoPE segments 26/26/26 + 2 pass-through dims)
     encH = VisionTransformer(img_size=TINY["img"], patch_size=16, num_frames=TINY["frames"], tubelet_size=2,
@@ -204,11 +211,37 @@ def main():
         G["encH.full"] = encH(clips)
         G["encH.masked"] = encH(clips, me)
 
+    # 8. encoder-only inference: out_layers (vision_transformer.py:204-208) and the evals' ClipAggregation wrappers
+    #    (evals/video_classification_frozen/modelcustom/vit_encoder_multiclip{,_multilevel}.py), 2 clips x 2 views
+    from evals.video_classification_frozen.modelcustom.vit_encoder_multiclip import ClipAggregation as CA
+    from evals.video_classification_frozen.modelcustom.vit_encoder_multiclip_multilevel import ClipAggregation as CAML
+    t = TINY
+    enc8 = VisionTransformer(img_size=t["img"], patch_size=16, num_frames=t["frames"], tubelet_size=2,
+                             embed_dim=t["dim"], depth=t["depth"], num_heads=t["heads"], mlp_ratio=t["mlp_ratio"],
+                             qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), use_rope=True)
+    enc8.load_state_dict(w_enc, strict=True)
+    enc8ml = VisionTransformer(img_size=t["img"], patch_size=16, num_frames=t["frames"], tubelet_size=2,
+                               embed_dim=t["dim"], depth=t["depth"], num_heads=t["heads"], mlp_ratio=t["mlp_ratio"],
+                               qkv_bias=True, norm_layer=partial(nn.LayerNorm, eps=1e-6), use_rope=True,
+                               out_layers=[0, 1])
+    enc8ml.load_state_dict(w_enc, strict=True)
+    views = [[tiny_clips(2, seed=20 + 2 * i + j) for j in range(2)] for i in range(2)]
+    with torch.no_grad():
+        outs = enc8ml(clips)
+        G2["infer.out_layers.0"], G2["infer.out_layers.1"] = outs[0], outs[1]
+        for j, o in enumerate(CA(enc8, tubelet_size=2)(views)):
+            G2[f"infer.agg.view{j}"] = o
+        for j, o in enumerate(CAML(enc8ml, tubelet_size=2)(views)):
+            G2[f"infer.aggml.view{j}"] = o
+
     out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     path = os.path.join(out_dir, "ref_golden.pt")
     torch.save({k: v.contiguous() for k, v in G.items()}, path)
     print("wrote", path, os.path.getsize(path), "bytes;", len(G), "tensors; torch", torch.__version__)
+    path2 = os.path.join(out_dir, "ref_golden_infer.pt")
+    torch.save({k: v.contiguous() for k, v in G2.items()}, path2)
+    print("wrote", path2, os.path.getsize(path2), "bytes;", len(G2), "tensors")
 
 
 if __name__ == "__main__":

@@ -162,7 +162,8 @@ def block(x, w, pfx, heads, ids, Hp, Wp):
 # ----------------------------------------------------------------------------
 # VisionTransformer.forward (src/models/vision_transformer.py:161-213), use_rope=True
 # ----------------------------------------------------------------------------
-def vit_forward(w, x, masks, depth, heads, tubelet=2, patch=16):
+def vit_forward(w, x, masks, depth, heads, tubelet=2, patch=16, out_layers=None):
+    """VisionTransformer.forward (vision_transformer.py:161-213); out_layers -> list of norm(x) after those blocks."""
     if masks is not None and not isinstance(masks, list):
         masks = [masks]
     _, _, T, H, W = x.shape
@@ -173,8 +174,13 @@ def vit_forward(w, x, masks, depth, heads, tubelet=2, patch=16):
         ids = torch.cat(masks, 0)
     else:
         ids = torch.arange(x.shape[1])
+    outs = []
     for i in range(depth):
         x = block(x, w, f"blocks.{i}.", heads, ids, Hp, Wp)
+        if out_layers is not None and i in out_layers:
+            outs.append(layer_norm(x, w["norm.weight"], w["norm.bias"]))
+    if out_layers is not None:
+        return outs
     return layer_norm(x, w["norm.weight"], w["norm.bias"])
 
 

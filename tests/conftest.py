@@ -30,3 +30,10 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import torch
     return torch.load(os.path.join(ROOT, "tests", "golden", "ref_golden.pt"), map_location="cpu")
+
+
+@pytest.fixture(scope="session")
+def golden_infer():
+    """Optimizer moments + encoder-only inference outputs of the real reference (oracle/make_golden.py section 8)."""
+    import torch
+    return torch.load(os.path.join(ROOT, "tests", "golden", "ref_golden_infer.pt"), map_location="cpu")

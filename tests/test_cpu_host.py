@@ -146,3 +146,148 @@ def test_bucketed_allreduce_gloo_world2(tmp_path):
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out.decode()
         assert b"ok" in out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# checkpoint wire format (train.py:315-333, app/vjepa/utils.py:90-135, src/hub/backbones.py:22-28)
+# ---------------------------------------------------------------------------------------------------------------
+def _tiny_models():
+    from functools import partial
+    import torch.nn as nn
+    from vjepa2_b200.predictor import vit_predictor
+    from vjepa2_b200.vision_transformer import VisionTransformer
+    from vjepa2_b200.wrappers import MultiSeqWrapper, PredictorMultiSeqWrapper
+    enc = VisionTransformer(img_size=32, patch_size=16, num_frames=4, embed_dim=64, depth=2, num_heads=2,
+                            norm_layer=partial(nn.LayerNorm, eps=1e-6), use_rope=True)
+    pred = vit_predictor(img_size=32, patch_size=16, num_frames=4, embed_dim=64, predictor_embed_dim=64, depth=1,
+                         num_heads=2, use_mask_tokens=True, num_mask_tokens=2, zero_init_mask_tokens=True,
+                         use_rope=True)
+    return MultiSeqWrapper(enc), PredictorMultiSeqWrapper(pred)
+
+
+def _reference_style_optimizer(encoder, predictor):
+    # init_opt's four groups, written against the WRAPPED modules exactly as app/vjepa/utils.py:224-239 does
+    groups = [
+        {"params": (p for n, p in encoder.named_parameters() if ("bias" not in n) and (len(p.shape) != 1))},
+        {"params": (p for n, p in predictor.named_parameters() if ("bias" not in n) and (len(p.shape) != 1))},
+        {"params": (p for n, p in encoder.named_parameters() if ("bias" in n) or (len(p.shape) == 1)),
+         "WD_exclude": True, "weight_decay": 0},
+        {"params": (p for n, p in predictor.named_parameters() if ("bias" in n) or (len(p.shape) == 1)),
+         "WD_exclude": True, "weight_decay": 0},
+    ]
+    return torch.optim.AdamW(groups, betas=(0.9, 0.999), eps=1e-8)
+
+
+def test_optimizer_state_dict_matches_torch_adamw_layout():
+    from vjepa2_b200 import checkpoint as C
+    enc, pred = _tiny_models()
+    opt = _reference_style_optimizer(enc, pred)
+    g = torch.Generator().manual_seed(3)
+    unused = pred.backbone.mask_tokens[1]
+    for p in list(enc.parameters()) + list(pred.parameters()):
+        if p is not unused:                           # a parameter without a gradient gets no optimizer state
+            p.grad = torch.randn(p.shape, generator=g)
+    for grp in opt.param_groups:
+        grp["lr"] = 1e-3
+        if not grp.get("WD_exclude", False):
+            grp["weight_decay"] = 0.04
+    opt.step()
+    opt.step()
+    ref_sd = opt.state_dict()
+
+    groups = C.opt_param_groups(enc, pred)
+    by_param = {}
+    for grp in opt.param_groups:
+        for p in grp["params"]:
+            if p in opt.state:
+                by_param[id(p)] = (opt.state[p]["exp_avg"], opt.state[p]["exp_avg_sq"])
+    ours = C.build_opt_state_dict(groups, lambda t: by_param.get(id(t)), step=2, lr=1e-3, wd=0.04)
+
+    assert [g_["params"] for g_ in ours["param_groups"]] == [g_["params"] for g_ in ref_sd["param_groups"]]
+    for a, b in zip(ours["param_groups"], ref_sd["param_groups"]):
+        assert set(a.keys()) == set(b.keys())
+        for k in ("lr", "weight_decay", "betas", "eps", "amsgrad"):
+            assert a[k] == b[k], k
+        assert a.get("WD_exclude", None) == b.get("WD_exclude", None)
+    assert set(ours["state"].keys()) == set(ref_sd["state"].keys())
+    for k, s in ref_sd["state"].items():
+        assert float(ours["state"][k]["step"]) == float(s["step"]) == 2.0
+        assert torch.equal(ours["state"][k]["exp_avg"], s["exp_avg"])
+        assert torch.equal(ours["state"][k]["exp_avg_sq"], s["exp_avg_sq"])
+
+    # torch's own loader accepts it, and the inverse mapping restores every moment bit for bit
+    opt2 = _reference_style_optimizer(enc, pred)
+    opt2.load_state_dict(ours)
+    bufs = {id(t): (torch.full(t.shape, 7.0), torch.full(t.shape, 7.0)) for grp in groups for _, t in grp}
+    step = C.restore_opt_state(groups, ref_sd, lambda t: bufs[id(t)])
+    assert step == 2
+    for grp in groups:
+        for _, t in grp:
+            if t is unused:
+                assert float(bufs[id(t)][0].abs().sum()) == 0.0
+            else:
+                assert torch.equal(bufs[id(t)][0], by_param[id(t)][0])
+                assert torch.equal(bufs[id(t)][1], by_param[id(t)][1])
+
+
+def test_checkpoint_key_prefixes_and_pretrained_loading():
+    from vjepa2_b200 import checkpoint as C
+    enc, _ = _tiny_models()
+    sd = {"module.backbone." + k: v.clone() + 1.0 for k, v in enc.backbone.state_dict().items()}
+    sd["module.backbone.pos_embed"] = torch.zeros(1, 8, 64)               # sincos checkpoints carry one (backbones.py:132)
+    cleaned = C.clean_backbone_key(sd)
+    assert "patch_embed.proj.weight" in cleaned and not any(k.startswith("module") for k in cleaned)
+    bad = dict(sd)
+    bad["module.backbone.norm.weight"] = torch.zeros(3)                   # wrong shape: the model's tensor is kept
+    before = enc.backbone.norm.weight.detach().clone()
+    msg = C.load_pretrained(enc, {"target_encoder": bad}, checkpoint_key="target_encoder")
+    assert list(msg.unexpected_keys) == ["pos_embed"] and not msg.missing_keys
+    assert torch.equal(enc.backbone.norm.weight, before)
+    assert torch.equal(enc.backbone.blocks[0].attn.qkv.weight, sd["module.backbone.blocks.0.attn.qkv.weight"])
+    assert C._prefix_of(enc) == "backbone."
+
+    class _DDP(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+    assert C._prefix_of(_DDP(enc)) == "module.backbone."
+
+
+def test_clip_aggregation_regroups_views_and_clips_like_the_reference():
+    """vit_encoder_multiclip.py:107-149 with a stand-in encoder (token = clip statistics), so the regrouping of
+    [clips x views x batch] into per-view time-concatenated token lists is checked without a GPU."""
+    from vjepa2_b200.inference import ClipAggregation
+
+    class _Enc(torch.nn.Module):
+        embed_dim, num_heads, tubelet_size = 4, 1, 2
+
+        def forward(self, x):                                   # [n, C, F, H, W] -> [n, (F/2)*S, D], S = 3
+            n, _, F, _, _ = x.shape
+            t = x.reshape(n, 3, F // 2, 2, -1).mean(dim=(1, 3, 4))           # [n, T]
+            return t[:, :, None, None].expand(n, F // 2, 3, 4).reshape(n, -1, 4).contiguous()
+
+    B, F = 2, 4
+    g = torch.Generator().manual_seed(0)
+    x = [[torch.randn(B, 3, F, 8, 8, generator=g) for _ in range(3)] for _ in range(2)]     # 2 clips x 3 views
+    agg = ClipAggregation(_Enc(), tubelet_size=2)
+    outs = agg(x)
+    assert len(outs) == 3 and outs[0].shape == (B, 2 * (F // 2) * 3, 4)
+    enc = _Enc()
+    for j in range(3):
+        want = torch.cat([enc(x[i][j]).reshape(B, F // 2, 3, 4) for i in range(2)], dim=1).flatten(1, 2)
+        assert torch.equal(outs[j], want)
+
+
+def test_hub_constructors_build_reference_shapes():
+    from vjepa2_b200 import inference as I
+    enc, pred = I.vjepa2_vit_large(num_frames=16)
+    assert enc.embed_dim == 1024 and len(enc.blocks) == 24 and enc.num_patches == 8 * 16 * 16
+    assert pred.predictor_embed.weight.shape == (384, 1024) and len(pred.mask_tokens) == 10
+    with pytest.raises(RuntimeError):
+        I.vjepa2_vit_large(pretrained=True)                    # no download path: a local checkpoint is required
+    ck = {"encoder": {"module.backbone." + k: v for k, v in enc.state_dict().items()},
+          "predictor": {"module.backbone." + k: v for k, v in pred.state_dict().items()}}
+    ck["encoder"]["module.backbone.pos_embed"] = torch.zeros(1, 2048, 1024)
+    enc2, pred2 = I.vjepa2_vit_large(pretrained=True, checkpoint=ck, num_frames=16)
+    assert torch.equal(enc2.blocks[3].mlp.fc1.weight, enc.blocks[3].mlp.fc1.weight)
+    assert torch.equal(pred2.predictor_proj.weight, pred.predictor_proj.weight)

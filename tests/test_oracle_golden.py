@@ -78,7 +78,7 @@ def test_schedules(golden):
     close(torch.tensor(wd, dtype=torch.float64), golden["sched.wd"], 1e-12, 0)
 
 
-def test_train_step(golden):
+def test_train_step(golden, golden_infer):
     w_enc, w_pred = tiny_weights()
     st = O.StepState(w_enc, w_pred, dict(depth=TINY["depth"], heads=TINY["heads"]),
                      dict(depth=TINY["pred_depth"], heads=TINY["pred_heads"], grid_size=GRID, num_patches=NTOK,
@@ -102,3 +102,18 @@ def test_train_step(golden):
             close(st.w_tgt[k[len("step.after.tgt."):]], v, 1e-4, 1e-6)
         if k.startswith("step.after.pred."):
             close(st.w_pred[k[len("step.after.pred."):]], v, 1e-4, 1e-6)
+    # AdamW moments after the two steps (what a checkpoint's "opt" entry carries)
+    assert float(golden_infer["opt.step"]) == st.step == 2
+    for k, v in golden_infer.items():
+        if k.startswith("opt.enc.exp_avg_sq."):
+            close(st.adam_enc[k[len("opt.enc.exp_avg_sq."):]][1], v, 2e-3, 1e-12)
+        elif k.startswith("opt.enc.exp_avg."):
+            close(st.adam_enc[k[len("opt.enc.exp_avg."):]][0], v, 1e-3, 1e-8)
+
+
+def test_encoder_out_layers(golden_infer):
+    w_enc, _ = tiny_weights()
+    outs = O.vit_forward(w_enc, tiny_clips(2), None, TINY["depth"], TINY["heads"], out_layers=[0, 1])
+    assert len(outs) == 2
+    close(outs[0], golden_infer["infer.out_layers.0"])
+    close(outs[1], golden_infer["infer.out_layers.1"])

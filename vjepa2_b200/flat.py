@@ -104,6 +104,9 @@ class FlatStore:
             self.exp_avg = torch.zeros(self.total, dtype=torch.float32, device=self.device)
             self.exp_avg_sq = torch.zeros(self.total, dtype=torch.float32, device=self.device)
 
+    def is_frozen(self, p) -> bool:
+        return bool(self.flags_host[self.offsets[self.index[id(p)]] // TILE] & FLAG_FROZEN)
+
     def set_frozen(self, params, frozen=True):
         """Mark parameters that never get a gradient (e.g. unused predictor mask tokens, a1/a17)."""
         for p in params:

@@ -147,13 +147,17 @@ class JepaTrainStep:
         for p in self.target_encoder.parameters():
             p.requires_grad = False                                # train.py:282-283
         self.betas, self.eps = betas, eps
+        self.ipe = ipe
+        self.last_lr_wd = (start_lr, weight_decay)
         T_max = int(ipe_scale * epochs * ipe)
         self.scheduler = WarmupCosineSchedule(int(warmup * ipe), start_lr, lr, T_max, final_lr)
         self.wd_scheduler = CosineWDSchedule(weight_decay, T_max, final_weight_decay)
         self.momentum = momentum_schedule(ema, ipe, epochs, ipe_scale)
         self.bucketer = GradBucketer(process_group)
         self.world = self.bucketer.world
-        self._step = 0
+        # optimizer step count (torch keeps it per parameter; an inf-skipped step still counts here, which only
+        # differs from torch after a GradScaler overflow -- never seen with bf16 at these scales)
+        self.applied_steps = 0
         # the step manages bf16 shadows itself (AdamW / EMA kernels rewrite them)
         for m in (self.encoder, self.predictor, self.target_encoder):
             m._manual_shadows = False
@@ -196,12 +200,35 @@ class JepaTrainStep:
             fs.set_frozen([t for k, t in enumerate(toks) if k not in used], True)
             self._frozen_key = key
 
+    # ------------------------------------------------------------------------------------------ resume support
+    def reload_weights(self):
+        """After load_state_dict / any in-place edit of the fp32 parameters: rebuild the bf16 operand shadows."""
+        for rt in (self.enc_rt, self.pred_rt, self.tgt_rt):
+            if not rt.fs.valid():
+                raise RuntimeError("vjepa2_b200: parameters were re-allocated (e.g. .to()); build a new JepaTrainStep")
+            rt.fs.refresh_shadows()
+
+    def set_scaler(self, scale, growth_tracker=0):
+        """GradScaler.load_state_dict (app/vjepa/utils.py:121-122)."""
+        self.scale.fill_(float(scale))
+        self.inv_scale.fill_(1.0 / (float(scale) * self.world))
+        self.growth_tracker.fill_(int(growth_tracker))
+
+    def fast_forward(self, n_steps):
+        """train.py:309-313: advance the LR / WD / momentum schedules by n_steps iterations without training."""
+        for _ in range(int(n_steps)):
+            lr = self.scheduler.step()
+            wd = self.wd_scheduler.step()
+            next(self.momentum)
+            self.last_lr_wd = (lr, wd)
+
     def step(self, clips, masks_enc, masks_pred):
         """clips: list (one fp32 [B,3,T,H,W] tensor per fpc group); masks_enc / masks_pred: list over
         groups of lists over masks of int64 [B, K].  Returns (loss [1] fp32 device tensor, lr, wd)."""
-        self._step += 1
+        self.applied_steps += 1
         new_lr = self.scheduler.step()
         new_wd = self.wd_scheduler.step()
+        self.last_lr_wd = (new_lr, new_wd)
         st = ops.stream()
         enc_rt, pred_rt, tgt_rt = self.enc_rt, self.pred_rt, self.tgt_rt
         efs, pfs, tfs = enc_rt.fs, pred_rt.fs, tgt_rt.fs
@@ -266,7 +293,7 @@ class JepaTrainStep:
         b1, b2 = self.betas
         for fs in (efs, pfs):
             ops.adamw_step(fs.p32, fs.g32, fs.exp_avg, fs.exp_avg_sq, fs.p16, fs.flags, new_lr, b1, b2, self.eps,
-                           new_wd, self._step, self.inv_scale, self.found_inf, st)
+                           new_wd, self.applied_steps, self.inv_scale, self.found_inf, st)
         if self.mixed_precision:
             ops.scaler_update(self.scale, self.inv_scale, self.growth_tracker, self.found_inf, float(self.world), st=st)
         else:
