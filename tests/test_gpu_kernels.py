@@ -317,6 +317,26 @@ def test_colsum_and_l1(dev):
     assert torch.equal(dz.float(), (torch.sign(z.float() - hg) * (4.0 * 0.5 / z.numel())).bfloat16().float())
 
 
+@pytest.mark.parametrize("rows,D,dt", [(49152 // 8, 1408, BF16), (1001, 384, BF16), (37, 6144, BF16), (5, 128, F32),
+                                       (3000, 1536, F32), (700, 130, BF16), (1, 64, BF16)])
+def test_colsum_shapes_repeatable(dev, rows, D, dt):
+    """Bias-gradient column sums: 16-byte-load kernel (D % 8 == 0) with in-kernel finalisation, the narrow fallback
+    (D = 130), ragged row counts, accumulate on / off; two launches give bit-identical sums (fixed order)."""
+    from vjepa2_b200 import ops
+    x = randn(rows, D, seed=rows + D, dtype=dt).to(dev)
+    ref = x.double().sum(0)
+    a = torch.full((D,), 3.0, device=dev)
+    ops.colsum(x, a, True)
+    b = torch.full((D,), -7.0, device=dev)
+    ops.colsum(x, b, False)
+    c = torch.empty(D, device=dev)
+    ops.colsum(x, c, False)
+    assert torch.equal(b, c)
+    tol = 1e-5 * float(x.double().abs().sum(0).max()) + 1e-6
+    assert float((b.double() - ref).abs().max()) < tol
+    assert float((a.double() - 3.0 - ref).abs().max()) < tol + 1e-5
+
+
 def test_flat_optimizer_kernels(dev):
     import vjepa_oracle as O
     from vjepa2_b200 import ops

@@ -240,7 +240,7 @@ static inline unsigned ln_grid(long long rows) {
 // ---------------------------------------------------------------- column reductions
 // partial[chunk][c] = sum over the chunk's rows of f(r,c);  WITH_XHAT: also dy*xhat (LN dgamma).
 // block (32, 8): thread owns 2 adjacent columns, warps stride over rows.  grid (ceil(D/64), chunks).
-constexpr int COL_CHUNKS_MAX = 64;
+constexpr int COL_CHUNKS_MAX = 128;
 
 __device__ __forceinline__ float2 load2(const void* base, int dtype, long long off) {
   if (dtype == VJ_BF16) {
@@ -310,11 +310,143 @@ __global__ void colreduce_final_kernel(const float* __restrict__ part, float* __
 }
 
 static inline int col_chunks(long long rows) {
-  long long c = (rows + 255) / 256;
+  long long c = (rows + 127) / 128;
   if (c < 1) c = 1;
   if (c > COL_CHUNKS_MAX) c = COL_CHUNKS_MAX;
   return (int)c;
 }
+
+// Wide variant (D % 8 == 0): a thread owns 8 adjacent columns (one 16-byte load per bf16 row, two per fp32 row), a
+// warp covers 256 columns = 512 contiguous bytes per row, four rows in flight per thread.  The last CTA of a column
+// group to finish (ticket counter, self-resetting) adds the chunk partials in chunk order and writes / accumulates
+// the result, so there is no separate finalize launch and the sum order stays deterministic.
+constexpr int COLW_GROUPS_MAX = 256;                   // D <= 65536
+__device__ unsigned int g_colw_tickets[COLW_GROUPS_MAX];
+
+template <bool WITH_XHAT>
+__global__ void __launch_bounds__(256) colreduce_wide_kernel(const void* __restrict__ dy, int dy_dtype,
+                                                             const void* __restrict__ x, int x_dtype,
+                                                             const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd,
+                                                             float* __restrict__ part_sum,   // [chunks][D]
+                                                             float* __restrict__ part_xh,    // [chunks][D]
+                                                             float* __restrict__ out_sum,    // [D] or null
+                                                             float* __restrict__ out_xh,     // [D] or null
+                                                             long long rows, int D, long long rows_per_chunk,
+                                                             int accumulate) {
+  __shared__ float sm[WITH_XHAT ? 2 : 1][8][256 + 8];
+  __shared__ unsigned int s_ticket;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int col = blockIdx.x * 256 + tx * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  const long long r1 = min(rows, r0 + rows_per_chunk);
+  float a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = b[k] = 0.f;
+  if (col < D) {
+    long long r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {                      // four rows (8 apart) in flight
+      float d[4][8], xv[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8(dy, dy_dtype, (r + 8 * u) * D + col, d[u]);
+      if (WITH_XHAT) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) load8(x, x_dtype, (r + 8 * u) * D + col, xv[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (WITH_XHAT) {
+          const float m = __ldg(mean + r + 8 * u), rs = __ldg(rstd + r + 8 * u);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { a[k] += d[u][k]; b[k] += d[u][k] * (xv[u][k] - m) * rs; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) a[k] += d[u][k];
+        }
+      }
+    }
+    for (; r < r1; r += 8) {
+      float d[8], xv[8];
+      load8(dy, dy_dtype, r * D + col, d);
+      if (WITH_XHAT) {
+        load8(x, x_dtype, r * D + col, xv);
+        const float m = __ldg(mean + r), rs = __ldg(rstd + r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { a[k] += d[k]; b[k] += d[k] * (xv[k] - m) * rs; }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += d[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sm[0][ty][tx * 8 + k] = a[k];
+    if (WITH_XHAT) sm[WITH_XHAT ? 1 : 0][ty][tx * 8 + k] = b[k];
+  }
+  __syncthreads();
+  const int t = ty * 32 + tx;
+  const int c = blockIdx.x * 256 + t;
+  if (c < D) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sm[0][w][t];
+    part_sum[(long long)blockIdx.y * D + c] = s;
+    if (WITH_XHAT) {
+      float q = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) q += sm[WITH_XHAT ? 1 : 0][w][t];
+      part_xh[(long long)blockIdx.y * D + c] = q;
+    }
+  }
+  // ---- last CTA of this column group adds the partials: warp ty takes chunks ty, ty+8, ... (fixed order)
+  __threadfence();
+  __syncthreads();
+  if (t == 0) s_ticket = atomicAdd(&g_colw_tickets[blockIdx.x], 1u);
+  __syncthreads();
+  if (s_ticket != gridDim.y - 1) return;
+  __threadfence();
+  const int chunks = (int)gridDim.y;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = b[k] = 0.f;
+  if (col < D) {
+#pragma unroll 4
+    for (int k = ty; k < chunks; k += 8) {
+      const float4* ps = reinterpret_cast<const float4*>(part_sum + (long long)k * D + col);
+      const float4 u = __ldcg(ps), v = __ldcg(ps + 1);
+      a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w; a[4] += v.x; a[5] += v.y; a[6] += v.z; a[7] += v.w;
+      if (WITH_XHAT) {
+        const float4* px = reinterpret_cast<const float4*>(part_xh + (long long)k * D + col);
+        const float4 p = __ldcg(px), q = __ldcg(px + 1);
+        b[0] += p.x; b[1] += p.y; b[2] += p.z; b[3] += p.w; b[4] += q.x; b[5] += q.y; b[6] += q.z; b[7] += q.w;
+      }
+    }
+  }
+  __syncthreads();                                       // everyone is done reading sm from the first phase
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sm[0][ty][tx * 8 + k] = a[k];
+    if (WITH_XHAT) sm[WITH_XHAT ? 1 : 0][ty][tx * 8 + k] = b[k];
+  }
+  __syncthreads();
+  if (c < D) {
+    if (out_sum) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += sm[0][w][t];
+      out_sum[c] = accumulate ? out_sum[c] + s : s;
+    }
+    if (WITH_XHAT && out_xh) {
+      float q = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) q += sm[WITH_XHAT ? 1 : 0][w][t];
+      out_xh[c] = accumulate ? out_xh[c] + q : q;
+    }
+  }
+  if (t == 0) g_colw_tickets[blockIdx.x] = 0u;          // ready for the next launch on this stream
+}
+
+static inline bool colw_ok(int64_t D) { return D % 8 == 0 && (D + 255) / 256 <= COLW_GROUPS_MAX; }
 
 // ---------------------------------------------------------------- RoPE
 // Table layout (fp16): [row][2][hd] -- cos then sin PER ELEMENT d of the head: angle index of element d in
@@ -780,13 +912,20 @@ extern "C" int vj_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int
     const long long rpc = (rows + chunks - 1) / chunks;
     float* ps = reinterpret_cast<float*>(scratch);
     float* px = ps + (size_t)chunks * D;
-    dim3 grid((unsigned)((D + 63) / 64), (unsigned)chunks), block(32, 8);
-    colreduce_kernel<true><<<grid, block, 0, STREAM(stream)>>>(dy, dy_dtype, x, x_dtype, mean, rstd, ps, px, rows,
-                                                              (int)D, rpc);
-    VJ_LAUNCH_CHECK();
-    if (dbeta) colreduce_final_kernel<<<(unsigned)((D + 255) / 256), 256, 0, STREAM(stream)>>>(ps, dbeta, chunks, (int)D, 1);
-    if (dgamma) colreduce_final_kernel<<<(unsigned)((D + 255) / 256), 256, 0, STREAM(stream)>>>(px, dgamma, chunks, (int)D, 1);
-    VJ_LAUNCH_CHECK();
+    if (colw_ok(D)) {
+      dim3 grid((unsigned)((D + 255) / 256), (unsigned)chunks), block(32, 8);
+      colreduce_wide_kernel<true><<<grid, block, 0, STREAM(stream)>>>(dy, dy_dtype, x, x_dtype, mean, rstd, ps, px,
+                                                                     dbeta, dgamma, rows, (int)D, rpc, 1);
+      VJ_LAUNCH_CHECK();
+    } else {
+      dim3 grid((unsigned)((D + 63) / 64), (unsigned)chunks), block(32, 8);
+      colreduce_kernel<true><<<grid, block, 0, STREAM(stream)>>>(dy, dy_dtype, x, x_dtype, mean, rstd, ps, px, rows,
+                                                                (int)D, rpc);
+      VJ_LAUNCH_CHECK();
+      if (dbeta) colreduce_final_kernel<<<(unsigned)((D + 255) / 256), 256, 0, STREAM(stream)>>>(ps, dbeta, chunks, (int)D, 1);
+      if (dgamma) colreduce_final_kernel<<<(unsigned)((D + 255) / 256), 256, 0, STREAM(stream)>>>(px, dgamma, chunks, (int)D, 1);
+      VJ_LAUNCH_CHECK();
+    }
   }
   return 0;
 }
@@ -800,6 +939,13 @@ extern "C" int vj_colsum(const void* x, int x_dtype, float* out, int accumulate,
   const int chunks = col_chunks(rows);
   const long long rpc = (rows + chunks - 1) / chunks;
   float* ps = reinterpret_cast<float*>(scratch);
+  if (colw_ok(D)) {
+    dim3 grid((unsigned)((D + 255) / 256), (unsigned)chunks), block(32, 8);
+    colreduce_wide_kernel<false><<<grid, block, 0, STREAM(stream)>>>(x, x_dtype, nullptr, 0, nullptr, nullptr, ps, nullptr,
+                                                                    out, nullptr, rows, (int)D, rpc, accumulate);
+    VJ_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid((unsigned)((D + 63) / 64), (unsigned)chunks), block(32, 8);
   colreduce_kernel<false><<<grid, block, 0, STREAM(stream)>>>(x, x_dtype, nullptr, 0, nullptr, nullptr, ps, nullptr,
                                                              rows, (int)D, rpc);

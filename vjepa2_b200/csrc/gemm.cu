@@ -15,6 +15,7 @@
 // Tile: 128 (M) x BN (N) x 64 (K) per stage.  Operands may be K-major or MN-major (transposed storage), which
 // covers forward (x W^T), dgrad (dy W) and wgrad (dy^T x) without any transpose pass.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "host_common.h"
@@ -608,6 +609,412 @@ static int launch_gemm(const vj_gemm_args* g, int flags, cudaStream_t stream) {
   return 0;
 }
 
+// =====================================================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of a cluster (the two SMs of a TPC) compute one 256 x BN tile.  CTA r owns
+// output rows m0 + 128 r .. +127: it loads ITS 128 rows of A and HALF of the B tile (n_live / 2 rows); the leader CTA
+// (rank 0) issues tcgen05.mma.cta_group::2 with M = 256, which reads A and the two B halves from both CTAs' shared
+// memory and writes each CTA's 128 x BN accumulator half into that CTA's TMEM.  Per SM and k-block the tensor core
+// does the same work as in the 1-CTA kernel while shared memory holds / feeds 32 KB instead of 48 KB of operands, so
+// the ring is deeper and operand traffic (smem reads, L2 -> smem) per FLOP drops by a third.
+//   full[s]   (leader)      1 arrival (leader's expect_tx) + the TMA bytes of BOTH CTAs
+//   empty[s]  (each CTA)    tcgen05.commit multicast to both CTAs
+//   tfull[a]  (each CTA)    tcgen05.commit multicast to both CTAs
+//   tempty[a] (leader)      16 arrivals: the 8 epilogue warps of each CTA (the peer's arrive remotely)
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to an mbarrier in the leader CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at the same smem offset in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+template <bool AUX>
+struct Gemm2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;          // this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;         // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;          // 32 KB
+  static constexpr int STG_PER_WARP = (AUX ? 2 : 1) * GEMM_STG_BYTES;
+  static constexpr int STG_TOTAL = 8 * STG_PER_WARP;
+  static constexpr int STAGES_RAW = (227 * 1024 - STG_TOTAL - 2048) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int ACC_STRIDE = 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_STG + STG_TOTAL;
+  static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+};
+
+template <bool A_MN, bool B_MN, bool AUX>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, GemmEpi epi, int M,
+             int N, int K, int splits) {
+  using Cfg = Gemm2Cfg<AUX>;
+  constexpr int BN = Cfg::BN;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int num_m = (M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);      // 256-row blocks
+  const int num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  const int kb_per = (num_kb + splits - 1) / splits;
+  const int num_work = num_tiles * splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 16);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // the peer's barriers exist before anything targets them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int work = pair; work < num_work; work += num_pairs) {
+        const int split = work / num_tiles, tile = work - split * num_tiles;
+        int mb, nb;
+        tile_coords(tile, num_m, num_n, mb, nb);
+        const int m0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM, n0 = nb * BN;
+        const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        const int n_live = min(BN, ((N - n0) + 15) & ~15);
+        const int n_half = n_live >> 1;                 // B rows / columns each CTA supplies
+        const int nb0 = n0 + (int)rank * n_half;
+        const int b_boxes = B_MN ? (n_half + 63) / 64 : 0;
+        const uint32_t my_bytes = Cfg::A_BYTES + (B_MN ? b_boxes * 8192 : Cfg::B_BYTES);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          if (leader) mbar_expect_tx(&full[stage], 2 * my_bytes);
+          const uint32_t fb = mapa_shared(smem_u32(&full[stage]), 0);
+          if (!A_MN) {
+            tma_load_2d_pair(sa, &tmA, fb, kb * GEMM_BK, m0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < GEMM_BM / 64; ++c) tma_load_2d_pair(sa + c * 8192, &tmA, fb, m0 + c * 64, kb * GEMM_BK);
+          }
+          if (!B_MN) {
+            tma_load_2d_pair(sb, &tmB, fb, kb * GEMM_BK, nb0);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 2 / 64; ++c)
+              if (c < b_boxes) tma_load_2d_pair(sb + c * 8192, &tmB, fb, nb0 + c * 64, kb * GEMM_BK);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int work = pair; work < num_work; work += num_pairs, ++local) {
+        const int split = work / num_tiles;
+        const int kb0 = split * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+        int mb_, nb_;
+        tile_coords(work - split * num_tiles, num_m, num_n, mb_, nb_);
+        const int n_live = min(BN, ((N - nb_ * BN) + 15) & ~15);
+        const uint32_t idesc = make_idesc(2 * GEMM_BM, n_live, A_MN, B_MN);
+        const int as = local & 1;
+        const uint32_t aphase = (local >> 1) & 1;
+        mbar_wait(&tempty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+            const uint32_t sb = sa + Cfg::A_BYTES;
+            const uint64_t ad = A_MN ? desc_mnmajor<128>(sa, 8192) : desc_kmajor<128>(sa);
+            const uint64_t bd = B_MN ? desc_mnmajor<128>(sb, 8192) : desc_kmajor<128>(sb);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              const uint64_t adk = desc_advance(ad, A_MN ? k * 2048 : k * 32);
+              const uint64_t bdk = desc_advance(bd, B_MN ? k * 2048 : k * 32);
+              umma_bf16_pair(d_tmem, adk, bdk, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            }
+            umma_commit_pair(&empty[stage]);
+            if (kb == kb1 - 1) umma_commit_pair(&tfull[as]);
+          }
+          __syncwarp();
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------ epilogue (both CTAs, each on its own 128 rows)
+    const int q = warp & 3;
+    const int ew = warp - 4;
+    const int eg = ew >> 2;
+    const bool out_f32 = (epi.flags & VJ_EPI_OUT_F32) != 0;
+    constexpr bool want_aux = AUX;
+    const bool reduce = (epi.flags & EPI_INTERNAL_REDUCE) != 0;
+    const int gw = out_f32 ? 32 : 64;
+    const int ngroups = BN / gw;
+    uint8_t* stg_out = smem + Cfg::OFF_STG + ew * Cfg::STG_PER_WARP;
+    uint8_t* stg_aux = stg_out + GEMM_STG_BYTES;
+    const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty[0]), 0);
+    const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty[1]), 0);
+    int local = 0;
+    for (int work = pair; work < num_work; work += num_pairs, ++local) {
+      const int tile = work % num_tiles;
+      int mb, nb;
+      tile_coords(tile, num_m, num_n, mb, nb);
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      const int row0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM + q * 32;
+      const long long row = (long long)row0 + lane;
+      const bool row_ok = row < M;
+      const int n0 = nb * BN;
+      const int nlim = min(N, n0 + BN);
+      EpiSide side;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) side.v[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok && n0 + eg * gw < nlim) epilogue_prefetch(epi, side, row, n0 + eg * gw, nlim);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
+      if (row0 < M) {                                   // warp-uniform: a fully out-of-range 32-row slab stores nothing
+#pragma unroll 1
+        for (int g = eg; g < ngroups; g += 2) {
+          const int gcol = n0 + g * gw;
+          if (gcol >= N) break;
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          const int halves = out_f32 ? 1 : 2;
+#pragma unroll 1
+          for (int hh = 0; hh < halves; ++hh) {
+            const int col0 = gcol + hh * 32;
+            if (col0 >= nlim) break;
+            uint32_t acc[32];
+            tmem_ld32(taddr + g * gw + hh * 32, acc);
+            tmem_ld_wait();
+            const EpiSide cur = side;
+            {
+              int ncol = col0 + 32;
+              if (hh + 1 >= halves) ncol = gcol + 2 * gw;
+              if (row_ok && ncol < nlim) epilogue_prefetch(epi, side, row, ncol, nlim);
+            }
+            float v[32], pre[32];
+            if (want_aux) {
+              epilogue_math<true>(epi, acc, cur, col0, nlim, v, pre);
+              stage_bf16x32(stg_aux, lane, hh, pre);
+            } else {
+              epilogue_math<false>(epi, acc, cur, col0, nlim, v, pre);
+            }
+            if (out_f32) stage_f32x32(stg_out, lane, v);
+            else stage_bf16x32(stg_out, lane, hh, v);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (reduce) tma_reduce_add_2d(&tmOut, stg_out, gcol, row0);
+            else tma_store_2d(&tmOut, stg_out, gcol, row0);
+            if (want_aux) tma_store_2d(&tmAux, stg_aux, gcol, row0);
+            bulk_commit();
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(as ? tempty_leader1 : tempty_leader0);
+    }
+    if (lane == 0) bulk_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                  // both CTAs are done with both TMEM halves and all barriers
+  if (warp == 2)
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS)
+                 : "memory");
+}
+
+static int max_pairs_cached(const void* kern, int smem_bytes) {
+  // co-resident CTA pairs for this kernel (74 on a B200: one pair per TPC)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (unsigned)sm_count());
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = sm_count() / 2;
+  }
+  return n;
+}
+
+template <bool A_MN, bool B_MN, bool AUX>
+static int launch_gemm2(const vj_gemm_args* g, int flags, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<AUX>;
+  constexpr int BN = Cfg::BN;
+  CUtensorMap tmA, tmB, tmOut, tmAux;
+  {
+    const uint64_t dimsK[2] = {(uint64_t)g->K, (uint64_t)g->M};
+    const uint64_t dimsM[2] = {(uint64_t)g->M, (uint64_t)g->K};
+    const uint64_t str[1] = {(uint64_t)g->lda * 2};
+    const uint32_t boxK[2] = {64, GEMM_BM};
+    const uint32_t boxM[2] = {64, GEMM_BK};
+    int r = make_tmap(&tmA, g->a, VJ_BF16, 2, A_MN ? dimsM : dimsK, str, A_MN ? boxM : boxK, 128);
+    if (r) return r;
+  }
+  {
+    const uint64_t dimsK[2] = {(uint64_t)g->K, (uint64_t)g->N};
+    const uint64_t dimsN[2] = {(uint64_t)g->N, (uint64_t)g->K};
+    const uint64_t str[1] = {(uint64_t)g->ldb * 2};
+    const uint32_t boxK[2] = {64, (uint32_t)BN / 2};
+    const uint32_t boxN[2] = {64, GEMM_BK};
+    int r = make_tmap(&tmB, g->b, VJ_BF16, 2, B_MN ? dimsN : dimsK, str, B_MN ? boxN : boxK, 128);
+    if (r) return r;
+  }
+  {
+    const bool f32 = (flags & VJ_EPI_OUT_F32) != 0;
+    const uint64_t dims[2] = {(uint64_t)g->N, (uint64_t)g->M};
+    const uint64_t str[1] = {(uint64_t)g->ldo * (f32 ? 4 : 2)};
+    const uint32_t box[2] = {f32 ? 32u : 64u, 32u};
+    int r = make_tmap(&tmOut, g->out, f32 ? VJ_F32 : VJ_BF16, 2, dims, str, box, 128);
+    if (r) return r;
+    tmAux = tmOut;
+    if (flags & VJ_EPI_AUX_OUT) {
+      const uint64_t stra[1] = {(uint64_t)g->ld_aux * 2};
+      const uint32_t boxa[2] = {64u, 32u};
+      r = make_tmap(&tmAux, g->aux_out, VJ_BF16, 2, dims, stra, boxa, 128);
+      if (r) return r;
+    }
+  }
+  GemmEpi e;
+  e.bias = g->bias; e.residual = g->residual; e.aux_in = g->aux_in;
+  e.ldr = g->ldr; e.ld_aux = g->ld_aux; e.flags = flags;
+  e.rope = reinterpret_cast<const __half*>(g->rope_table); e.rope_hd = g->rope_hd; e.rope_D = g->rope_D;
+
+  auto kern = gemm2_kernel<A_MN, B_MN, AUX>;
+  static int pairs = 0;
+  if (pairs == 0) {
+    VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    pairs = max_pairs_cached(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
+  }
+  const int num_m = (int)((g->M + 2 * GEMM_BM - 1) / (2 * GEMM_BM));
+  const int num_n = (int)((g->N + BN - 1) / BN);
+  const int tiles = num_m * num_n;
+  const int num_kb = (int)((g->K + GEMM_BK - 1) / GEMM_BK);
+  int splits = 1;
+  if ((flags & EPI_INTERNAL_REDUCE) && !(flags & VJ_EPI_BIAS)) {
+    double best = 0.0;
+    for (int sp = 1; sp <= 32; ++sp) {
+      const int kb_per = (num_kb + sp - 1) / sp;
+      if (sp > 1 && kb_per < 8) break;
+      const int sp_eff = (num_kb + kb_per - 1) / kb_per;
+      const long long items = (long long)tiles * sp_eff;
+      const long long waves = (items + pairs - 1) / pairs;
+      const double score = (double)items / (double)(waves * pairs) * kb_per / (kb_per + 6.0);
+      if (score > best * 1.02) { best = score; splits = sp_eff; }
+    }
+  }
+  const long long work = (long long)tiles * splits;
+  const int npairs = work < pairs ? (int)work : pairs;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (unsigned)npairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  VJ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmAux, e, (int)g->M, (int)g->N, (int)g->K, splits));
+  return 0;
+}
+
+// CTA-pair kernel: on by default for problems with enough 256-row blocks; VJ_GEMM_2CTA=0 forces the 1-CTA kernels
+static bool use_pair_kernel(long long M, long long N) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* s = getenv("VJ_GEMM_2CTA");
+    mode = (s && s[0] >= '0' && s[0] <= '2') ? s[0] - '0' : 1;      // 0 off, 1 auto, 2 every shape (tests)
+  }
+  return mode == 2 || (mode == 1 && M >= 1024 && N >= 128);
+}
+
 // Pick the N tile.  Measured on B200 (profiles/r01_*): per-FLOP speed of the mainloop is ~1.0 at BN=256,
 // ~0.86 at 192 and ~0.7 at 128 (smaller tiles re-read A more often and give the single MMA-issuing thread
 // less time per k-block), so a wide tile wins unless it leaves many dead columns or a ragged last wave.
@@ -664,6 +1071,15 @@ extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
   }
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
   VJ_CHECK(!(amn && !bmn), "vj_gemm: (A MN-major, B K-major) is not instantiated");
+  if (use_pair_kernel(g->M, g->N)) {
+    if (flags & VJ_EPI_AUX_OUT) {
+      VJ_CHECK(!amn && !bmn, "vj_gemm: AUX_OUT is only instantiated for K-major operands");
+      return launch_gemm2<false, false, true>(g, flags, stream);
+    }
+    if (!amn && !bmn) return launch_gemm2<false, false, false>(g, flags, stream);
+    if (!amn && bmn) return launch_gemm2<false, true, false>(g, flags, stream);
+    return launch_gemm2<true, true, false>(g, flags, stream);
+  }
   const int bn = pick_bn(g->N, g->M);
   if (flags & VJ_EPI_AUX_OUT) {
     VJ_CHECK(!amn && !bmn, "vj_gemm: AUX_OUT is only instantiated for K-major operands");
