@@ -4,6 +4,8 @@
 // [B*S][3D] with a 3-D tensor map (d, S, B) -- no head-major relayout pass.  Roles: see attn_fwd_kernel.
 #include "common.cuh"
 #include "host_common.h"
+#include <stdlib.h>
+
 #include "attn_common.cuh"
 #include "../../include/vjepa2_b200.h"
 
@@ -362,7 +364,30 @@ struct AttnFwd2Cfg {
   static_assert(O_COL + 2 * HD <= TMEM_COLS, "TMEM budget");
 };
 
-template <int HD>
+// exp2 of a packed pair on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max rel. error 7.5e-5 --
+// 50x below the bf16 rounding P gets anyway): x = n + f, n = round(x), f in [-0.5, 0.5]; 2^x = p(f) * 2^n with the
+// exponent added straight into the float bits.  x is clamped at -126 (covers the -inf of masked keys: 2^-126 ~ 0).
+__device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& p0, float& p1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const uint64_t x = f32x2_pack(x0, x1);
+  const uint64_t magic = f32x2_pack(12582912.0f, 12582912.0f);          // 1.5 * 2^23: rounds to integer
+  const uint64_t nmagic = f32x2_pack(-12582912.0f, -12582912.0f);
+  const uint64_t fx = f32x2_add(x, magic);                               // low mantissa bits = n (two's complement)
+  const uint64_t xr = f32x2_add(fx, nmagic);                             // n as float
+  const uint64_t f = f32x2_fma(xr, f32x2_pack(-1.0f, -1.0f), x);         // x - n
+  uint64_t p = f32x2_fma(f, f32x2_pack(0.0551716685f, 0.0551716685f), f32x2_pack(0.2426111251f, 0.2426111251f));
+  p = f32x2_fma(p, f, f32x2_pack(0.6932609677f, 0.6932609677f));
+  p = f32x2_fma(p, f, f32x2_pack(0.9999280572f, 0.9999280572f));
+  float q0, q1, n0, n1;
+  f32x2_unpack(p, q0, q1);
+  f32x2_unpack(fx, n0, n1);
+  p0 = __uint_as_float(__float_as_uint(q0) + (__float_as_uint(n0) << 23));
+  p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(n1) << 23));
+}
+
+// POLY8: how many of every 8 probability pairs (16 keys) take the polynomial instead of MUFU.EX2 (0, 2, 3 or 4)
+template <int HD, int POLY8>
 __global__ void __launch_bounds__(384, 2)
 attn_fwd2_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ TMapPair tmKV,
                  bf16* __restrict__ out, float* __restrict__ lse, int S, int H, int D, float scale_log2, int n_qt,
@@ -635,7 +660,17 @@ attn_fwd2_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ T
                 f32x2_fma(f32x2_pack(__uint_as_float(src[2 * k]), __uint_as_float(src[2 * k + 1])), sc2, nm2);
             float x0, x1;
             f32x2_unpack(x, x0, x1);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            float p0, p1;
+            // pairs of a 16-key group (two chunks) that go to the FMA pipe: chosen at compile time, spread over the group
+            const bool kPoly = (POLY8 >= 4) ? (k & 1) == 1
+                                 : (POLY8 == 3) ? ((ch & 1) ? (k & 1) == 1 : k == 3)
+                                 : (POLY8 == 2) ? k == 3 : false;
+            if (kPoly) {
+              exp2_poly_pair(x0, x1, p0, p1);
+            } else {
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
+            }
             rsum[k] = f32x2_add(rsum[k], f32x2_pack(p0, p1));
             pk[k] = pack_bf16x2(p0, p1);
           }
@@ -784,7 +819,7 @@ attn_fwd2_kernel(const __grid_constant__ TMapPair tmQ, const __grid_constant__ T
   if (warp == 8) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int HD>
+template <int HD, int POLY8>
 static int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int S, int H, cudaStream_t stream) {
   using Cfg = AttnFwd2Cfg<HD>;
   const int D = H * HD;
@@ -793,7 +828,7 @@ static int launch_attn_fwd2(const void* qkv, void* out, float* lse, int B, int S
   if (r) return r;
   r = make_head_tmaps<HD>(&tmKV, qkv, (uint64_t)3 * D, (uint64_t)S, (uint64_t)B, Cfg::BN);
   if (r) return r;
-  auto kern = attn_fwd2_kernel<HD>;
+  auto kern = attn_fwd2_kernel<HD, POLY8>;
   static bool attr_set = false;
   if (!attr_set) {
     VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -840,8 +875,22 @@ extern "C" int vj_attn_fwd(const void* qkv, void* out, float* lse, int B, int S,
   VJ_CHECK(B > 0 && S > 0 && H > 0, "vj_attn_fwd: bad shape B=%d S=%d H=%d", B, S, H);
   VJ_CHECK(B <= 65535 && H <= 65535, "vj_attn_fwd: B/H exceed grid limits");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (head_dim == 64) return launch_attn_fwd2<64>(qkv, out, lse, B, S, H, st);
-  if (head_dim == 32) return launch_attn_fwd2<32>(qkv, out, lse, B, S, H, st);
+  // share of the softmax exponentials evaluated on the FMA pipe instead of MUFU (VJ_ATTN_POLY = 0, 2, 3, 4 of 8)
+  static int poly = -1;
+  if (poly < 0) {
+    const char* e = getenv("VJ_ATTN_POLY");
+    poly = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 3;
+  }
+#define VJ_FWD2(HD_)                                                                           \
+  if (head_dim == HD_) {                                                                       \
+    if (poly == 0) return launch_attn_fwd2<HD_, 0>(qkv, out, lse, B, S, H, st);               \
+    if (poly <= 2) return launch_attn_fwd2<HD_, 2>(qkv, out, lse, B, S, H, st);               \
+    if (poly == 3) return launch_attn_fwd2<HD_, 3>(qkv, out, lse, B, S, H, st);               \
+    return launch_attn_fwd2<HD_, 4>(qkv, out, lse, B, S, H, st);                              \
+  }
+  VJ_FWD2(64)
+  VJ_FWD2(32)
+#undef VJ_FWD2
   if (head_dim == 80) return launch_attn_fwd<80>(qkv, out, lse, B, S, H, st);
   set_error("vj_attn_fwd: head_dim %d not supported (32, 64, 80)", head_dim);
   return -1;

@@ -164,29 +164,35 @@ __device__ __forceinline__ float mufu_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// erfc(|z|) via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 6 FMA-pipe ops.
-// Also returns e = exp(-z*z) (the Gaussian factor gelu' needs).
-__device__ __forceinline__ float erfc_abs(float z, float& e) {
-  const float az = fabsf(z);
-  const float t = mufu_rcp(fmaf(0.3275911f, az, 1.0f));
-  e = mufu_ex2(az * az * -1.4426950408889634f);
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  return p * t * e;
+// Exact-erf GELU without the erf: h(u) = erfc(u / sqrt2) / 2 = 2^(-q(u)) with q a degree-5 polynomial in u = |x|
+// (fit of -log2(erfc) on [0, 6 sqrt2], abs. error of h <= 3e-7, of gelu <= 1.2e-6, of gelu' <= 5e-7 -- three orders
+// below the bf16 rounding of the result).  Phi(x) = 1 - h for x >= 0, h for x < 0 (no cancellation in the tail).
+// Two elements at a time on packed fp32 (FFMA2): 5 packed FMAs + one MUFU.EX2 per element, no reciprocal.
+__device__ __forceinline__ uint64_t gelu_neg_q_pair(float ua, float ub) {
+  const uint64_t u = f32x2_pack(ua, ub);
+  uint64_t r = f32x2_fma(u, f32x2_pack(-0.00052044867f, -0.00052044867f), f32x2_pack(0.0073974645f, 0.0073974645f));
+  r = f32x2_fma(r, u, f32x2_pack(-0.052561168f, -0.052561168f));
+  r = f32x2_fma(r, u, f32x2_pack(-0.45925471f, -0.45925471f));
+  r = f32x2_fma(r, u, f32x2_pack(-1.1510913f, -1.1510913f));
+  return f32x2_fma(r, u, f32x2_pack(-1.0f, -1.0f));     // -(1 + u R(u)): the "/ 2" is the leading -1
 }
-// gelu(x) = x * Phi(x), Phi(x) = 1 - erfc(x/sqrt2)/2 for x >= 0, erfc(|x|/sqrt2)/2 for x < 0 (no cancellation)
-__device__ __forceinline__ float gelu_fast(float x) {
-  float e;
-  const float h = 0.5f * erfc_abs(x * 0.70710678118654752f, e);
-  return x * (x >= 0.f ? 1.0f - h : h);
+__device__ __forceinline__ void gelu_pair(float& a, float& b) {
+  float r0, r1;
+  f32x2_unpack(gelu_neg_q_pair(fabsf(a), fabsf(b)), r0, r1);
+  const float t0 = a * mufu_ex2(r0), t1 = b * mufu_ex2(r1);    // x * h
+  a = a >= 0.f ? a - t0 : t0;
+  b = b >= 0.f ? b - t1 : t1;
 }
-__device__ __forceinline__ float dgelu_fast(float x) {
-  float e;
-  const float h = 0.5f * erfc_abs(x * 0.70710678118654752f, e);
-  const float cdf = x >= 0.f ? 1.0f - h : h;
-  return fmaf(x * 0.39894228040143268f, e, cdf);
+// gelu'(x) = Phi(x) + x * pdf(x)
+__device__ __forceinline__ void dgelu_pair(float a, float b, float& da, float& db) {
+  float r0, r1, e0, e1;
+  f32x2_unpack(gelu_neg_q_pair(fabsf(a), fabsf(b)), r0, r1);
+  const uint64_t x = f32x2_pack(a, b);
+  f32x2_unpack(f32x2_mul(f32x2_mul(x, x), f32x2_pack(-0.72134752f, -0.72134752f)), e0, e1);   // -x^2/2 * log2(e)
+  const float h0 = mufu_ex2(r0), h1 = mufu_ex2(r1);
+  const float c0 = a >= 0.f ? 1.0f - h0 : h0, c1 = b >= 0.f ? 1.0f - h1 : h1;
+  da = fmaf(a * 0.39894228040143268f, mufu_ex2(e0), c0);
+  db = fmaf(b * 0.39894228040143268f, mufu_ex2(e1), c1);
 }
 
 // 32 consecutive columns of one output row: accumulator -> final values (v) and optional pre-activation (pre)
@@ -228,16 +234,20 @@ __device__ __forceinline__ void epilogue_math(const GemmEpi& e, const uint32_t (
   }
   if (flags & VJ_EPI_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+    for (int i = 0; i < 32; i += 2) gelu_pair(v[i], v[i + 1]);
   }
   if (flags & VJ_EPI_DGELU) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint4 u = s.v[4 + i];
-      v[i * 8] *= dgelu_fast(bf16_lo(u.x)); v[i * 8 + 1] *= dgelu_fast(bf16_hi(u.x));
-      v[i * 8 + 2] *= dgelu_fast(bf16_lo(u.y)); v[i * 8 + 3] *= dgelu_fast(bf16_hi(u.y));
-      v[i * 8 + 4] *= dgelu_fast(bf16_lo(u.z)); v[i * 8 + 5] *= dgelu_fast(bf16_hi(u.z));
-      v[i * 8 + 6] *= dgelu_fast(bf16_lo(u.w)); v[i * 8 + 7] *= dgelu_fast(bf16_hi(u.w));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float d0, d1;
+        dgelu_pair(bf16_lo(w[j]), bf16_hi(w[j]), d0, d1);
+        v[i * 8 + 2 * j] *= d0;
+        v[i * 8 + 2 * j + 1] *= d1;
+      }
     }
   }
   if (flags & VJ_EPI_RESIDUAL) {

@@ -335,6 +335,7 @@ static void bench_gemm(const char* name, long long M, long long N, long long K, 
   const bool accumulate = (flags & VJ_EPI_RESIDUAL) && of32 && (flags & VJ_EPI_RES_F32);
   g.a_mn_major = a_mn; g.b_mn_major = b_mn; g.flags = flags; g.bias = bias; g.residual = accumulate ? out : side; g.ldr = N;
   g.aux_out = side; g.aux_in = side; g.ld_aux = N;
+  if (flags & VJ_EPI_ROPE) { g.rope_table = side; g.rope_hd = 64; g.rope_D = (int)(N / 3); }   // zero table: timing only
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int i = 0; i < 3; ++i) VJ(vj_gemm(&g, 0));
@@ -503,6 +504,21 @@ int main(int argc, char** argv) {
     bench_gemm("pred proj wgrad", 384, 384, 36000, 1, 1, VJ_EPI_OUT_F32 | VJ_EPI_RES_F32 | VJ_EPI_RESIDUAL);
     bench_gemm("8192^3", 8192, 8192, 8192, 0, 0, 0);
     bench_attn(24, 2048, 22, 64, false);
+  }
+  if (!strcmp(what, "benchepi")) {   // what each fused epilogue costs on top of the bare GEMM
+    const int RB = VJ_EPI_ROUND_BF16;
+    bench_gemm("qkv  none", 49152, 4224, 1408, 0, 0, 0);
+    bench_gemm("qkv  bias", 49152, 4224, 1408, 0, 0, VJ_EPI_BIAS);
+    bench_gemm("qkv  bias+rope", 49152, 4224, 1408, 0, 0, VJ_EPI_BIAS | VJ_EPI_ROPE);
+    bench_gemm("fc1  bias", 49152, 6144, 1408, 0, 0, VJ_EPI_BIAS);
+    bench_gemm("fc1  bias+gelu", 49152, 6144, 1408, 0, 0, VJ_EPI_BIAS | VJ_EPI_GELU | RB);
+    bench_gemm("fc1  bias+gelu+aux", 49152, 6144, 1408, 0, 0, VJ_EPI_BIAS | VJ_EPI_GELU | RB | VJ_EPI_AUX_OUT);
+    bench_gemm("proj bias", 49152, 1408, 1408, 0, 0, VJ_EPI_BIAS);
+    bench_gemm("proj bias+res", 49152, 1408, 1408, 0, 0, VJ_EPI_BIAS | VJ_EPI_RESIDUAL | RB);
+    bench_gemm("fc2  bias", 49152, 1408, 6144, 0, 0, VJ_EPI_BIAS);
+    bench_gemm("fc2  bias+res", 49152, 1408, 6144, 0, 0, VJ_EPI_BIAS | VJ_EPI_RESIDUAL | RB);
+    bench_gemm("dgelu none", 16384, 6144, 1408, 0, 1, 0);
+    bench_gemm("dgelu", 16384, 6144, 1408, 0, 1, VJ_EPI_DGELU);
   }
   if (!strcmp(what, "stressattn")) {   // back-to-back launches (CTAs of consecutive launches overlap on the SMs)
     const int reps = argc > 2 ? atoi(argv[2]) : 20;
