@@ -393,13 +393,14 @@ def main():
         achieved = d_fl / (d_ms / 1e3) / 1e12
         traffic, traffic_src = None, None
         try:        # dram__bytes_read.sum + dram__bytes_write.sum of ONE such launch, from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_ncu_traffic.json")))["fc1gelu"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_ncu_traffic.json")))["fc1gelu_pair"]
             if (Md, Nd, Kd) == (49152, 6144, 1408):
-                traffic, traffic_src = tj["dram_bytes"], "profiles/r01b_ncu_full_summary.txt (ncu --set full, same shape and epilogue)"
+                traffic, traffic_src = tj["dram_bytes"], "profiles/r01c_ncu_gemm2_gelu_summary.txt (ncu --set full, same kernel, shape and epilogue)"
         except Exception:
             pass
         roof = dict(bound="tensor",
-                    kernel=f"vj::gemm_kernel<256,0,0,0> (tcgen05 GEMM): fc1 forward +bias +GELU of the target encoder, "
+                    kernel=f"vj::gemm2_kernel<0,0,0> (tcgen05 cta_group::2 GEMM, 256x256 tile per CTA pair): fc1 forward +bias +GELU of "
+                           f"the target encoder, "
                            f"M={Md} N={Nd} K={Kd}",
                     achieved=achieved, peak=peaks["sustained"], unit="TFLOP/s", frac=achieved / peaks["sustained"],
                     peak_source=f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)",

@@ -33,7 +33,7 @@ constexpr int EPI_INTERNAL_REDUCE = 1 << 20;  // out += acc through TMA reduce-a
 //  [0] MMA warp total  [1] MMA wait full (TMA late)  [2] MMA wait tempty (epilogue late)
 //  [3] producer wait empty  [4] epilogue wait tfull  [5] epilogue busy  [6] CTAs  [7] epilogue tmem ld+wait
 #ifdef VJ_GEMM_PROFILE
-__device__ unsigned long long g_gemm_prof[8];
+__device__ unsigned long long g_gemm_prof[12];   // [8] wait_read stall [9] math+stage [10] fence+issue
 #define VJ_PROF_T0(v) const long long v = clock64()
 #define VJ_PROF_ADD(acc, v) acc += clock64() - v
 #else
@@ -166,33 +166,26 @@ __device__ __forceinline__ float mufu_ex2(float x) {
 }
 // Exact-erf GELU without the erf: h(u) = erfc(u / sqrt2) / 2 = 2^(-q(u)) with q a degree-5 polynomial in u = |x|
 // (fit of -log2(erfc) on [0, 6 sqrt2], abs. error of h <= 3e-7, of gelu <= 1.2e-6, of gelu' <= 5e-7 -- three orders
-// below the bf16 rounding of the result).  Phi(x) = 1 - h for x >= 0, h for x < 0 (no cancellation in the tail).
-// Two elements at a time on packed fp32 (FFMA2): 5 packed FMAs + one MUFU.EX2 per element, no reciprocal.
-__device__ __forceinline__ uint64_t gelu_neg_q_pair(float ua, float ub) {
-  const uint64_t u = f32x2_pack(ua, ub);
-  uint64_t r = f32x2_fma(u, f32x2_pack(-0.00052044867f, -0.00052044867f), f32x2_pack(0.0073974645f, 0.0073974645f));
-  r = f32x2_fma(r, u, f32x2_pack(-0.052561168f, -0.052561168f));
-  r = f32x2_fma(r, u, f32x2_pack(-0.45925471f, -0.45925471f));
-  r = f32x2_fma(r, u, f32x2_pack(-1.1510913f, -1.1510913f));
-  return f32x2_fma(r, u, f32x2_pack(-1.0f, -1.0f));     // -(1 + u R(u)): the "/ 2" is the leading -1
+// below the bf16 rounding of the result).  Phi(x) = 1 - h for x >= 0, h for x < 0 (no cancellation in the tail), so
+// gelu(x) = max(x, 0) - |x| h.  Scalar FFMAs with immediate coefficients: 5 FFMA + 1 MUFU.EX2 + FMNMX + FFMA per
+// element (the packed-fp32 form spent more on building register pairs than it saved; ncu opcode mix, profiles/).
+__device__ __forceinline__ float gelu_neg_q(float u) {
+  float r = fmaf(u, -0.00052044867f, 0.0073974645f);
+  r = fmaf(r, u, -0.052561168f);
+  r = fmaf(r, u, -0.45925471f);
+  r = fmaf(r, u, -1.1510913f);
+  return fmaf(r, u, -1.0f);                              // -(1 + u R(u)): the "/ 2" is the leading -1
 }
-__device__ __forceinline__ void gelu_pair(float& a, float& b) {
-  float r0, r1;
-  f32x2_unpack(gelu_neg_q_pair(fabsf(a), fabsf(b)), r0, r1);
-  const float t0 = a * mufu_ex2(r0), t1 = b * mufu_ex2(r1);    // x * h
-  a = a >= 0.f ? a - t0 : t0;
-  b = b >= 0.f ? b - t1 : t1;
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float u = fabsf(x);
+  return fmaf(-u, mufu_ex2(gelu_neg_q(u)), fmaxf(x, 0.f));
 }
 // gelu'(x) = Phi(x) + x * pdf(x)
-__device__ __forceinline__ void dgelu_pair(float a, float b, float& da, float& db) {
-  float r0, r1, e0, e1;
-  f32x2_unpack(gelu_neg_q_pair(fabsf(a), fabsf(b)), r0, r1);
-  const uint64_t x = f32x2_pack(a, b);
-  f32x2_unpack(f32x2_mul(f32x2_mul(x, x), f32x2_pack(-0.72134752f, -0.72134752f)), e0, e1);   // -x^2/2 * log2(e)
-  const float h0 = mufu_ex2(r0), h1 = mufu_ex2(r1);
-  const float c0 = a >= 0.f ? 1.0f - h0 : h0, c1 = b >= 0.f ? 1.0f - h1 : h1;
-  da = fmaf(a * 0.39894228040143268f, mufu_ex2(e0), c0);
-  db = fmaf(b * 0.39894228040143268f, mufu_ex2(e1), c1);
+__device__ __forceinline__ float dgelu_fast(float x) {
+  const float u = fabsf(x);
+  const float h = mufu_ex2(gelu_neg_q(u));
+  const float cdf = 0.5f + copysignf(0.5f - h, x);
+  return fmaf(x * 0.39894228040143268f, mufu_ex2(x * x * -0.72134752f), cdf);
 }
 
 // 32 consecutive columns of one output row: accumulator -> final values (v) and optional pre-activation (pre)
@@ -203,11 +196,19 @@ __device__ __forceinline__ void epilogue_math(const GemmEpi& e, const uint32_t (
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
   const int flags = e.flags;
   if (flags & VJ_EPI_BIAS) {
+    if (col0 + 32 <= N) {                               // full block (all but a ragged last one): no per-load checks
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      if (col0 + i < N) {
+      for (int i = 0; i < 32; i += 4) {
         const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + i));
         v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        if (col0 + i < N) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + i));
+          v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+        }
       }
     }
   }
@@ -234,20 +235,16 @@ __device__ __forceinline__ void epilogue_math(const GemmEpi& e, const uint32_t (
   }
   if (flags & VJ_EPI_GELU) {
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) gelu_pair(v[i], v[i + 1]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
   }
   if (flags & VJ_EPI_DGELU) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const uint4 u = s.v[4 + i];
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float d0, d1;
-        dgelu_pair(bf16_lo(w[j]), bf16_hi(w[j]), d0, d1);
-        v[i * 8 + 2 * j] *= d0;
-        v[i * 8 + 2 * j + 1] *= d1;
-      }
+      v[i * 8] *= dgelu_fast(bf16_lo(u.x)); v[i * 8 + 1] *= dgelu_fast(bf16_hi(u.x));
+      v[i * 8 + 2] *= dgelu_fast(bf16_lo(u.y)); v[i * 8 + 3] *= dgelu_fast(bf16_hi(u.y));
+      v[i * 8 + 4] *= dgelu_fast(bf16_lo(u.z)); v[i * 8 + 5] *= dgelu_fast(bf16_hi(u.z));
+      v[i * 8 + 6] *= dgelu_fast(bf16_lo(u.w)); v[i * 8 + 7] *= dgelu_fast(bf16_hi(u.w));
     }
   }
   if (flags & VJ_EPI_RESIDUAL) {
@@ -451,8 +448,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* stg_out = smem + Cfg::OFF_STG + ew * Cfg::STG_PER_WARP;
     uint8_t* stg_aux = stg_out + GEMM_STG_BYTES;
     int local = 0;
-    long long prof_w = 0, prof_b = 0, prof_ld = 0;
-    (void)prof_w; (void)prof_b; (void)prof_ld;
+    long long prof_w = 0, prof_b = 0, prof_ld = 0, prof_wr = 0, prof_ms = 0, prof_fi = 0;
+    (void)prof_w; (void)prof_b; (void)prof_ld; (void)prof_wr; (void)prof_ms; (void)prof_fi;
     for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++local) {
       const int tile = work % num_tiles;
       int mb, nb;
@@ -479,8 +476,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int gcol = n0 + g * gw;
         if (gcol >= N) break;                       // warp-uniform
         // the previous TMA store of this warp must have finished READING the staging buffers
+        VJ_PROF_T0(t6);
         if (lane == 0) bulk_wait_read0();
         __syncwarp();
+        VJ_PROF_ADD(prof_wr, t6);
         const int halves = out_f32 ? 1 : 2;
 #pragma unroll 1
         for (int hh = 0; hh < halves; ++hh) {
@@ -491,6 +490,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           tmem_ld32(taddr + g * gw + hh * 32, acc);
           tmem_ld_wait();
           VJ_PROF_ADD(prof_ld, t5);
+          VJ_PROF_T0(t7);
           const EpiSide cur = side;
           // prefetch the side inputs of the next 32-column block this warp will process
           {
@@ -507,7 +507,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (out_f32) stage_f32x32(stg_out, lane, v);
           else stage_bf16x32(stg_out, lane, hh, v);
+          VJ_PROF_ADD(prof_ms, t7);
         }
+        VJ_PROF_T0(t8);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -516,6 +518,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (want_aux) tma_store_2d(&tmAux, stg_aux, gcol, row0);
           bulk_commit();
         }
+        VJ_PROF_ADD(prof_fi, t8);
       }
       tc_fence_before();
       __syncwarp();
@@ -528,6 +531,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       atomicAdd(&g_gemm_prof[4], (unsigned long long)prof_w);
       atomicAdd(&g_gemm_prof[5], (unsigned long long)prof_b);
       atomicAdd(&g_gemm_prof[7], (unsigned long long)prof_ld);
+      atomicAdd(&g_gemm_prof[8], (unsigned long long)prof_wr);
+      atomicAdd(&g_gemm_prof[9], (unsigned long long)prof_ms);
+      atomicAdd(&g_gemm_prof[10], (unsigned long long)prof_fi);
     }
 #endif
   }
@@ -1116,9 +1122,9 @@ extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
 #ifdef VJ_GEMM_PROFILE
 extern "C" int vj_gemm_prof_read(unsigned long long* out8, int reset) {
   cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(out8, vj::g_gemm_prof, 8 * sizeof(unsigned long long));
+  cudaMemcpyFromSymbol(out8, vj::g_gemm_prof, 12 * sizeof(unsigned long long));
   if (reset) {
-    unsigned long long z[8] = {0};
+    unsigned long long z[12] = {0};
     cudaMemcpyToSymbol(vj::g_gemm_prof, z, sizeof(z));
   }
   return 0;

@@ -342,7 +342,7 @@ static void bench_gemm(const char* name, long long M, long long N, long long K, 
   CK(cudaDeviceSynchronize());
   const int iters = 10;
 #ifdef VJ_GEMM_PROFILE
-  unsigned long long pr[8];
+  unsigned long long pr[12];
   vj_gemm_prof_read(pr, 1);
 #endif
   cudaEventRecord(e0);
@@ -360,6 +360,7 @@ static void bench_gemm(const char* name, long long M, long long N, long long K, 
   printf("      per-CTA cycles: mma_total %.0f | mma wait TMA %.1f%% | mma wait epilogue %.1f%% | producer wait slot %.1f%%"
          " | epilogue wait acc %.0f busy %.0f (tmem ld+wait %.0f)\n",
          pr[0] / n, 100.0 * pr[1] / pr[0], 100.0 * pr[2] / pr[0], 100.0 * pr[3] / pr[0], pr[4] / n, pr[5] / n, pr[7] / n);
+  printf("      epilogue warp 4: store-read wait %.0f | math+stage %.0f | fence+TMA issue %.0f\n", pr[8] / n, pr[9] / n, pr[10] / n);
 #endif
   cudaFree(A); cudaFree(B); cudaFree(out); cudaFree(bias); cudaFree(side);
 }
