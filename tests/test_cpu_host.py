@@ -291,3 +291,23 @@ def test_hub_constructors_build_reference_shapes():
     enc2, pred2 = I.vjepa2_vit_large(pretrained=True, checkpoint=ck, num_frames=16)
     assert torch.equal(enc2.blocks[3].mlp.fc1.weight, enc.blocks[3].mlp.fc1.weight)
     assert torch.equal(pred2.predictor_proj.weight, pred.predictor_proj.weight)
+
+
+def test_mask_passes_respect_the_activation_budget():
+    """JepaTrainStep runs all masks of a group in one pass unless their saved activations exceed the budget
+    (64f x 384px geometry); then it goes pass by pass, never splitting a mask and keeping the order."""
+    from types import SimpleNamespace
+    from vjepa2_b200.train import JepaTrainStep
+    enc, pred = _tiny_models()
+    B = 4
+    mes = [torch.zeros(B, 100, dtype=torch.int64), torch.zeros(B, 30, dtype=torch.int64), torch.zeros(B, 60, dtype=torch.int64)]
+    mps = [torch.zeros(B, 50, dtype=torch.int64), torch.zeros(B, 120, dtype=torch.int64), torch.zeros(B, 90, dtype=torch.int64)]
+    ns = SimpleNamespace(encoder=enc.backbone, predictor=pred.backbone, ACT_BUDGET_BYTES=JepaTrainStep.ACT_BUDGET_BYTES)
+    assert JepaTrainStep._mask_passes(ns, mes, mps) == [(0, 3)]
+    per_enc = 2 * (16 * 64 + 4 * 256)
+    per_pred = 1 * (20 * 64 + 4 * 256)
+    need = [int(1.1 * (me.numel() * per_enc + (me.numel() + mp.numel()) * per_pred)) for me, mp in zip(mes, mps)]
+    ns.ACT_BUDGET_BYTES = need[0] + need[1]              # first two fit together, the third starts a new pass
+    assert JepaTrainStep._mask_passes(ns, mes, mps) == [(0, 2), (2, 3)]
+    ns.ACT_BUDGET_BYTES = 1                               # nothing fits: one mask per pass, never an empty pass
+    assert JepaTrainStep._mask_passes(ns, mes, mps) == [(0, 1), (1, 2), (2, 3)]

@@ -222,6 +222,25 @@ class JepaTrainStep:
             next(self.momentum)
             self.last_lr_wd = (lr, wd)
 
+    ACT_BUDGET_BYTES = 70 << 30          # saved activations of one forward/backward pass (of 180 GB HBM)
+
+    def _mask_passes(self, mes, mps):
+        """Greedy split of a group's masks into passes whose saved activations fit ACT_BUDGET_BYTES: per token and
+        block the engine keeps ~(16 D + 4 Hm) bytes (LN outputs, qkv, attention out, fc1 pre/post, residual stream)."""
+        e, p = self.encoder, self.predictor
+        per_tok_enc = len(e.blocks) * (16 * e.embed_dim + 4 * e.blocks[0].mlp.fc1.out_features)
+        pd = p.predictor_embed.out_features
+        per_tok_pred = len(p.predictor_blocks) * (20 * pd + 4 * p.predictor_blocks[0].mlp.fc1.out_features)
+        passes, lo, acc = [], 0, 0
+        for j, (me, mp) in enumerate(zip(mes, mps)):
+            need = int(1.1 * (me.numel() * per_tok_enc + (me.numel() + mp.numel()) * per_tok_pred))
+            if j > lo and acc + need > self.ACT_BUDGET_BYTES:
+                passes.append((lo, j))
+                lo, acc = j, 0
+            acc += need
+        passes.append((lo, len(mes)))
+        return passes
+
     def step(self, clips, masks_enc, masks_pred):
         """clips: list (one fp32 [B,3,T,H,W] tensor per fpc group); masks_enc / masks_pred: list over
         groups of lists over masks of int64 [B, K].  Returns (loss [1] fp32 device tensor, lr, wd)."""
@@ -252,39 +271,42 @@ class JepaTrainStep:
             Bq, N, D = h.shape
             h2 = h.view(Bq * N, D)
             ops.layernorm_fwd(h2, None, None, h2, None, None, 1e-5, st)     # in place (row-local)
-            # ---- all masks of the group in ONE pass: the masked copies are row blocks of the same token matrix, so
-            #      every LayerNorm / GEMM / reduction launch covers them all (attention runs per mask); the reference
-            #      loops over the masks (wrappers.py:15-43), which is the same arithmetic row by row
-            mes = [m.contiguous() for m in masks_enc[i]]
-            mps = [m.contiguous() for m in masks_pred[i]]
-            pair_no += len(mes)
-            last = pair_no == n_pairs
-            # ---- context + predictor forward (train.py:420-423)
-            zs, sv_e = engine.encoder_forward(enc_rt, c, mes, grid, save=True, ws=ws)
-            preds, sv_p = engine.predictor_forward(pred_rt, zs, mes, mps, i, save=True, ws=ws)
-            # ---- loss (train.py:425-435) and its gradient, GradScaler-scaled (train.py:445)
-            Din = preds[0].shape[2]
-            rows = sum(pr.shape[0] * pr.shape[1] for pr in preds)
-            dz = ws.act((rows, Din), preds[0].dtype)
-            r0 = 0
-            for pr, mp in zip(preds, mps):
-                n = pr.shape[0] * pr.shape[1]
-                inv = 1.0 / (n_pairs * pr.numel())
-                mk = ws.mark()
-                ops.l1_loss(pr, h, mp, self.loss_accum, dz[r0:r0 + n], inv, inv, self.scale, st, ws.tmp)
-                ws.release(mk)
-                r0 += n
-            # ---- backward
-            dzenc = engine.predictor_backward(pred_rt, sv_p, dz, pfs.g32, ws=ws)
-            del sv_p
-            if last and self.world > 1:
-                self.bucketer.submit(pfs.g32, 0, pfs.total)
-                hook = lambda b, efs=efs: self.bucketer.submit(efs.g32, *self._enc_ranges[b])  # noqa: E731
-            else:
-                hook = None
-            engine.encoder_backward(enc_rt, sv_e, dzenc, efs.g32, ws=ws, on_block_done=hook)
-            del sv_e, zs, preds, dz, dzenc
-            ws._act.reset()                                       # this group's activations are dead
+            # ---- all masks of the group in ONE pass when their saved activations fit the budget: the masked copies are
+            #      row blocks of the same token matrix, so every LayerNorm / GEMM / reduction launch covers them all
+            #      (attention runs per mask); the reference loops over the masks (wrappers.py:15-43), which is the same
+            #      arithmetic row by row.  The 64f x 384px geometry (62 GB for mask 0 alone) goes mask by mask.
+            all_me = [m.contiguous() for m in masks_enc[i]]
+            all_mp = [m.contiguous() for m in masks_pred[i]]
+            for lo, hi in self._mask_passes(all_me, all_mp):
+                mes, mps = all_me[lo:hi], all_mp[lo:hi]
+                pair_no += len(mes)
+                last = pair_no == n_pairs
+                # ---- context + predictor forward (train.py:420-423)
+                zs, sv_e = engine.encoder_forward(enc_rt, c, mes, grid, save=True, ws=ws)
+                preds, sv_p = engine.predictor_forward(pred_rt, zs, mes, mps, i, save=True, ws=ws)
+                # ---- loss (train.py:425-435) and its gradient, GradScaler-scaled (train.py:445)
+                Din = preds[0].shape[2]
+                rows = sum(pr.shape[0] * pr.shape[1] for pr in preds)
+                dz = ws.act((rows, Din), preds[0].dtype)
+                r0 = 0
+                for pr, mp in zip(preds, mps):
+                    n = pr.shape[0] * pr.shape[1]
+                    inv = 1.0 / (n_pairs * pr.numel())
+                    mk = ws.mark()
+                    ops.l1_loss(pr, h, mp, self.loss_accum, dz[r0:r0 + n], inv, inv, self.scale, st, ws.tmp)
+                    ws.release(mk)
+                    r0 += n
+                # ---- backward
+                dzenc = engine.predictor_backward(pred_rt, sv_p, dz, pfs.g32, ws=ws)
+                del sv_p
+                if last and self.world > 1:
+                    self.bucketer.submit(pfs.g32, 0, pfs.total)
+                    hook = lambda b, efs=efs: self.bucketer.submit(efs.g32, *self._enc_ranges[b])  # noqa: E731
+                else:
+                    hook = None
+                engine.encoder_backward(enc_rt, sv_e, dzenc, efs.g32, ws=ws, on_block_done=hook)
+                del sv_e, zs, preds, dz, dzenc
+                ws._act.reset()                                   # this pass's activations are dead
         self.bucketer.wait()
 
         # ---- unscale + inf check + AdamW (train.py:446-451; app/vjepa/utils.py:239), flat kernels

@@ -16,6 +16,7 @@ from __future__ import annotations
 import torch
 
 _ALIGN = 256
+_GROW_CAP = 8 << 30
 
 
 class TorchAlloc:
@@ -52,8 +53,10 @@ class _Bump:
             while self.ci < len(self.chunks) and self.chunks[self.ci].numel() < nbytes:
                 self.ci += 1
             if self.ci == len(self.chunks):
+                # geometric growth, capped: a 60 GB arena (64f x 384px activations) must not double to 120 GB
                 total = sum(ch.numel() for ch in self.chunks)
-                self.chunks.append(torch.empty(max(nbytes, total), dtype=torch.uint8, device=self.device))
+                self.chunks.append(torch.empty(max(nbytes, min(total, _GROW_CAP)), dtype=torch.uint8,
+                                               device=self.device))
             self.off = 0
             c = self.chunks[self.ci]
         out = c[self.off:self.off + n * dtype.itemsize].view(dtype).view(shape)
