@@ -18,6 +18,8 @@
 
 #include "common.cuh"
 #include "host_common.h"
+#include <stdlib.h>
+
 #include "attn_common.cuh"
 #include "../../include/vjepa2_b200.h"
 
@@ -400,7 +402,11 @@ struct AttnBwd2Cfg {
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <int HD>
+// POLY: share of the P = exp2(.) evaluations done as a polynomial on the FMA pipe instead of MUFU.EX2 (16384
+// exponentials per 128 x 128 tile = 1024 MUFU cycles of a ~1475-cycle math phase): 0 none (default), 1 = one pair in
+// 8, 2 = one in 4, 4 = one in 2.  Measured on B200 (VJ_ATTN_BWD_POLY): every non-zero share is 1-6 % SLOWER, i.e. the
+// phase is bound by the issue / LDS mix, not by MUFU throughput; kept as an experiment switch.
+template <int HD, int POLY>
 __global__ void __launch_bounds__(320, 1)
 attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__ TMapPair tmDO,
                  const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse,
@@ -637,7 +643,15 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
                                          f32x2_pack(__uint_as_float(nl[e]), __uint_as_float(nl[e + 1])));
             float x0, x1;
             f32x2_unpack(x, x0, x1);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            float p0, p1;
+            const bool poly = POLY >= 4 ? e == 2 : POLY == 2 ? (e == 2 && (j & 4)) : POLY == 1 ? (e == 2 && (j & 12) == 12)
+                                                                                  : false;
+            if (poly) {
+              exp2_poly_pair(x0, x1, p0, p1);
+            } else {
+              p0 = ex2_approx(x0);
+              p1 = ex2_approx(x1);
+            }
             const uint64_t t = f32x2_fma(f32x2_pack(__uint_as_float(dv[j + e]), __uint_as_float(dv[j + e + 1])), s2,
                                          f32x2_pack(__uint_as_float(nd[e]), __uint_as_float(nd[e + 1])));
             const uint64_t d = f32x2_mul(f32x2_pack(p0, p1), t);
@@ -804,11 +818,17 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
                                                 scale * 1.4426950408889634f);
   } else {
     using Cfg2 = AttnBwd2Cfg<HD>;
-    auto kern = attn_bwd2_kernel<HD>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int poly = -1;
+    if (poly < 0) {
+      const char* e = getenv("VJ_ATTN_BWD_POLY");
+      poly = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 0;   // measured: no share wins here (profiles/)
+    }
+    auto kern = poly == 0 ? attn_bwd2_kernel<HD, 0> : poly == 1 ? attn_bwd2_kernel<HD, 1>
+              : poly <= 3 ? attn_bwd2_kernel<HD, 2> : attn_bwd2_kernel<HD, 4>;
+    static bool attr_set[5] = {false, false, false, false, false};
+    if (!attr_set[poly]) {
       VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
-      attr_set = true;
+      attr_set[poly] = true;
     }
     const int n_kt = (S + Cfg2::BT - 1) / Cfg2::BT;
     const long long n_items = (long long)n_kt * H * B;

@@ -33,11 +33,12 @@ def stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-# kernels launched per C-ABI call (bench.py reports the total as `gpu_launches`)
+# kernels launched per C-ABI call (bench.py reports the total as `gpu_launches`); layernorm_bwd = dx kernel + one
+# column-reduction kernel (every model width is a multiple of 8), colsum = one column-reduction kernel
 KERNELS_PER_CALL = {
-    "vj_gemm": 1, "vj_layernorm_fwd": 1, "vj_layernorm_bwd": 4, "vj_rope_table": 1, "vj_rope_apply": 1,
+    "vj_gemm": 1, "vj_layernorm_fwd": 1, "vj_layernorm_bwd": 2, "vj_rope_table": 1, "vj_rope_apply": 1,
     "vj_attn_fwd": 1, "vj_attn_bwd": 3, "vj_gather_rows": 1, "vj_scatter_add_rows": 1, "vj_mask_to_rows": 1,
-    "vj_im2col_tubelets": 1, "vj_colsum": 2, "vj_l1_loss": 2, "vj_argsort_rank": 1, "vj_pred_indices": 1,
+    "vj_im2col_tubelets": 1, "vj_colsum": 1, "vj_l1_loss": 2, "vj_argsort_rank": 1, "vj_pred_indices": 1,
     "vj_ema_update": 1, "vj_grad_check": 1, "vj_adamw_step": 1, "vj_scaler_update": 1, "vj_cast_f32_bf16": 1,
 }
 LAUNCHES = 0
