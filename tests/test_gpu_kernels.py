@@ -96,6 +96,75 @@ def test_gemm_wgrad_accumulate(dev, Nw, Kw, tok):
     assert relerr(g, ref) < 1e-5
 
 
+# the CTA-pair kernel (tcgen05 cta_group::2; selected for M >= 1024): every operand layout and epilogue, ragged M / N / K
+@pytest.mark.parametrize("M,N,K", [(1024, 256, 64), (1300, 1408, 1408), (2049, 384, 1536), (4097, 4224, 200)])
+def test_gemm_pair_kernel_forward_and_epilogues(dev, M, N, K):
+    from vjepa2_b200 import ops
+    a = randn(M, K, seed=1, dtype=BF16).to(dev)
+    w = randn(N, K, seed=2, dtype=BF16, scale=0.05).to(dev)
+    bias = randn(N, seed=3).to(dev)
+    res = randn(M, N, seed=4, dtype=BF16).to(dev)
+    pre = a.float() @ w.float().t() + bias
+    out = torch.empty(M, N, dtype=BF16, device=dev)
+    ops.gemm(a, w, out, M, N, K, bias=bias)
+    assert relerr(out, pre) < 4e-3
+    act = torch.empty(M, N, dtype=BF16, device=dev)
+    hpre = torch.empty(M, N, dtype=BF16, device=dev)
+    ops.gemm(a, w, act, M, N, K, bias=bias, gelu=True, round_bf16=True, aux_out=hpre)
+    assert relerr(hpre, pre) < 4e-3
+    assert relerr(act, torch.nn.functional.gelu(pre.bfloat16().float())) < 6e-3
+    ops.gemm(a, w, out, M, N, K, bias=bias, residual=res, round_bf16=True)
+    assert relerr(out, pre.bfloat16().float() + res.float()) < 4e-3
+    out32 = torch.empty(M, N, dtype=F32, device=dev)
+    ops.gemm(a, w, out32, M, N, K, bias=bias, residual=res.float(), round_bf16=True)
+    assert relerr(out32, pre.bfloat16().float() + res.float()) < 3e-3
+    aux = randn(M, N, seed=5, dtype=BF16, scale=2.0).to(dev)
+    dg = torch.empty(M, N, dtype=BF16, device=dev)
+    ops.gemm(a, w, dg, M, N, K, dgelu_aux=aux)
+    x = aux.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    assert relerr(dg, (a.float() @ w.float().t()) * x.grad) < 5e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(1100, 1408, 4224), (3000, 384, 1152)])
+def test_gemm_pair_kernel_dgrad(dev, M, N, K):
+    from vjepa2_b200 import ops
+    dy = randn(M, K, seed=1, dtype=BF16).to(dev)
+    w = randn(K, N, seed=2, dtype=BF16, scale=0.05).to(dev)
+    out = torch.empty(M, N, dtype=BF16, device=dev)
+    ops.gemm(dy, w, out, M, N, K, b_mn=True)
+    assert relerr(out, dy.float() @ w.float()) < 4e-3
+
+
+@pytest.mark.parametrize("Nw,Kw,tok", [(1408, 384, 1000), (4224, 1408, 3001), (1536, 384, 20000), (6144, 1408, 520)])
+def test_gemm_pair_kernel_wgrad_accumulate(dev, Nw, Kw, tok):
+    """Weight gradients: both operands MN-major, fp32 TMA reduce-add in place, split-K over the token dimension."""
+    from vjepa2_b200 import ops
+    dy = randn(tok, Nw, seed=1, dtype=BF16).to(dev)
+    x = randn(tok, Kw, seed=2, dtype=BF16).to(dev)
+    g0 = randn(Nw, Kw, seed=3).to(dev)
+    g = g0.clone()
+    ops.gemm(dy, x, g, Nw, Kw, tok, a_mn=True, b_mn=True, residual=g)
+    ref = g0 + dy.float().t() @ x.float()
+    assert relerr(g, ref) < 2e-5
+
+
+def test_gemm_pair_and_single_cta_kernels_agree_bitwise(dev):
+    """Same tile arithmetic (k-blocks of 64 in order, fp32 accumulate, identical epilogue): forcing the 1-CTA kernels
+    through a fresh process-level switch is not possible in-process, so compare M = 1023 (1-CTA) with the first 1023
+    rows of M = 1024 (pair): identical inputs per row must give identical bits."""
+    from vjepa2_b200 import ops
+    N, K = 1408, 1408
+    a = randn(1024, K, seed=1, dtype=BF16).to(dev)
+    w = randn(N, K, seed=2, dtype=BF16, scale=0.05).to(dev)
+    bias = randn(N, seed=3).to(dev)
+    o_pair = torch.empty(1024, N, dtype=BF16, device=dev)
+    o_one = torch.empty(1023, N, dtype=BF16, device=dev)
+    ops.gemm(a, w, o_pair, 1024, N, K, bias=bias, gelu=True, round_bf16=True)
+    ops.gemm(a[:1023].contiguous(), w, o_one, 1023, N, K, bias=bias, gelu=True, round_bf16=True)
+    assert torch.equal(o_pair[:1023], o_one)
+
+
 # ----------------------------------------------------------------------------------------------- attention
 def _sdpa_ref(qkv, B, S, H, hd):
     D = H * hd
