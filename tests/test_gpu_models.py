@@ -400,3 +400,25 @@ def test_encoder_inference_paths_vs_reference_golden(dev, golden_infer):
             want = golden_infer[f"infer.{name}.view{j}"]
             assert tuple(o.shape) == tuple(want.shape)
             assert relerr(o, want) < 1e-2, (name, j, relerr(o, want))
+
+
+@pytest.mark.gpu
+def test_target_stream_overlap_is_bit_identical(dev):
+    """The target-encoder forward on a second stream (fork after the previous EMA, join before the loss) must give
+    exactly the serial schedule's numbers: same kernels, same inputs, only the interleaving differs."""
+    from vjepa2_b200.train import JepaTrainStep
+    clips = tiny_clips(2)
+    me, mp = step_masks()
+    cd = [clips.to(dev)]
+    med, mpd = [[m.to(dev) for m in me]], [[m.to(dev) for m in mp]]
+    res = []
+    for overlap in (False, True):
+        enc, pred, _, _ = build_models(dev)
+        step = JepaTrainStep(enc, pred, overlap_target=overlap, **OPT_CFG)
+        assert step.overlap_target is overlap
+        losses = [float(step.step(cd, med, mpd)[0].item()) for _ in range(3)]
+        torch.cuda.synchronize()
+        res.append((losses, step.enc_rt.fs.p32.clone(), step.tgt_rt.fs.p32.clone(), step.pred_rt.fs.p32.clone()))
+    assert res[0][0] == res[1][0]
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert torch.equal(a, b)

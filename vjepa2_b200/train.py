@@ -136,7 +136,7 @@ class JepaTrainStep:
     def __init__(self, encoder, predictor, target_encoder=None, *, ipe=300, epochs=800, ipe_scale=1.25, warmup=40,
                  start_lr=1e-4, lr=5.25e-4, final_lr=5.25e-4, weight_decay=0.04, final_weight_decay=0.04,
                  ema=(0.99925, 0.99925), betas=(0.9, 0.999), eps=1e-8, loss_exp=1.0, mixed_precision=True,
-                 process_group=None):
+                 process_group=None, overlap_target=None):
         if loss_exp != 1.0:
             raise NotImplementedError("vjepa2_b200: loss_exp must be 1.0 (L1), as in every shipped config")
         self.encoder = _unwrap(encoder)
@@ -183,6 +183,21 @@ class JepaTrainStep:
         self.growth_tracker = torch.zeros(1, dtype=torch.int32, device=dev)
         self._frozen_key = None
         self.ws = Arena(dev)                                        # activations / temporaries (no allocator in-step)
+        # Optional: the target-encoder forward (train.py:414-418) does not depend on the context pass, so it can run
+        # on a second stream with its own arena, the prologue / tail of every persistent kernel of one stream filled
+        # by the other stream's next kernel (joined by an event before the loss reads h; forked after the previous
+        # step's EMA has rewritten the target weights).  Bit-identical results.  Measured on B200 (profiles/
+        # r01c_overlap_target_ab.txt): 78.13 vs 78.05 clips/s -- the step is power-capped, the filled gaps come back
+        # as a lower SM clock (1.46 vs 1.62 GHz) -- so it is OFF by default (VJ_OVERLAP_TARGET=1 / overlap_target=True).
+        if overlap_target is None:
+            import os
+            overlap_target = os.environ.get("VJ_OVERLAP_TARGET", "0") == "1"
+        self.overlap_target = bool(overlap_target)
+        self._side = torch.cuda.Stream(dev) if self.overlap_target else None
+        self.ws_t = None
+        if self.overlap_target:
+            with torch.cuda.stream(self._side):
+                self.ws_t = Arena(dev, act_bytes=1 << 20, tmp_bytes=1 << 28)
         # flat ranges of the per-block buckets (reverse order of completion in backward)
         fs = self.enc_rt.fs
         self._enc_ranges = {i: fs.range_of(h.params) for i, h in enumerate(self.enc_rt.blocks)}
@@ -267,10 +282,26 @@ class JepaTrainStep:
             _, _, T, H, W = c.shape
             grid = (H // p, W // p) if enc.handle_nonsquare_inputs else (enc.grid_size, enc.grid_size)
             # ---- target (train.py:414-418): no-grad encoder + non-affine LayerNorm, eps 1e-5
-            h, _ = engine.encoder_forward(tgt_rt, c, None, grid, save=False, ws=ws)   # stays on the tmp stack
-            Bq, N, D = h.shape
-            h2 = h.view(Bq * N, D)
-            ops.layernorm_fwd(h2, None, None, h2, None, None, 1e-5, st)     # in place (row-local)
+            ev_h = None
+            if self.overlap_target:
+                main = torch.cuda.current_stream()
+                ev_fork = torch.cuda.Event()
+                ev_fork.record(main)                      # previous EMA / loss reads of the old h are ahead of this
+                self._side.wait_event(ev_fork)
+                with torch.cuda.stream(self._side):
+                    if i == 0:
+                        self.ws_t.reset()
+                    h, _ = engine.encoder_forward(tgt_rt, c, None, grid, save=False, ws=self.ws_t)
+                    Bq, N, D = h.shape
+                    h2 = h.view(Bq * N, D)
+                    ops.layernorm_fwd(h2, None, None, h2, None, None, 1e-5, ops.stream())
+                    ev_h = torch.cuda.Event()
+                    ev_h.record(self._side)
+            else:
+                h, _ = engine.encoder_forward(tgt_rt, c, None, grid, save=False, ws=ws)   # stays on the tmp stack
+                Bq, N, D = h.shape
+                h2 = h.view(Bq * N, D)
+                ops.layernorm_fwd(h2, None, None, h2, None, None, 1e-5, st)     # in place (row-local)
             # ---- all masks of the group in ONE pass when their saved activations fit the budget: the masked copies are
             #      row blocks of the same token matrix, so every LayerNorm / GEMM / reduction launch covers them all
             #      (attention runs per mask); the reference loops over the masks (wrappers.py:15-43), which is the same
@@ -285,6 +316,9 @@ class JepaTrainStep:
                 zs, sv_e = engine.encoder_forward(enc_rt, c, mes, grid, save=True, ws=ws)
                 preds, sv_p = engine.predictor_forward(pred_rt, zs, mes, mps, i, save=True, ws=ws)
                 # ---- loss (train.py:425-435) and its gradient, GradScaler-scaled (train.py:445)
+                if ev_h is not None:
+                    torch.cuda.current_stream().wait_event(ev_h)      # join: h is complete
+                    ev_h = None
                 Din = preds[0].shape[2]
                 rows = sum(pr.shape[0] * pr.shape[1] for pr in preds)
                 dz = ws.act((rows, Din), preds[0].dtype)
