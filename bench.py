@@ -423,7 +423,7 @@ def main():
         import collections
         agg = collections.defaultdict(list)
         names = ["gemm", "layernorm_fwd", "layernorm_bwd", "attn_fwd", "attn_bwd", "gather_rows", "im2col_tubelets",
-                 "colsum", "l1_loss", "pred_indices", "rope_table", "cast_f32_bf16", "adamw_step", "ema_update",
+                 "colsum", "l1_loss", "pred_indices", "rope_table", "cast_f32_bf16", "adamw_step", "adam_prepare", "ema_update",
                  "grad_check", "scaler_update"]
         saved = {n: getattr(ops, n) for n in names}
 

@@ -187,10 +187,18 @@ int vj_grad_check(const float* g, int64_t n, float* found_inf, void* stream);
 /* torch.optim.AdamW (app/vjepa/utils.py:239) over a flat buffer, grads multiplied by *inv_scale,
  * skipped entirely when *found_inf != 0 (GradScaler.step).  tile_flags: one byte per 1024
  * elements: bit0 = weight decay applies, bit1 = frozen (no grad ever produced).  Also refreshes
- * the bf16 shadow.  bias corrections are passed in (host scalars: 1-b1^t, 1-b2^t). */
+ * the bf16 shadow.  bias corrections 1-b1^t, 1-b2^t: host scalars, or -- when dev_bias_c is non-null -- the two
+ * device floats written by vj_adam_prepare (the host scalars are then ignored). */
 int vj_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* p_bf16,
                   const uint8_t* tile_flags, int64_t n, float lr, float beta1, float beta2, float eps, float wd,
-                  float bias_c1, float bias_c2, const float* inv_scale, const float* found_inf, void* stream);
+                  float bias_c1, float bias_c2, const float* dev_bias_c, const float* inv_scale,
+                  const float* found_inf, void* stream);
+/* torch's optimizer step count does not advance on a step GradScaler skips (train.py:447-450).  Keeps that count on
+ * the device without a host sync: t = step - *skipped (step = number of calls so far, this one included); writes
+ * bias_c[0..1] = 1-b1^t, 1-b2^t (double precision) and, if *found_inf != 0, counts this step as skipped.
+ * Call once per step after vj_grad_check and before the vj_adamw_step launches. */
+int vj_adam_prepare(float* bias_c, int32_t* skipped, const float* found_inf, int step, double beta1, double beta2,
+                    void* stream);
 /* GradScaler.update() on device scalars (train.py:451): scale *= backoff if *found_inf else grows by
  * `growth` every `interval` clean steps; writes inv_scale = 1/(scale*world), clears found_inf. */
 int vj_scaler_update(float* scale, float* inv_scale, int32_t* growth_tracker, float* found_inf, float growth,

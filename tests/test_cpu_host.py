@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in include/vjepa2_b200.h but not exported"
         assert s in _cabi.SIGNATURES, f"{s} has no ctypes prototype"
     assert set(_cabi.SIGNATURES) == set(syms)
-    assert lib.vj_abi_version() == 1
+    assert lib.vj_abi_version() == 2
 
 
 def test_product_path_has_no_cpu_fallback():

@@ -444,6 +444,24 @@ def test_flat_optimizer_kernels(dev):
     tracker = torch.zeros(1, dtype=torch.int32, device=dev)
     ops.scaler_update(scale, inv_scale, tracker, found, world=2.0)
     assert float(scale) == 32768.0 and float(found) == 0.0 and abs(float(inv_scale) - 1 / 65536.0) < 1e-12
+    # device-side step count: the skipped step (3) must not advance torch's count, so the next applied step (host
+    # call 4) uses t = 3 -- checked against the oracle stepping 1, 2, 3 with no gap
+    bc = torch.ones(2, device=dev)
+    skipped = torch.zeros(1, dtype=torch.int32, device=dev)
+    found.fill_(1.0)
+    ops.adam_prepare(bc, skipped, found, 3, 0.9, 0.999)              # step 3: found_inf -> counted as skipped
+    assert int(skipped) == 1
+    ops.adamw_step(p, g2, m, v, sh, flags, 1e-3, 0.9, 0.999, 1e-8, 0.05, 3, inv_scale, found, dev_bias=bc)
+    assert torch.equal(p, before)
+    found.zero_()
+    inv_scale.fill_(0.5)
+    ops.adam_prepare(bc, skipped, found, 4, 0.9, 0.999)              # step 4 -> t = 3
+    assert int(skipped) == 1
+    assert abs(float(bc[0]) - (1 - 0.9 ** 3)) < 1e-7 and abs(float(bc[1]) - (1 - 0.999 ** 3)) < 1e-9
+    ops.adamw_step(p, g, m, v, sh, flags, 1e-3, 0.9, 0.999, 1e-8, 0.05, 4, inv_scale, found, dev_bias=bc)
+    O.adamw_step(pr, gr, st, 3, 1e-3, 0.05)
+    ref = torch.cat([t.reshape(-1) for t in pr.values()])
+    assert relerr(p.cpu(), ref) < 1e-6
     # EMA
     t = randn(n, seed=5).to(dev)
     t0 = t.clone()

@@ -422,3 +422,49 @@ def test_target_stream_overlap_is_bit_identical(dev):
     assert res[0][0] == res[1][0]
     for a, b in zip(res[0][1:], res[1][1:]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_overflow_skipped_step_does_not_advance_the_optimizer_step_count(dev):
+    """GradScaler semantics (train.py:446-451): a step whose scaled gradients overflow is skipped, the scale backs
+    off, and torch's per-parameter step count (hence the Adam bias corrections) does not advance.  Force one skipped
+    step (found_inf raised right after the gradient check), restore the scale, and the next step must equal the FIRST
+    step of an undisturbed run."""
+    from vjepa2_b200.train import JepaTrainStep
+    clips = tiny_clips(2)
+    me, mp = step_masks()
+    cd = [clips.to(dev)]
+    med, mpd = [[m.to(dev) for m in me]], [[m.to(dev) for m in mp]]
+
+    enc, pred, w_enc, _ = build_models(dev)
+    step = JepaTrainStep(enc, pred, **OPT_CFG)
+    import vjepa2_b200.ops as vops
+    real_check = vops.grad_check
+
+    def forced(g, found_inf, st=None):
+        real_check(g, found_inf, st)
+        found_inf.fill_(1.0)                                   # what an overflowed gradient would have produced
+    p_before = step.enc_rt.fs.p32.clone()
+    vops.grad_check = forced
+    try:
+        step.step(cd, med, mpd)
+    finally:
+        vops.grad_check = real_check
+    torch.cuda.synchronize()
+    assert torch.equal(step.enc_rt.fs.p32, p_before)           # skipped: weights untouched
+    assert torch.equal(step.enc_rt.fs.exp_avg, torch.zeros_like(step.enc_rt.fs.exp_avg))
+    assert float(step.scale) == 32768.0 and int(step.skipped) == 1
+    assert step.applied_steps == 1 and step.optimizer_steps() == 0
+    step.set_scaler(65536.0)
+    step.step(cd, med, mpd)
+    assert step.optimizer_steps() == 1
+
+    enc2, pred2, _, _ = build_models(dev)
+    ref = JepaTrainStep(enc2, pred2, **OPT_CFG)
+    ref.fast_forward(1)                                        # same LR / WD / momentum position as the disturbed run
+    ref.step(cd, med, mpd)
+    torch.cuda.synchronize()
+    a, b = step.enc_rt.fs.p32, ref.enc_rt.fs.p32
+    # with a wrong count (t = 2) the first update would be (1-b1)/(1-b1^2) = 0.53x as large
+    upd_a, upd_b = a - p_before, b - p_before
+    assert relerr(upd_a, upd_b) < 1e-3, relerr(upd_a, upd_b)

@@ -62,7 +62,8 @@ SIGNATURES = {
     "vj_ema_update": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_void_p]),
     "vj_grad_check": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "vj_adamw_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float,
-                              c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p]),
+                              c_float, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vj_adam_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.c_double, ctypes.c_double, c_void_p]),
     "vj_scaler_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_float,
                                  c_void_p]),
     "vj_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

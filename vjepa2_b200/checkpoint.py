@@ -144,7 +144,7 @@ def save_checkpoint(path, step, epoch, *, loss=0.0, batch_size=None, world_size=
         "encoder": _wrapped_state_dict(step.encoder, _prefix_of(encoder) if encoder is not None else "backbone."),
         "predictor": _wrapped_state_dict(step.predictor,
                                          _prefix_of(predictor) if predictor is not None else "backbone."),
-        "opt": build_opt_state_dict(groups, _moments_of(step), step.applied_steps, cur_lr, cur_wd, step.betas, step.eps),
+        "opt": build_opt_state_dict(groups, _moments_of(step), step.optimizer_steps(), cur_lr, cur_wd, step.betas, step.eps),
         "scaler": scaler_state_dict(step),
         "target_encoder": _wrapped_state_dict(step.target_encoder,
                                               _prefix_of(target_encoder) if target_encoder is not None else "backbone."),
@@ -172,7 +172,7 @@ def load_checkpoint(r_path, step, *, fast_forward=True, ipe=None):
         model.load_state_dict(clean_backbone_key(ckpt[key]))         # strict, like the reference
     step.reload_weights()
     groups = opt_param_groups(step.encoder, step.predictor)
-    step.applied_steps = restore_opt_state(groups, ckpt["opt"], _moments_of(step, skip_frozen=False))
+    step.set_optimizer_steps(restore_opt_state(groups, ckpt["opt"], _moments_of(step, skip_frozen=False)))
     sc = ckpt.get("scaler")
     if sc is not None and step.mixed_precision:
         step.set_scaler(float(sc["scale"]), int(sc["_growth_tracker"]))

@@ -762,16 +762,34 @@ struct AdamArgs {
   float step_size;     // lr / bias_c1
   float inv_sqrt_bc2;  // 1 / sqrt(bias_c2)
   float eps;
+  float lr;            // for device-side bias corrections
 };
+
+// torch keeps a per-parameter step count that an inf-skipped step (GradScaler.step) does NOT advance.  The host only
+// knows the number of step() calls; the number of skipped ones lives on the device: t = step - skipped.
+__global__ void adam_prepare_kernel(float* bias_c, int* skipped, const float* found_inf, int step, double b1, double b2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int sk = skipped[0];
+  int t = step - sk;
+  if (t < 1) t = 1;
+  if (found_inf && found_inf[0] != 0.f) skipped[0] = sk + 1;      // this step will be skipped by adamw_kernel
+  bias_c[0] = (float)(1.0 - pow(b1, (double)t));
+  bias_c[1] = (float)(1.0 - pow(b2, (double)t));
+}
 
 // one block per 4 tiles of 1024 elements; thread handles one float4 per tile
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                     float* __restrict__ m, float* __restrict__ v,
                                                     bf16* __restrict__ shadow, const uint8_t* __restrict__ flags,
                                                     long long ntiles, AdamArgs a, const float* __restrict__ inv_scale,
-                                                    const float* __restrict__ found_inf) {
+                                                    const float* __restrict__ found_inf,
+                                                    const float* __restrict__ dev_bias_c) {
   if (found_inf && found_inf[0] != 0.f) return;
   const float is = inv_scale ? inv_scale[0] : 1.0f;
+  if (dev_bias_c) {                                     // bias corrections of the device-side step count
+    a.step_size = a.lr / __ldg(dev_bias_c);
+    a.inv_sqrt_bc2 = 1.0f / sqrtf(__ldg(dev_bias_c + 1));
+  }
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const long long tile = (long long)blockIdx.x * 4 + t;
@@ -1072,8 +1090,8 @@ extern "C" int vj_grad_check(const float* g, int64_t n, float* found_inf, void* 
 
 extern "C" int vj_adamw_step(float* p, const float* g, float* exp_avg, float* exp_avg_sq, void* p_bf16,
                              const uint8_t* tile_flags, int64_t n, float lr, float beta1, float beta2, float eps,
-                             float wd, float bias_c1, float bias_c2, const float* inv_scale, const float* found_inf,
-                             void* stream) {
+                             float wd, float bias_c1, float bias_c2, const float* dev_bias_c, const float* inv_scale,
+                             const float* found_inf, void* stream) {
   VJ_CHECK(p && g && exp_avg && exp_avg_sq && tile_flags, "vj_adamw_step: null pointer");
   VJ_CHECK(n > 0 && n % 1024 == 0, "vj_adamw_step: n=%lld must be a positive multiple of 1024", (long long)n);
   AdamArgs a;
@@ -1084,10 +1102,20 @@ extern "C" int vj_adamw_step(float* p, const float* g, float* exp_avg, float* ex
   a.step_size = (float)((double)lr / (double)bias_c1);
   a.inv_sqrt_bc2 = (float)(1.0 / sqrt((double)bias_c2));
   a.eps = eps;
+  a.lr = lr;
   const long long ntiles = n / 1024;
   adamw_kernel<<<(unsigned)((ntiles + 3) / 4), 256, 0, STREAM(stream)>>>(p, g, exp_avg, exp_avg_sq,
                                                                         reinterpret_cast<bf16*>(p_bf16), tile_flags,
-                                                                        ntiles, a, inv_scale, found_inf);
+                                                                        ntiles, a, inv_scale, found_inf, dev_bias_c);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int vj_adam_prepare(float* bias_c, int32_t* skipped, const float* found_inf, int step, double beta1,
+                               double beta2, void* stream) {
+  VJ_CHECK(bias_c && skipped, "vj_adam_prepare: null pointer");
+  VJ_CHECK(step >= 1, "vj_adam_prepare: step=%d must be >= 1", step);
+  adam_prepare_kernel<<<1, 32, 0, STREAM(stream)>>>(bias_c, skipped, found_inf, step, beta1, beta2);
   VJ_LAUNCH_CHECK();
   return 0;
 }

@@ -39,7 +39,7 @@ KERNELS_PER_CALL = {
     "vj_gemm": 1, "vj_layernorm_fwd": 1, "vj_layernorm_bwd": 2, "vj_rope_table": 1, "vj_rope_apply": 1,
     "vj_attn_fwd": 1, "vj_attn_bwd": 3, "vj_gather_rows": 1, "vj_scatter_add_rows": 1, "vj_mask_to_rows": 1,
     "vj_im2col_tubelets": 1, "vj_colsum": 1, "vj_l1_loss": 2, "vj_argsort_rank": 1, "vj_pred_indices": 1,
-    "vj_ema_update": 1, "vj_grad_check": 1, "vj_adamw_step": 1, "vj_scaler_update": 1, "vj_cast_f32_bf16": 1,
+    "vj_ema_update": 1, "vj_grad_check": 1, "vj_adamw_step": 1, "vj_adam_prepare": 1, "vj_scaler_update": 1, "vj_cast_f32_bf16": 1,
 }
 LAUNCHES = 0
 _real_check = C.check
@@ -267,13 +267,20 @@ def grad_check(g, found_inf, st=None):
 
 
 def adamw_step(p, g, m, v, p_bf16, tile_flags, lr, beta1, beta2, eps, wd, step, inv_scale=None, found_inf=None,
-               st=None):
+               st=None, dev_bias=None):
+    """dev_bias: the two device floats of adam_prepare (step count that skips inf-skipped steps, like torch's);
+    without it the bias corrections come from the host-side `step`."""
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
     _counting_check(C.load().vj_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(p_bf16),
                                    tile_flags.data_ptr(), p.numel(), lr, beta1, beta2, eps, wd, bc1, bc2,
-                                   _p(inv_scale), _p(found_inf), st if st is not None else stream()),
+                                   _p(dev_bias), _p(inv_scale), _p(found_inf), st if st is not None else stream()),
             "vj_adamw_step")
+
+
+def adam_prepare(bias_c, skipped, found_inf, step, beta1, beta2, st=None):
+    _counting_check(C.load().vj_adam_prepare(bias_c.data_ptr(), skipped.data_ptr(), _p(found_inf), int(step), float(beta1),
+                                             float(beta2), st if st is not None else stream()), "vj_adam_prepare")
 
 
 def scaler_update(scale, inv_scale, growth_tracker, found_inf, world=1.0, growth=2.0, backoff=0.5, interval=2000,

@@ -155,8 +155,8 @@ class JepaTrainStep:
         self.momentum = momentum_schedule(ema, ipe, epochs, ipe_scale)
         self.bucketer = GradBucketer(process_group)
         self.world = self.bucketer.world
-        # optimizer step count (torch keeps it per parameter; an inf-skipped step still counts here, which only
-        # differs from torch after a GradScaler overflow -- never seen with bf16 at these scales)
+        # optimizer step() calls so far; the steps GradScaler skipped (found_inf) are counted on the device
+        # (self.skipped), so the bias corrections use torch's count, applied_steps - skipped, without a host sync
         self.applied_steps = 0
         # the step manages bf16 shadows itself (AdamW / EMA kernels rewrite them)
         for m in (self.encoder, self.predictor, self.target_encoder):
@@ -181,6 +181,8 @@ class JepaTrainStep:
         self.inv_scale = torch.full((1,), 1.0 / (init_scale * self.world), dtype=f32, device=dev)
         self.found_inf = torch.zeros(1, dtype=f32, device=dev)
         self.growth_tracker = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.skipped = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.bias_c = torch.ones(2, dtype=f32, device=dev)
         self._frozen_key = None
         self.ws = Arena(dev)                                        # activations / temporaries (no allocator in-step)
         # Optional: the target-encoder forward (train.py:414-418) does not depend on the context pass, so it can run
@@ -222,6 +224,14 @@ class JepaTrainStep:
             if not rt.fs.valid():
                 raise RuntimeError("vjepa2_b200: parameters were re-allocated (e.g. .to()); build a new JepaTrainStep")
             rt.fs.refresh_shadows()
+
+    def optimizer_steps(self):
+        """torch's optimizer step count: step() calls minus the ones GradScaler skipped (one 4-byte D2H read)."""
+        return self.applied_steps - int(self.skipped.item())
+
+    def set_optimizer_steps(self, n):
+        self.applied_steps = int(n)
+        self.skipped.zero_()
 
     def set_scaler(self, scale, growth_tracker=0):
         """GradScaler.load_state_dict (app/vjepa/utils.py:121-122)."""
@@ -347,9 +357,10 @@ class JepaTrainStep:
         ops.grad_check(efs.g32, self.found_inf, st)
         ops.grad_check(pfs.g32, self.found_inf, st)
         b1, b2 = self.betas
+        ops.adam_prepare(self.bias_c, self.skipped, self.found_inf, self.applied_steps, b1, b2, st)
         for fs in (efs, pfs):
             ops.adamw_step(fs.p32, fs.g32, fs.exp_avg, fs.exp_avg_sq, fs.p16, fs.flags, new_lr, b1, b2, self.eps,
-                           new_wd, self.applied_steps, self.inv_scale, self.found_inf, st)
+                           new_wd, self.applied_steps, self.inv_scale, self.found_inf, st, dev_bias=self.bias_c)
         if self.mixed_precision:
             ops.scaler_update(self.scale, self.inv_scale, self.growth_tracker, self.found_inf, float(self.world), st=st)
         else:
