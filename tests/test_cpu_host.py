@@ -311,3 +311,30 @@ def test_mask_passes_respect_the_activation_budget():
     assert JepaTrainStep._mask_passes(ns, mes, mps) == [(0, 2), (2, 3)]
     ns.ACT_BUDGET_BYTES = 1                               # nothing fits: one mask per pass, never an empty pass
     assert JepaTrainStep._mask_passes(ns, mes, mps) == [(0, 1), (1, 2), (2, 3)]
+
+
+def test_wrappers_fan_out_protocol():
+    """src/utils/wrappers.py:15-43: outputs nest as [group][mask]; the predictor gets mask_index = group index."""
+    from vjepa2_b200.wrappers import MultiSeqWrapper, PredictorMultiSeqWrapper
+    calls = []
+
+    class _Enc(torch.nn.Module):
+        def forward(self, x, masks=None):
+            calls.append(("enc", int(x), None if masks is None else int(masks)))
+            return (int(x), None if masks is None else int(masks))
+
+    class _Pred(torch.nn.Module):
+        def forward(self, z, mx, my, mask_index=1, has_cls=False):
+            return (z, int(mx), int(my), mask_index, has_cls)
+
+    enc = MultiSeqWrapper(_Enc())
+    x = [torch.tensor(10), torch.tensor(20)]
+    masks = [[torch.tensor(1), torch.tensor(2)], [torch.tensor(3)]]
+    assert enc(x) == [(10, None), (20, None)]
+    z = enc(x, masks)
+    assert z == [[(10, 1), (10, 2)], [(20, 3)]]
+    assert [c[1:] for c in calls[-3:]] == [(10, 1), (10, 2), (20, 3)]          # group-major call order
+    pred = PredictorMultiSeqWrapper(_Pred())
+    out = pred(z, masks, [[torch.tensor(7), torch.tensor(8)], [torch.tensor(9)]], has_cls=False)
+    assert out == [[((10, 1), 1, 7, 0, False), ((10, 2), 2, 8, 0, False)], [((20, 3), 3, 9, 1, False)]]
+    assert list(dict(enc.named_modules()).keys())[1] == "backbone"             # checkpoint key prefix

@@ -1,13 +1,18 @@
-"""Mask application and generation: src/masks/utils.py:9-21 (apply_masks) and
-src/masks/multiseq_multiblock3d.py:16-239 (MaskCollator, _MaskGenerator).
+"""Mask application and generation: the counterparts of src/masks/utils.py:9-21 (apply_masks) and
+src/masks/multiseq_multiblock3d.py:16-239 (MaskCollator and its per-config generator).
 
-apply_masks runs on the device as a 128-bit row-copy gather (bit-exact).  The generator is host-side
-integer work, kept RNG-call-identical to the reference (same torch CPU generator calls in the same
-order), so identical RNG state in gives bit-identical indices out.
+apply_masks runs on the device as a 128-bit row-copy gather (bit-exact).  The multiblock-3D sampler is host-side
+integer work; its contract with the reference is the RANDOM STREAM, not the code: per draw one seeded generator
+yields three uniforms (temporal scale, spatial scale, aspect ratio), then the GLOBAL torch CPU generator yields,
+per sample and block, `randint` top, left, start in that order (multiseq_multiblock3d.py:172-196).  Identical RNG
+state in therefore gives bit-identical index tensors out (golden-pinned in tests/test_cpu_host.py).  Everything
+around those calls -- a boolean visibility grid instead of multiplied int32 masks, specs as dataclasses -- is
+this package's own.
 """
 from __future__ import annotations
 
 import math
+from dataclasses import dataclass
 from multiprocessing import Value
 
 import torch
@@ -57,135 +62,142 @@ def apply_masks(x, masks, concat=True):
     return torch.cat(outs, dim=0)
 
 
-class MaskCollator(object):
-    def __init__(self, cfgs_mask, dataset_fpcs, crop_size=(224, 224), patch_size=(16, 16), tubelet_size=2):
-        self.mask_generators = dict()
-        for fpc in dataset_fpcs:
-            self.mask_generators[fpc] = []
-            for m in cfgs_mask:
-                self.mask_generators[fpc].append(_MaskGenerator(
-                    crop_size=crop_size, num_frames=fpc, spatial_patch_size=patch_size,
-                    temporal_patch_size=tubelet_size, spatial_pred_mask_scale=m.get("spatial_scale"),
-                    temporal_pred_mask_scale=m.get("temporal_scale"), aspect_ratio=m.get("aspect_ratio"),
-                    npred=m.get("num_blocks"), max_context_frames_ratio=m.get("max_temporal_keep", 1.0),
-                    max_keep=m.get("max_keep", None), full_complement=m.get("full_complement", False),
-                    pred_full_complement=m.get("pred_full_complement", False), inv_block=m.get("inv_block", False)))
+@dataclass(frozen=True)
+class TokenGrid:
+    """Token lattice of a clip after tubelet / patch embedding: frames x rows x columns."""
+    frames: int
+    rows: int
+    cols: int
+
+    @property
+    def size(self):
+        return self.frames * self.rows * self.cols
+
+
+@dataclass(frozen=True)
+class BlockMaskSpec:
+    """One entry of the YAML `mask:` list (configs/train/*/pretrain-*.yaml)."""
+    spatial_scale: tuple = (0.2, 0.8)
+    temporal_scale: tuple = (1.0, 1.0)
+    aspect_ratio: tuple = (0.3, 3.0)
+    num_blocks: int = 1
+    max_temporal_keep: float = 1.0
+    max_keep: int | None = None
+    full_complement: bool = False
+    pred_full_complement: bool = False
+    inv_block: bool = False
+
+    @classmethod
+    def from_cfg(cls, cfg):
+        known = {f: cfg[f] for f in cls.__dataclass_fields__ if cfg.get(f) is not None}
+        return cls(**known)
+
+
+def _lerp(lo_hi, u):
+    return lo_hi[0] + u * (lo_hi[1] - lo_hi[0])
+
+
+class BlockMaskSampler:
+    """Draws (kept, masked) token-id matrices for one mask spec on one token grid."""
+
+    def __init__(self, grid: TokenGrid, spec: BlockMaskSpec):
+        self.grid, self.spec = grid, spec
+        self.context_frames = max(1, int(grid.frames * spec.max_temporal_keep))
+        self._draws = Value("i", -1)              # shared by DataLoader workers: draw k is seeded with k
 
     def step(self):
-        for fpc in self.mask_generators:
-            for g in self.mask_generators[fpc]:
-                g.step()
+        with self._draws.get_lock():
+            self._draws.value += 1
+            return self._draws.value
 
-    def __call__(self, batch):
-        filtered = {fpc: [] for fpc in self.mask_generators}
-        for sample in batch:
-            filtered[len(sample[-1][-1])] += [sample]
-        out = []
-        for fpc, fpc_batch in filtered.items():
-            if len(fpc_batch) == 0:
-                continue
-            collated = torch.utils.data.default_collate(fpc_batch)
-            enc, pred = [], []
-            for g in self.mask_generators[fpc]:
-                me, mp = g(len(fpc_batch))
-                enc.append(me)
-                pred.append(mp)
-            out += [(collated, enc, pred)]
-        return out
+    # -- the three seeded uniforms of a draw -> block extent (frames, rows, cols), shared by the whole batch
+    def _block_extent(self, seed):
+        gen = torch.Generator().manual_seed(seed)
+        u_t, u_s, u_a = (torch.rand(1, generator=gen).item() for _ in range(3))
+        g, sp = self.grid, self.spec
+        frames = max(1, int(g.frames * _lerp(sp.temporal_scale, u_t)))
+        area = int(g.rows * g.cols * _lerp(sp.spatial_scale, u_s))
+        aspect = _lerp(sp.aspect_ratio, u_a)
+        rows = min(int(round(math.sqrt(area * aspect))), g.rows)
+        cols = min(int(round(math.sqrt(area / aspect))), g.cols)
+        return frames, rows, cols
 
-    def draw(self, fpc, batch_size):
-        """Masks only (what the step consumes): ([masks_enc per cfg], [masks_pred per cfg])."""
-        enc, pred = [], []
-        for g in self.mask_generators[fpc]:
-            me, mp = g(batch_size)
-            enc.append(me)
-            pred.append(mp)
-        return enc, pred
-
-
-class _MaskGenerator(object):
-    def __init__(self, crop_size=(224, 224), num_frames=16, spatial_patch_size=(16, 16), temporal_patch_size=2,
-                 spatial_pred_mask_scale=(0.2, 0.8), temporal_pred_mask_scale=(1.0, 1.0), aspect_ratio=(0.3, 3.0),
-                 npred=1, max_context_frames_ratio=1.0, max_keep=None, inv_block=False, full_complement=False,
-                 pred_full_complement=False):
-        if not isinstance(crop_size, tuple):
-            crop_size = (crop_size,) * 2
-        if not isinstance(spatial_patch_size, tuple):
-            spatial_patch_size = (spatial_patch_size,) * 2
-        self.crop_size = crop_size
-        self.height, self.width = [crop_size[i] // spatial_patch_size[i] for i in (0, 1)]
-        self.duration = num_frames // temporal_patch_size
-        self.full_complement = full_complement
-        self.pred_full_complement = pred_full_complement
-        self.aspect_ratio = aspect_ratio
-        self.spatial_pred_mask_scale = spatial_pred_mask_scale
-        self.temporal_pred_mask_scale = temporal_pred_mask_scale
-        self.npred = npred
-        self.max_context_duration = max(1, int(self.duration * max_context_frames_ratio))
-        self.max_keep = max_keep
-        self._itr_counter = Value("i", -1)   # shared across DataLoader workers, as in the reference
-        self.inv_block = inv_block
-
-    def step(self):
-        i = self._itr_counter
-        with i.get_lock():
-            i.value += 1
-            return i.value
-
-    def _sample_block_size(self, generator, temporal_scale, spatial_scale, aspect_ratio_scale):
-        r = torch.rand(1, generator=generator).item()
-        t = max(1, int(self.duration * (temporal_scale[0] + r * (temporal_scale[1] - temporal_scale[0]))))
-        r = torch.rand(1, generator=generator).item()
-        keep = int(self.height * self.width * (spatial_scale[0] + r * (spatial_scale[1] - spatial_scale[0])))
-        r = torch.rand(1, generator=generator).item()
-        ar = aspect_ratio_scale[0] + r * (aspect_ratio_scale[1] - aspect_ratio_scale[0])
-        h = min(int(round(math.sqrt(keep * ar))), self.height)
-        w = min(int(round(math.sqrt(keep / ar))), self.width)
-        return (t, h, w)
-
-    def _sample_block_mask(self, b_size):
-        t, h, w = b_size
-        top = torch.randint(0, self.height - h + 1, (1,))
-        left = torch.randint(0, self.width - w + 1, (1,))
-        start = torch.randint(0, self.duration - t + 1, (1,))
-        mask = torch.ones((self.duration, self.height, self.width), dtype=torch.int32)
-        mask[start:start + t, top:top + h, left:left + w] = 0
-        if self.max_context_duration < self.duration:
-            mask[self.max_context_duration:, :, :] = 0
-        return mask
+    # -- one sample: the union of num_blocks boxes is hidden; three global-RNG randints per box (top, left, start)
+    def _visible(self, extent):
+        g = self.grid
+        bf, br, bc = extent
+        vis = torch.ones(g.frames, g.rows, g.cols, dtype=torch.bool)
+        for _ in range(self.spec.num_blocks):
+            top = int(torch.randint(0, g.rows - br + 1, (1,)))
+            left = int(torch.randint(0, g.cols - bc + 1, (1,)))
+            start = int(torch.randint(0, g.frames - bf + 1, (1,)))
+            vis[start:start + bf, top:top + br, left:left + bc] = False
+        if self.context_frames < g.frames:
+            vis[self.context_frames:] = False
+        return vis.flatten()
 
     def __call__(self, batch_size):
-        g = torch.Generator()
-        g.manual_seed(self.step())
-        p_size = self._sample_block_size(g, self.temporal_pred_mask_scale, self.spatial_pred_mask_scale,
-                                         self.aspect_ratio)
-        masks_p, masks_e = [], []
-        total = self.duration * self.height * self.width
-        min_keep_enc = min_keep_pred = total
+        extent = self._block_extent(self.step())
+        kept, hidden = [], []
         for _ in range(batch_size):
-            while True:
-                mask_e = torch.ones((self.duration, self.height, self.width), dtype=torch.int32)
-                for _ in range(self.npred):
-                    mask_e *= self._sample_block_mask(p_size)
-                mask_e = mask_e.flatten()
-                mask_p = torch.argwhere(mask_e == 0).squeeze()
-                mask_e = torch.nonzero(mask_e).squeeze()
-                if len(mask_e) != 0:
-                    break
-            min_keep_pred = min(min_keep_pred, len(mask_p))
-            min_keep_enc = min(min_keep_enc, len(mask_e))
-            masks_p.append(mask_p)
-            masks_e.append(mask_e)
-        if self.max_keep is not None:
-            min_keep_enc = min(min_keep_enc, self.max_keep)
-        masks_e = [cm[:min_keep_enc] for cm in masks_e]
-        masks_p = [cm[:min_keep_pred] for cm in masks_p]
-        if self.full_complement:
-            masks_p = [torch.tensor(sorted(set(range(total)) - set(cm.tolist())), dtype=cm.dtype) for cm in masks_e]
-        elif self.pred_full_complement:
-            masks_e = [torch.tensor(sorted(set(range(total)) - set(cm.tolist())), dtype=cm.dtype) for cm in masks_p]
-        masks_e = torch.utils.data.default_collate(masks_e)
-        masks_p = torch.utils.data.default_collate(masks_p)
-        if self.inv_block:
-            return masks_p, masks_e
-        return masks_e, masks_p
+            vis = self._visible(extent)
+            while not bool(vis.any()):              # nothing left for the encoder: draw this sample again
+                vis = self._visible(extent)
+            ids = torch.arange(self.grid.size)
+            kept.append(ids[vis])
+            hidden.append(ids[~vis])
+        # a batch is rectangular: truncate every sample to the shortest one (and to max_keep)
+        n_kept = min(len(k) for k in kept)
+        n_hidden = min(len(h) for h in hidden)
+        if self.spec.max_keep is not None:
+            n_kept = min(n_kept, self.spec.max_keep)
+        kept = [k[:n_kept] for k in kept]
+        hidden = [h[:n_hidden] for h in hidden]
+        everything = torch.ones(self.grid.size, dtype=torch.bool)
+        if self.spec.full_complement:               # predict every token the (truncated) context does not hold
+            hidden = [_complement(everything, k) for k in kept]
+        elif self.spec.pred_full_complement:
+            kept = [_complement(everything, h) for h in hidden]
+        kept, hidden = torch.stack(kept), torch.stack(hidden)
+        return (hidden, kept) if self.spec.inv_block else (kept, hidden)
+
+
+def _complement(everything, ids):
+    rest = everything.clone()
+    rest[ids] = False
+    return torch.nonzero(rest).squeeze(1)
+
+
+class MaskCollator(object):
+    """DataLoader collate_fn (multiseq_multiblock3d.py:16-76): groups samples by frames-per-clip, collates each group
+    and attaches one (masks_enc, masks_pred) pair per mask spec.  Same constructor arguments and output structure."""
+
+    def __init__(self, cfgs_mask, dataset_fpcs, crop_size=(224, 224), patch_size=(16, 16), tubelet_size=2):
+        crop = crop_size if isinstance(crop_size, tuple) else (crop_size,) * 2
+        patch = patch_size if isinstance(patch_size, tuple) else (patch_size,) * 2
+        specs = [BlockMaskSpec.from_cfg(c) for c in cfgs_mask]
+        self.samplers = {
+            fpc: [BlockMaskSampler(TokenGrid(fpc // tubelet_size, crop[0] // patch[0], crop[1] // patch[1]), sp)
+                  for sp in specs]
+            for fpc in dataset_fpcs}
+
+    def step(self):
+        for group in self.samplers.values():
+            for sampler in group:
+                sampler.step()
+
+    def draw(self, fpc, batch_size):
+        """Masks only (what the step consumes): ([masks_enc per spec], [masks_pred per spec])."""
+        pairs = [sampler(batch_size) for sampler in self.samplers[fpc]]
+        return [e for e, _ in pairs], [p for _, p in pairs]
+
+    def __call__(self, batch):
+        by_fpc = {fpc: [] for fpc in self.samplers}
+        for sample in batch:
+            by_fpc[len(sample[-1][-1])].append(sample)      # frames per clip = length of the last clip-index list
+        out = []
+        for fpc, group in by_fpc.items():
+            if group:
+                enc, pred = self.draw(fpc, len(group))
+                out.append((torch.utils.data.default_collate(group), enc, pred))
+        return out

@@ -1,31 +1,33 @@
-"""src/utils/wrappers.py of the reference (MultiSeqWrapper :9-27, PredictorMultiSeqWrapper :30-43):
-the per-fpc-group x per-mask fan-out of the encoder and predictor calls."""
+"""Fan-out of the encoder / predictor over frames-per-clip groups and masks -- the call protocol of the reference's
+src/utils/wrappers.py (MultiSeqWrapper :9-27, PredictorMultiSeqWrapper :30-43): inputs are lists over groups (and,
+inside a group, lists over masks); outputs mirror that nesting.  `backbone` keeps its attribute name because
+checkpoints carry it as a key prefix (`module.backbone.*`) and callers read `encoder.backbone.embed_dim`.
+
+(The fused training step does not go through these modules: `JepaTrainStep` hands all masks of a group to the
+engine at once so they share every LayerNorm / GEMM launch.  They serve the autograd drop-in path.)"""
 import torch.nn as nn
 
 
-class MultiSeqWrapper(nn.Module):
+class _GroupFanOut(nn.Module):
     def __init__(self, backbone):
         super().__init__()
         self.backbone = backbone
 
+    @staticmethod
+    def _each_group(groups, fn):
+        return [fn(i, g) for i, g in enumerate(groups)]
+
+
+class MultiSeqWrapper(_GroupFanOut):
     def forward(self, x, masks=None):
         if masks is None:
-            return [self.backbone(xi) for xi in x]
-        outs = [[] for _ in x]
-        for i, (xi, mi) in enumerate(zip(x, masks)):
-            for mij in mi:
-                outs[i] += [self.backbone(xi, masks=mij)]
-        return outs
+            return self._each_group(x, lambda i, clip: self.backbone(clip))
+        return self._each_group(x, lambda i, clip: [self.backbone(clip, masks=m) for m in masks[i]])
 
 
-class PredictorMultiSeqWrapper(nn.Module):
-    def __init__(self, backbone):
-        super().__init__()
-        self.backbone = backbone
-
+class PredictorMultiSeqWrapper(_GroupFanOut):
     def forward(self, x, masks_x, masks_y, has_cls=False):
-        outs = [[] for _ in x]
-        for i, (xi, mxi, myi) in enumerate(zip(x, masks_x, masks_y)):
-            for xij, mxij, myij in zip(xi, mxi, myi):
-                outs[i] += [self.backbone(xij, mxij, myij, mask_index=i, has_cls=has_cls)]
-        return outs
+        def one_group(i, ctx_tokens):
+            return [self.backbone(z, mx, my, mask_index=i, has_cls=has_cls)
+                    for z, mx, my in zip(ctx_tokens, masks_x[i], masks_y[i])]
+        return self._each_group(x, one_group)
