@@ -650,8 +650,11 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// default (.release.cta) semantics: the arrive only has to follow this warp's tcgen05.ld + wait::ld in program order
+// (the data is already in registers); a .release.cluster arrive compiles to MEMBAR.ALL + ERRBAR and cost 11 % of the
+// epilogue warps' stall samples (profiles/r01c_ncu_gemm2_gelu_summary.txt)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion bytes are credited to an mbarrier in the leader CTA of the pair
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
