@@ -47,10 +47,11 @@ def block_flops(S, D, Hm):
     return 8 * S * D * D + 4 * S * D * Hm + 4 * S * S * D
 
 
-def step_flops(model, B, k_enc, k_pred):
+def step_flops(model, B, k_enc, k_pred, ntok=None):
     """Algorithmic FLOPs of one train step for B clips (backward = 2x forward, no recompute counted)."""
     D, depth, _, Hm = MODELS[model]
     pe = 2 * 1536 * D
+    NTOK = ntok if ntok is not None else globals()["NTOK"]
     f = depth * block_flops(NTOK, D, Hm) + NTOK * pe                       # target forward
     for ke, kp in zip(k_enc, k_pred):
         f += 3 * depth * block_flops(ke, D, Hm) + 2 * ke * pe                # context fwd+bwd (+patch embed fwd, wgrad)
@@ -109,29 +110,62 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def make_masks(collator, B, steps):
+def make_masks(collator, B, steps, frames=None):
     out = []
     for _ in range(steps):
-        enc, pred = collator.draw(FRAMES, B)
+        enc, pred = collator.draw(frames or FRAMES, B)
         out.append((enc, pred))
     return out
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step_time(model, max_seconds=240.0, steps=1, warmup=0, batch=1, log=None):
-    """Times the oracle's restatement of the reference step (fp32, torch CPU, all host threads)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+def host_threads():
+    """Use every host core: torchrun exports OMP_NUM_THREADS=1, which would cripple the CPU arm."""
     import torch
-    import vjepa_oracle as O
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0)) or n
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def ref_harness():
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_harness as H
+    return H
+
+
+def cpu_reference_step_time(model, max_seconds=240.0, steps=1, warmup=0, batch=1, log=None):
+    """Times the reference's CPU path of the step (fp32, torch CPU, all host threads) on 1-clip samples of the
+    workload.  kind "reference": the reference's own modules (baseline/_ref, see baseline/ref_harness.py) around the
+    restated step closure; kind "port": oracle/vjepa_oracle.py when the reference tree is absent."""
+    import torch
     D, depth, heads, Hm = MODELS[model]
+    H = ref_harness()
+    kind = "reference" if H.find_ref_root() is not None else "port"
     torch.manual_seed(0)
-    w_enc = O.init_encoder_weights(D, depth, Hm / D, seed=0)
-    w_pred = O.init_predictor_weights(D, PRED["dim"], PRED["depth"], 6, seed=1)
-    st = O.StepState(w_enc, w_pred, dict(depth=depth, heads=heads),
-                     dict(depth=PRED["depth"], heads=PRED["heads"], grid_size=CROP // PATCH, num_patches=NTOK,
-                          num_mask_tokens=6), dict(OPT, loss_exp=1.0))
-    del w_enc, w_pred
-    gens = O.make_mask_generators(O.DEFAULT_MASK_CFG, (CROP, CROP), FRAMES)
+    if kind == "reference":
+        R = H.import_reference()
+        enc, pred = H.build_models(R, model, crop=CROP, frames=FRAMES, pred_depth=PRED["depth"], pred_heads=PRED["heads"],
+                                   pred_dim=PRED["dim"], num_mask_tokens=6)
+        rs = H.RefStep(R, enc, pred, dict(OPT, loss_exp=1.0), mixed_precision=False)
+        coll = R.MaskCollator(cfgs_mask=MASK_CFG, dataset_fpcs=[FRAMES], crop_size=(CROP, CROP), patch_size=(PATCH, PATCH),
+                              tubelet_size=TUB)
+        gens = coll.mask_generators[FRAMES]
+        run = lambda c, me, mp: rs.step([c], [me], [mp])["loss"]  # noqa: E731
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import vjepa_oracle as O
+        w_enc = O.init_encoder_weights(D, depth, Hm / D, seed=0)
+        w_pred = O.init_predictor_weights(D, PRED["dim"], PRED["depth"], 6, seed=1)
+        st = O.StepState(w_enc, w_pred, dict(depth=depth, heads=heads),
+                         dict(depth=PRED["depth"], heads=PRED["heads"], grid_size=CROP // PATCH, num_patches=NTOK,
+                              num_mask_tokens=6), dict(OPT, loss_exp=1.0))
+        del w_enc, w_pred
+        gens = O.make_mask_generators(O.DEFAULT_MASK_CFG, (CROP, CROP), FRAMES)
+        run = lambda c, me, mp: O.train_step(st, c, me, mp)  # noqa: E731
     torch.manual_seed(239)
     g = torch.Generator().manual_seed(0)
     times, flops = [], []
@@ -141,16 +175,124 @@ def cpu_reference_step_time(model, max_seconds=240.0, steps=1, warmup=0, batch=1
         masks = [gen(batch) for gen in gens]
         me, mp = [m[0] for m in masks], [m[1] for m in masks]
         t0 = time.time()
-        loss = O.train_step(st, clips, me, mp)
+        loss = run(clips, me, mp)
         dt = time.time() - t0
         if log:
-            log(f"cpu reference step {it}: {dt:.1f}s loss {loss:.4f}")
+            log(f"cpu {kind} step {it}: {dt:.1f}s loss {loss:.4f}")
         if it >= warmup:
             times.append(dt)
             flops.append(step_flops(model, batch, [m.shape[1] for m in me], [m.shape[1] for m in mp]))
         if time.time() - t_begin > max_seconds and times:
             break
-    return times, flops, batch
+    return times, flops, batch, kind
+
+
+def cpu_sample_text(kind, n_steps, batch):
+    what = ("the reference's own modules (baseline/_ref) + restated train.py:409-471" if kind == "reference"
+            else "oracle/vjepa_oracle.py")
+    return (f"{n_steps} step(s) of 1 clip (same model, masks and optimizer; the GPU arm runs batch {batch}), "
+            f"{what} on torch CPU fp32")
+
+
+# ---------------------------------------------------------------------------------------------- reference on the GPU
+def torch_cuda_baseline(model, B, masks_host, clips_host, dev, warmup=2, steps=3, log=None):
+    """The like-for-like bar (SURVEY 8d "also report"): the UNMODIFIED reference's PyTorch-eager CUDA path --
+    train.py:409-471 around the reference's modules, bf16 autocast + GradScaler, same batch, same mask draws, same
+    box -- with and without use_activation_checkpointing (vision_transformer.py:198-201; the shipped configs set
+    it to true).  None of this repo's kernels are on that path."""
+    import torch
+    H = ref_harness()
+    if H.find_ref_root() is None:
+        return dict(unavailable="reference tree not staged (baseline/_ref)")
+    R = H.import_reference()
+    out = dict(what="reference modules (PyTorch eager: cuDNN conv3d, cuBLASLt, SDPA, ATen), bf16 autocast + GradScaler, "
+                    f"batch {B}, same masks; CUDA events", unit="clips/s", torch=torch.__version__)
+    clips = clips_host.to(dev)
+    for tag, ac in (("activation_checkpointing", True), ("no_checkpointing", False)):
+        rs = None
+        try:
+            torch.manual_seed(0)
+            with torch.device(dev):
+                enc, pred = H.build_models(R, model, crop=CROP, frames=FRAMES, pred_depth=PRED["depth"],
+                                           pred_heads=PRED["heads"], pred_dim=PRED["dim"], num_mask_tokens=6,
+                                           activation_checkpointing=ac, device=dev)
+            rs = H.RefStep(R, enc, pred, dict(OPT, loss_exp=1.0), mixed_precision=True)
+            del enc, pred
+            md = [([m.to(dev) for m in e], [m.to(dev) for m in p]) for e, p in masks_host[:warmup + steps]]
+            for i in range(warmup):
+                rs.step([clips], [md[i][0]], [md[i][1]])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(warmup, warmup + steps):
+                loss = rs.step([clips], [md[i][0]], [md[i][1]])["loss"]
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[tag] = dict(value=B / (ms / 1e3), ms_per_step=ms, steps=steps, warmup=warmup, loss=loss,
+                            peak_mem_gb=torch.cuda.max_memory_allocated(dev) / 2 ** 30)
+            if log:
+                log(f"reference eager CUDA ({tag}): {ms:.1f} ms/step = {B / (ms / 1e3):.2f} clips/s, loss {loss:.4f}")
+        except torch.OutOfMemoryError as ex:
+            out[tag] = dict(value=None, error="out of memory: " + str(ex)[:120])
+        except Exception as ex:  # a baseline failure must not take our numbers down
+            out[tag] = dict(value=None, error=f"{type(ex).__name__}: {str(ex)[:200]}")
+        del rs
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- other configs
+ALL_CONFIGS = {   # BASELINE.json `configs` 1-4: (model, frames, crop, batch per GPU)
+    "C1 ViT-L/16 16x256x256 B=24": ("vit_large", 16, 256, 24),
+    "C2 ViT-H/16 16x256x256 B=24": ("vit_huge", 16, 256, 24),
+    "C3 ViT-g/16 16x256x256 B=24": ("vit_giant_xformers", 16, 256, 24),
+    "C4 ViT-g/16 cooldown 64x384x384 B=6": ("vit_giant_xformers", 64, 384, 6),
+}
+
+
+def quick_config(T, MaskCollator, model, frames, crop, B, dev, peaks, log, warmup=2, steps=3):
+    """Short device-timed run of the same fused step on another BASELINE.json geometry (fresh masks per step)."""
+    import torch
+    ntok = (frames // TUB) * (crop // PATCH) ** 2
+    torch.manual_seed(0)
+    with torch.device(dev):
+        encoder, predictor = T.init_video_model(
+            device=dev, patch_size=PATCH, max_num_frames=frames, tubelet_size=TUB, model_name=model, crop_size=crop,
+            pred_depth=PRED["depth"], pred_num_heads=PRED["heads"], pred_embed_dim=PRED["dim"], uniform_power=True,
+            use_mask_tokens=True, num_mask_tokens=6, zero_init_mask_tokens=True, use_sdpa=True, use_rope=True,
+            use_activation_checkpointing=True)
+    step = T.JepaTrainStep(encoder, predictor, **OPT)
+    coll = MaskCollator(cfgs_mask=MASK_CFG, dataset_fpcs=[frames], crop_size=(crop, crop), patch_size=(PATCH, PATCH),
+                        tubelet_size=TUB)
+    torch.manual_seed(239)
+    masks = make_masks(coll, B, warmup + steps, frames)
+    clips = torch.randn(B, 3, frames, crop, crop, generator=torch.Generator().manual_seed(1000)).to(dev)
+    md = [([m.to(dev) for m in e], [m.to(dev) for m in p]) for e, p in masks]
+    big = max(range(len(masks)), key=lambda i: sum(int(m.numel()) for m in masks[i][0]) * 4
+              + sum(int(m.numel()) for m in masks[i][1]))
+    step.step([clips], [md[big][0]], [md[big][1]])
+    for i in range(warmup):
+        step.step([clips], [md[i][0]], [md[i][1]])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(warmup, warmup + steps):
+        loss, _, _ = step.step([clips], [md[i][0]], [md[i][1]])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    fl = sum(step_flops(model, B, [m.shape[1] for m in masks[i][0]], [m.shape[1] for m in masks[i][1]], ntok)
+             for i in range(warmup, warmup + steps)) / steps
+    tf = fl / (ms / 1e3) / 1e12
+    res = dict(value=B / (ms / 1e3), unit="clips/s", ms_per_step=ms, steps=steps, warmup=warmup + 1, tokens_per_clip=ntok,
+               tflops_per_gpu=tf, frac_of_measured_sustained=tf / peaks["sustained"], loss=float(loss.item()))
+    log(f"all-configs {model} {frames}x{crop}^2 B={B}: {ms:.1f} ms/step = {res['value']:.2f} clips/s, {tf:.0f} TFLOP/s")
+    del step, encoder, predictor, clips, md
+    return res
 
 
 # ---------------------------------------------------------------------------------------------- main
@@ -166,6 +308,8 @@ def main():
     ap.add_argument("--crop", type=int, default=256, help="crop size (256 pretrain, 384 cooldown)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-torch-baseline", action="store_true", help="skip the reference's PyTorch-eager CUDA arm")
+    ap.add_argument("--no-all-configs", action="store_true", help="skip the short runs of the other BASELINE configs")
     ap.add_argument("--profile-ops", action="store_true",
                     help="after the timed region, run one extra step with CUDA events around every C-ABI call and "
                          "print a per-op time table to stderr")
@@ -189,14 +333,13 @@ def main():
     def log(msg):
         print(f"[bench r{rank}] {msg}", file=sys.stderr, flush=True)
 
-    # ------------------------------------------------------------------ reference arm (CPU port)
+    # ------------------------------------------------------------------ reference arm (the reference's CPU path)
     if args.impl == "reference":
         if rank != 0:
             return
-        import torch
-        cores = torch.get_num_threads()
-        times, flops, b = cpu_reference_step_time(args.model, max_seconds=200.0, steps=max(1, args.steps),
-                                                  warmup=min(1, args.warmup), batch=1, log=log)
+        cores = host_threads()
+        times, flops, b, kind = cpu_reference_step_time(args.model, max_seconds=200.0, steps=max(1, args.steps),
+                                                        warmup=min(1, args.warmup), batch=1, log=log)
         ms = 1e3 * sum(times) / len(times)
         val = b / (ms / 1e3)
         line = dict(metric=metric, value=val, unit="clips/s", impl="reference", n_gpus=args.gpus, device="cpu",
@@ -204,9 +347,8 @@ def main():
                     steps_requested=args.steps, warmup=min(1, args.warmup), ms_per_step=ms, higher_is_better=True,
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=config,
                     tokens_per_s=val * NTOK, tflops=sum(flops) / sum(times) / 1e12,
-                    cpu_baseline=dict(value=val, unit="clips/s", cores=cores, kind="port",
-                                      sample=f"{len(times)} step(s) of 1 clip (same model, masks and optimizer; "
-                                             f"reference batch is {args.batch}), oracle/vjepa_oracle.py on torch CPU fp32"),
+                    cpu_baseline=dict(value=val, unit="clips/s", cores=cores, kind=kind,
+                                      sample=cpu_sample_text(kind, len(times), args.batch)),
                     e2e=dict(value=val, unit="clips/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line), flush=True)
         return
@@ -234,11 +376,7 @@ def main():
             crop_size=CROP, pred_depth=PRED["depth"], pred_num_heads=PRED["heads"], pred_embed_dim=PRED["dim"],
             uniform_power=True, use_mask_tokens=True, num_mask_tokens=6, zero_init_mask_tokens=True, use_sdpa=True,
             use_rope=True, use_activation_checkpointing=True)
-    step = T.JepaTrainStep(encoder, predictor, **OPT)
-    if world > 1:                                      # DDP's construction-time parameter broadcast
-        for fs in (step.enc_rt.fs, step.pred_rt.fs, step.tgt_rt.fs):
-            dist.broadcast(fs.p32, 0)
-            fs.refresh_shadows()
+    step = T.JepaTrainStep(encoder, predictor, **OPT)     # world > 1: broadcasts rank 0's parameters (DDP construction)
     log(f"models built in {time.time() - t0:.1f}s; encoder params "
         f"{sum(p.numel() for p in step.encoder.parameters()) / 1e6:.1f}M")
 
@@ -464,18 +602,47 @@ def main():
         for ms, k, n, fl in sorted(rows, reverse=True):
             log(f"  {ms:8.2f} ms {100 * ms / tot:5.1f}%  n={n:4d}  {k}" + (f"  {fl / ms / 1e9:7.1f} TFLOP/s" if fl else ""))
 
+    # ---- the other BASELINE.json configs (C1 ViT-L, C2 ViT-H, C4 ViT-g cooldown 64 x 384^2), short runs of the same
+    #      code path, so those rows are driver-measured too (rank 0, N=1 only)
+    extras = rank == 0 and world == 1
+    all_cfg = None
+    if extras:
+        del step, encoder, predictor
+        step = encoder = predictor = None
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+    if extras and not args.no_all_configs:
+        all_cfg = {}
+        for tag, (mname, fr, cr, bb) in ALL_CONFIGS.items():
+            if (mname, fr, cr, bb) == (args.model, args.frames, args.crop, args.batch):
+                continue
+            try:
+                all_cfg[tag] = quick_config(T, MaskCollator, mname, fr, cr, bb, dev, peaks, log)
+            except Exception as ex:
+                all_cfg[tag] = dict(value=None, error=f"{type(ex).__name__}: {str(ex)[:200]}")
+            gc.collect()
+            torch.cuda.empty_cache()
+
+    # ---- the reference's own PyTorch-eager CUDA path on this GPU (the like-for-like bar; rank 0, N=1 only)
+    tcb = None
+    if extras and not args.no_torch_baseline:
+        tcb = torch_cuda_baseline(args.model, B, masks_host, clips_host, dev, log=log)
+        if tcb.get("activation_checkpointing", {}).get("value"):
+            tcb["speedup_vs_shipped_config"] = clips_s / tcb["activation_checkpointing"]["value"]
+        if tcb.get("no_checkpointing", {}).get("value"):
+            tcb["speedup_vs_no_checkpointing"] = clips_s / tcb["no_checkpointing"]["value"]
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same step on the host cores
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        del step, encoder, predictor
-        torch.cuda.empty_cache()
+    if extras and not args.no_cpu_baseline:
+        cores = host_threads()
         try:
-            times, _, b = cpu_reference_step_time(args.model, max_seconds=120.0, steps=1, warmup=0, batch=1, log=log)
-            cpu = dict(value=b / (sum(times) / len(times)), unit="clips/s", cores=torch.get_num_threads(), kind="port",
-                       sample=f"1 step of 1 clip (same model / masks / optimizer; the GPU arm runs batch {B}), "
-                              f"oracle/vjepa_oracle.py on torch CPU fp32")
+            times, _, b, kind = cpu_reference_step_time(args.model, max_seconds=120.0, steps=1, warmup=0, batch=1, log=log)
+            cpu = dict(value=b / (sum(times) / len(times)), unit="clips/s", cores=cores, kind=kind,
+                       sample=cpu_sample_text(kind, len(times), B))
         except Exception as ex:  # the CPU leg must never take the GPU numbers down with it
-            cpu = dict(value=None, unit="clips/s", cores=torch.get_num_threads(), kind="port", sample=f"failed: {ex}")
+            cpu = dict(value=None, unit="clips/s", cores=cores, kind="port", sample=f"failed: {ex}")
 
     if rank == 0:
         line = dict(metric=metric, value=clips_s, unit="clips/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -484,7 +651,8 @@ def main():
                     tflops_per_gpu=tflops_gpu, frac_of_nominal_2250=tflops_gpu / 2250.0,
                     frac_of_measured_sustained=tflops_gpu / peaks["sustained"],
                     frac_of_measured_burst=tflops_gpu / peaks["burst"], loss=loss_val, clocks=clocks,
-                    gpu_launches=launches, e2e=e2e, roofline=roof, cpu_baseline=cpu)
+                    gpu_launches=launches, e2e=e2e, roofline=roof, cpu_baseline=cpu, torch_cuda_baseline=tcb,
+                    all_configs=all_cfg)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -338,3 +338,138 @@ def test_wrappers_fan_out_protocol():
     out = pred(z, masks, [[torch.tensor(7), torch.tensor(8)], [torch.tensor(9)]], has_cls=False)
     assert out == [[((10, 1), 1, 7, 0, False), ((10, 2), 2, 8, 0, False)], [((20, 3), 3, 9, 1, False)]]
     assert list(dict(enc.named_modules()).keys())[1] == "backbone"             # checkpoint key prefix
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# boundary hygiene: the ctypes struct must follow the header field for field
+# ---------------------------------------------------------------------------------------------------------------
+def _header_struct_fields(name):
+    txt = open(os.path.join(ROOT, "include", "vjepa2_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    body = re.search(r"typedef\s+struct\s*\{(.*?)\}\s*" + name + r"\s*;", txt, flags=re.S).group(1)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        first, *more = [d.strip() for d in decl.split(",")]
+        ctype, fname = first.rsplit(None, 1) if "*" not in first else (first[:first.rindex("*") + 1], first[first.rindex("*") + 1:])
+        ctype = " ".join(ctype.split())
+        fields.append((fname.strip(), ctype))
+        fields += [(m, ctype) for m in more]
+    return fields
+
+
+def test_gemm_args_struct_matches_header_field_for_field():
+    import ctypes
+    from vjepa2_b200 import _cabi
+    want = _header_struct_fields("vj_gemm_args")
+    got = _cabi.GemmArgs._fields_
+    assert [n for n, _ in want] == [n for n, _ in got]
+    for (n, ctype), (_, ct) in zip(want, got):
+        if "*" in ctype:
+            assert ct is ctypes.c_void_p, n
+        elif ctype == "int64_t":
+            assert ct is ctypes.c_int64, n
+        elif ctype == "int32_t":
+            assert ct is ctypes.c_int32, n
+        else:
+            raise AssertionError(f"unexpected C type {ctype!r} for {n}")
+    # INTEGRATION.md shows the same struct to maintainers: every field must appear there, in order
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    pos = [doc.find(f'("{n}"') for n, _ in got]
+    assert all(p >= 0 for p in pos) and pos == sorted(pos), "INTEGRATION.md GemmArgs snippet is out of sync"
+    assert _cabi.ABI_VERSION == 2
+
+
+def test_stale_library_abi_is_rejected(monkeypatch):
+    from vjepa2_b200 import _cabi
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "ABI_VERSION", 999)
+    with pytest.raises(RuntimeError, match="ABI version"):
+        _cabi.load()
+    monkeypatch.setattr(_cabi, "ABI_VERSION", 2)
+    assert _cabi.load() is not None
+
+
+def test_default_checkpoint_prefix_strict_loads_into_ddp_wrapped_reference_layout():
+    """app/vjepa/utils.py:104-118 strict-loads into DDP(MultiSeqWrapper(model)): keys must be module.backbone.*"""
+    import torch.nn as nn
+    from vjepa2_b200 import checkpoint as C
+    enc, _ = _tiny_models()
+
+    class _DDP(nn.Module):                       # the wrapper nesting of train.py:279 without a process group
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+    sd = C._wrapped_state_dict(enc, C.DEFAULT_PREFIX)
+    missing = _DDP(enc).load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    assert set(C.clean_backbone_key(sd)) == set(enc.backbone.state_dict())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# find_unused_parameters semantics across ranks with UNEQUAL fpc-group counts (train.py:280)
+# ---------------------------------------------------------------------------------------------------------------
+_FROZEN_WORKER = r"""
+import os, sys
+import torch
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from vjepa2_b200.train import FrozenTokenSync
+rank = int(os.environ["RANK"])
+dist.init_process_group("gloo", rank=rank, world_size=2)
+# 8 tiles; tokens 0..2 live in tiles 2, 3 and 5 (tile 5 carries the weight-decay bit like a real mask token)
+flags = torch.zeros(8, dtype=torch.uint8)
+flags[[2, 3, 5]] = 1
+sync = FrozenTokenSync(flags, [(2, 1), (3, 1), (5, 1)])
+# rank 0 sees one fpc group (uses token 0), rank 1 sees two (tokens 0 and 1): token 1 is updated on BOTH ranks
+used = sync.update({0} if rank == 0 else {0, 1})
+assert used.tolist() == [1, 1, 0], used
+assert flags.tolist() == [0, 0, 1, 1, 0, 3, 0, 0], flags.tolist()
+# next step: nobody uses token 1 any more, rank 0 alone uses token 2
+sync.update({0, 2} if rank == 0 else {0})
+assert flags.tolist() == [0, 0, 1, 3, 0, 1, 0, 0], flags.tolist()
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+"""
+
+
+def test_frozen_mask_tokens_agree_across_ranks_gloo_world2(tmp_path):
+    script = tmp_path / "frozen_worker.py"
+    script.write_text(_FROZEN_WORKER)
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out.decode()
+        assert b"ok" in out
+
+
+def test_frozen_token_sync_single_process():
+    from vjepa2_b200.train import FrozenTokenSync
+    flags = torch.tensor([1, 1, 1, 0], dtype=torch.uint8)
+    sync = FrozenTokenSync(flags, [(0, 1), (1, 1), (2, 1)])
+    sync.update({0})
+    assert flags.tolist() == [1, 3, 3, 0]
+    assert sync.update({0}) is None                   # unchanged key: nothing to do
+    sync.update({0, 1, 2})
+    assert flags.tolist() == [1, 1, 1, 0]
+
+
+def test_mask_mirror_matches_reference_on_the_full_2048_token_grid():
+    """The shipped mask config on the real 8x16x16 grid, config seed 239: indices bit-exact against the reference's
+    MaskCollator (stored in the full-width golden file)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fullwidth_common as FW
+    from vjepa2_b200.masks import MaskCollator
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "ref_fullwidth.pt"), map_location="cpu")
+    me, mp = FW.draw_masks(MaskCollator)
+    for j in range(2):
+        assert torch.equal(me[j], gold[f"vit_large.masks_enc.{j}"].long())
+        assert torch.equal(mp[j], gold[f"vit_large.masks_pred.{j}"].long())
+        assert me[j].dtype == torch.int64 and int(me[j].max()) < 2048

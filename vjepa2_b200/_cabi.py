@@ -12,6 +12,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvjepa2_b200.so")
 
+ABI_VERSION = 2          # vj_abi_version() of the library this binding (struct layouts, prototypes) was written for
 VJ_BF16, VJ_F32 = 0, 1
 EPI_BIAS, EPI_GELU, EPI_DGELU, EPI_RESIDUAL = 1, 2, 4, 8
 EPI_OUT_F32, EPI_RES_F32, EPI_ROUND_BF16, EPI_AUX_OUT, EPI_ROPE = 16, 32, 64, 128, 256
@@ -86,6 +87,10 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the symbol is missing
         fn.restype = restype
         fn.argtypes = argtypes
+    got = lib.vj_abi_version()
+    if got != ABI_VERSION:               # a stale .so with another vj_gemm_args layout must not load silently
+        raise RuntimeError(f"vjepa2_b200: {LIB_PATH} has ABI version {got}, this binding expects {ABI_VERSION}; "
+                           "rebuild it (`make -C vjepa2_b200/csrc`)")
     _lib = lib
     return lib
 

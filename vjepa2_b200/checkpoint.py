@@ -109,6 +109,9 @@ def restore_opt_state(groups, opt_sd, moments):
     return step
 
 
+DEFAULT_PREFIX = "module.backbone."
+
+
 def _wrapped_state_dict(m, prefix):
     sd = _unwrap(m).state_dict()
     return {prefix + k: v.detach().cpu().clone() for k, v in sd.items()}
@@ -119,9 +122,11 @@ def _moments_of(step, skip_frozen=True):
         for rt in (step.enc_rt, step.pred_rt):
             fs = rt.fs
             if id(t) in fs.index:
-                if skip_frozen and fs.is_frozen(t):
+                m, v = fs._view(fs.exp_avg, t), fs._view(fs.exp_avg_sq, t)
+                # torch keeps no state for a parameter that never received a gradient (unused mask tokens)
+                if skip_frozen and fs.is_frozen(t) and not bool(v.any()):
                     return None
-                return fs._view(fs.exp_avg, t), fs._view(fs.exp_avg_sq, t)
+                return m, v
         raise KeyError("parameter is not owned by this train step")
     return moments
 
@@ -137,17 +142,19 @@ def scaler_state_dict(step):
 def save_checkpoint(path, step, epoch, *, loss=0.0, batch_size=None, world_size=None, lr=None, encoder=None,
                     predictor=None, target_encoder=None):
     """train.py:315-333.  `step` is the JepaTrainStep; pass the (possibly wrapped) modules to reproduce their key
-    prefixes, otherwise the reference's single-process prefix `backbone.` is written."""
+    prefixes, otherwise `module.backbone.` is written: app/vjepa/train.py always wraps the three models in
+    DistributedDataParallel(MultiSeqWrapper(...)) (train.py:279-281) and its load_checkpoint does a strict
+    load_state_dict on those (app/vjepa/utils.py:104-118), so that is the only prefix the reference loop accepts."""
     groups = opt_param_groups(step.encoder, step.predictor)
     cur_lr, cur_wd = step.last_lr_wd
     save_dict = {
-        "encoder": _wrapped_state_dict(step.encoder, _prefix_of(encoder) if encoder is not None else "backbone."),
+        "encoder": _wrapped_state_dict(step.encoder, _prefix_of(encoder) if encoder is not None else DEFAULT_PREFIX),
         "predictor": _wrapped_state_dict(step.predictor,
-                                         _prefix_of(predictor) if predictor is not None else "backbone."),
+                                         _prefix_of(predictor) if predictor is not None else DEFAULT_PREFIX),
         "opt": build_opt_state_dict(groups, _moments_of(step), step.optimizer_steps(), cur_lr, cur_wd, step.betas, step.eps),
         "scaler": scaler_state_dict(step),
         "target_encoder": _wrapped_state_dict(step.target_encoder,
-                                              _prefix_of(target_encoder) if target_encoder is not None else "backbone."),
+                                              _prefix_of(target_encoder) if target_encoder is not None else DEFAULT_PREFIX),
         "epoch": epoch,
         "loss": loss,
         "batch_size": batch_size,

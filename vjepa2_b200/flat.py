@@ -105,7 +105,8 @@ class FlatStore:
             self.exp_avg_sq = torch.zeros(self.total, dtype=torch.float32, device=self.device)
 
     def is_frozen(self, p) -> bool:
-        return bool(self.flags_host[self.offsets[self.index[id(p)]] // TILE] & FLAG_FROZEN)
+        """Current state of the device flag byte (train.FrozenTokenSync updates it on the device); one small D2H read."""
+        return bool(int(self.flags[self.offsets[self.index[id(p)]] // TILE].item()) & FLAG_FROZEN)
 
     def set_frozen(self, params, frozen=True):
         """Mark parameters that never get a gradient (e.g. unused predictor mask tokens, a1/a17)."""
@@ -117,4 +118,4 @@ class FlatStore:
                 self.flags_host[sl] |= FLAG_FROZEN
             else:
                 self.flags_host[sl] &= ~FLAG_FROZEN & 0xFF
-        self.flags = self.flags_host.to(self.device)
+        self.flags.copy_(self.flags_host)          # in place: kernels / FrozenTokenSync keep pointing at this tensor

@@ -52,13 +52,20 @@ def init_video_model(device, patch_size=16, max_num_frames=16, tubelet_size=2, m
     return encoder, predictor
 
 
+def _world_of(group):
+    """Ranks in `group` (None = the default group); group=False opts out of data parallelism inside a distributed job."""
+    if group is False or not (dist.is_available() and dist.is_initialized()):
+        return 1
+    return dist.get_world_size(group)
+
+
 class GradBucketer:
     """Bucketed, asynchronous all-reduce over ranges of a flat gradient buffer (device agnostic, so the
     N>1 logic is testable on CPU with gloo).  Ranges are reduced in the order they are submitted."""
 
     def __init__(self, group=None):
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.world = _world_of(group)
         self._works = []
 
     def submit(self, flat, start, end):
@@ -70,6 +77,47 @@ class GradBucketer:
         for w in self._works:
             w.wait()
         self._works = []
+
+
+class FrozenTokenSync:
+    """Which predictor mask tokens get an optimizer update this step (device agnostic, so testable with gloo).
+
+    The reference wraps the predictor in DDP(find_unused_parameters=True) (train.py:280): a mask token no rank used
+    keeps grad None and torch's AdamW skips it (no update, no weight decay), while a token ANY rank used receives the
+    all-reduced gradient and is updated on EVERY rank.  With several dataset_fpcs, ranks may see different fpc
+    groups in one step, so the used set is reduced over the ranks (MAX, on the device -- no host sync) and written into
+    the per-tile flag bytes the AdamW kernel reads."""
+
+    def __init__(self, flags, token_tiles, group=None):
+        """flags: uint8 [tiles] (FlatStore.flags); token_tiles: list over tokens of (first tile, n tiles)."""
+        self.flags, self.group = flags, group
+        self.world = _world_of(group)
+        dev = flags.device
+        tiles = [t for t0, n in token_tiles for t in range(t0, t0 + n)]
+        owner = [k for k, (t0, n) in enumerate(token_tiles) for _ in range(n)]
+        self.n_tokens = len(token_tiles)
+        self.tiles = torch.tensor(tiles, dtype=torch.int64, device=dev)
+        self.owner = torch.tensor(owner, dtype=torch.int64, device=dev)
+        self.base = (flags[self.tiles] & ~2 & 0xFF).clone()          # the non-frozen bits (weight-decay bit) of those tiles
+        self._key = None
+
+    def update(self, used_local):
+        """used_local: set of token indices this rank's step uses.  Returns the device tensor of globally used tokens
+        (world > 1) or None when nothing had to change."""
+        key = tuple(sorted(used_local))
+        if self.world == 1 and key == self._key:
+            return None
+        self._key = key
+        host = torch.zeros(self.n_tokens, dtype=torch.int32)
+        host[list(key)] = 1
+        if self.flags.is_cuda:
+            host = host.pin_memory()
+        used = host.to(self.flags.device, non_blocking=True)
+        if self.world > 1:
+            dist.all_reduce(used, op=dist.ReduceOp.MAX, group=self.group)
+        frozen_bit = ((1 - used[self.owner]) * 2).to(torch.uint8)
+        self.flags[self.tiles] = self.base | frozen_bit
+        return used
 
 
 class HostFeeder:
@@ -89,6 +137,9 @@ class HostFeeder:
         self._free = [None, None]  # event: compute finished reading this slot
 
     def prefetch(self, clips, masks_enc, masks_pred):
+        if len(self._q) >= 2:
+            raise RuntimeError("vjepa2_b200: HostFeeder is double buffered -- at most two prefetched steps may be "
+                               "outstanding (call get() first)")
         slot = self._slot
         self._slot ^= 1
         st = self.stream
@@ -136,9 +187,15 @@ class JepaTrainStep:
     def __init__(self, encoder, predictor, target_encoder=None, *, ipe=300, epochs=800, ipe_scale=1.25, warmup=40,
                  start_lr=1e-4, lr=5.25e-4, final_lr=5.25e-4, weight_decay=0.04, final_weight_decay=0.04,
                  ema=(0.99925, 0.99925), betas=(0.9, 0.999), eps=1e-8, loss_exp=1.0, mixed_precision=True,
-                 process_group=None, overlap_target=None):
+                 loss_scaling=True, process_group=None, overlap_target=None):
         if loss_exp != 1.0:
             raise NotImplementedError("vjepa2_b200: loss_exp must be 1.0 (L1), as in every shipped config")
+        if not mixed_precision:
+            # train.py:96-103: mixed_precision=False means dtype=float32 and no autocast.  The kernels compute with bf16
+            # tensor-core operands only, so a float32 config must not silently train in bf16.
+            raise NotImplementedError("vjepa2_b200: mixed_precision=False (fp32 training) is out of scope; every shipped "
+                                      "pre-training config uses dtype bfloat16.  For bf16 compute without GradScaler "
+                                      "loss scaling pass loss_scaling=False.")
         self.encoder = _unwrap(encoder)
         self.predictor = _unwrap(predictor)
         if target_encoder is None:
@@ -175,15 +232,23 @@ class JepaTrainStep:
             raise RuntimeError("target encoder layout differs from the encoder's")
         f32 = torch.float32
         self.loss_accum = torch.zeros(1, dtype=f32, device=dev)
-        init_scale = 65536.0 if mixed_precision else 1.0            # torch.cuda.amp.GradScaler() default
+        # loss_scaling=False (not a reference option; tests): bf16 compute, scale 1, and -- like the reference's plain
+        # optimizer.step() branch (train.py:452) -- the optimizer never skips a step
+        init_scale = 65536.0 if loss_scaling else 1.0               # torch.cuda.amp.GradScaler() default
         self.mixed_precision = mixed_precision
+        self.loss_scaling = bool(loss_scaling)
         self.scale = torch.full((1,), init_scale, dtype=f32, device=dev)
         self.inv_scale = torch.full((1,), 1.0 / (init_scale * self.world), dtype=f32, device=dev)
         self.found_inf = torch.zeros(1, dtype=f32, device=dev)
         self.growth_tracker = torch.zeros(1, dtype=torch.int32, device=dev)
         self.skipped = torch.zeros(1, dtype=torch.int32, device=dev)
         self.bias_c = torch.ones(2, dtype=f32, device=dev)
-        self._frozen_key = None
+        pfs = self.pred_rt.fs
+        self.frozen_sync = FrozenTokenSync(
+            pfs.flags, [(pfs.offsets[pfs.index[id(t)]] // 1024, (t.numel() + 1023) // 1024) for t in self.predictor.mask_tokens],
+            process_group)
+        if self.world > 1:
+            self.broadcast_state()                                  # DDP broadcasts rank 0's parameters at construction
         self.ws = Arena(dev)                                        # activations / temporaries (no allocator in-step)
         # Optional: the target-encoder forward (train.py:414-418) does not depend on the context pass, so it can run
         # on a second stream with its own arena, the prologue / tail of every persistent kernel of one stream filled
@@ -208,14 +273,25 @@ class JepaTrainStep:
 
     # ------------------------------------------------------------------------------------------
     def _set_frozen_mask_tokens(self, n_groups):
-        toks = list(self.predictor.mask_tokens)
-        used = {i % len(toks) for i in range(n_groups)}
-        key = tuple(sorted(used))
-        if key != self._frozen_key:
-            fs = self.pred_rt.fs
-            fs.set_frozen(toks, False)
-            fs.set_frozen([t for k, t in enumerate(toks) if k not in used], True)
-            self._frozen_key = key
+        """Group i uses mask token i % num_mask_tokens (wrappers.py:40, predictor.py:195); tokens no rank uses in this
+        step are skipped by the optimizer (see FrozenTokenSync)."""
+        n = len(self.predictor.mask_tokens)
+        self.frozen_sync.update({i % n for i in range(n_groups)})
+
+    def broadcast_state(self, src=0):
+        """DDP construction semantics (train.py:279-281): every rank starts from rank `src`'s parameters (encoder,
+        predictor, target encoder) -- and, after a checkpoint load, its optimizer state."""
+        if self.world == 1:
+            return
+        g = self.bucketer.group
+        for fs in (self.enc_rt.fs, self.pred_rt.fs, self.tgt_rt.fs):
+            dist.broadcast(fs.p32, src, group=g)
+            if fs.exp_avg is not None:
+                dist.broadcast(fs.exp_avg, src, group=g)
+                dist.broadcast(fs.exp_avg_sq, src, group=g)
+            fs.refresh_shadows()
+        for t in (self.scale, self.inv_scale, self.growth_tracker, self.skipped):
+            dist.broadcast(t, src, group=g)
 
     # ------------------------------------------------------------------------------------------ resume support
     def reload_weights(self):
@@ -224,6 +300,7 @@ class JepaTrainStep:
             if not rt.fs.valid():
                 raise RuntimeError("vjepa2_b200: parameters were re-allocated (e.g. .to()); build a new JepaTrainStep")
             rt.fs.refresh_shadows()
+        self.broadcast_state()
 
     def optimizer_steps(self):
         """torch's optimizer step count: step() calls minus the ones GradScaler skipped (one 4-byte D2H read)."""
@@ -277,6 +354,9 @@ class JepaTrainStep:
         enc_rt, pred_rt, tgt_rt = self.enc_rt, self.pred_rt, self.tgt_rt
         efs, pfs, tfs = enc_rt.fs, pred_rt.fs, tgt_rt.fs
         enc = self.encoder
+        for fs in (efs, pfs, tfs):
+            if fs._versions is None:                              # load_state_dict since the last step: masters changed
+                fs.refresh_shadows()
         self._set_frozen_mask_tokens(len(clips))
         efs.g32.zero_()                                           # optimizer.zero_grad() (train.py:454)
         pfs.g32.zero_()
@@ -357,11 +437,12 @@ class JepaTrainStep:
         ops.grad_check(efs.g32, self.found_inf, st)
         ops.grad_check(pfs.g32, self.found_inf, st)
         b1, b2 = self.betas
-        ops.adam_prepare(self.bias_c, self.skipped, self.found_inf, self.applied_steps, b1, b2, st)
+        skip_flag = self.found_inf if self.loss_scaling else None       # no GradScaler: never skip (train.py:452)
+        ops.adam_prepare(self.bias_c, self.skipped, skip_flag, self.applied_steps, b1, b2, st)
         for fs in (efs, pfs):
             ops.adamw_step(fs.p32, fs.g32, fs.exp_avg, fs.exp_avg_sq, fs.p16, fs.flags, new_lr, b1, b2, self.eps,
-                           new_wd, self.applied_steps, self.inv_scale, self.found_inf, st, dev_bias=self.bias_c)
-        if self.mixed_precision:
+                           new_wd, self.applied_steps, self.inv_scale, skip_flag, st, dev_bias=self.bias_c)
+        if self.loss_scaling:
             ops.scaler_update(self.scale, self.inv_scale, self.growth_tracker, self.found_inf, float(self.world), st=st)
         else:
             self.found_inf.zero_()

@@ -52,7 +52,9 @@ class _FlatModule(nn.Module):
             fs = FlatStore(self, p0.device)
             self._fs = fs
             self._rt = None
-        elif not self._manual_shadows and (fs._versions is None or fs.shadows_stale()):
+        elif fs._versions is None or (not self._manual_shadows and fs.shadows_stale()):
+            # _versions is None: load_state_dict / load_pretrained rewrote the fp32 masters (post hook), also while a
+            # JepaTrainStep owns the shadows; otherwise (drop-in use) in-place edits are detected by version counters
             fs.refresh_shadows()
         return fs
 
@@ -209,7 +211,35 @@ def vit_giant_xformers_rope(patch_size=16, **kwargs):
     return _vit(1408, 40, 22, 48 / 11, patch_size, use_rope=True, **kwargs)
 
 
+def vit_huge_rope(patch_size=16, **kwargs):
+    return _vit(1280, 32, 16, 4, patch_size, use_rope=True, **kwargs)
+
+
+def vit_gigantic_xformers(patch_size=16, **kwargs):
+    # the reference passes `mpl_ratio=64/13` (vision_transformer.py:470, a typo swallowed by **kwargs), so its
+    # mlp_ratio stays at the default 4.0 -- mirrored, so that the parameter shapes agree
+    return _vit(1664, 48, 26, 4.0, patch_size, **kwargs)
+
+
+# The remaining names of the reference's lookup seam have head dims no attention kernel here covers (the shipped
+# pre-training configs use none of them); they exist so that the lookup fails with a precise message, not a KeyError.
+def vit_giant(patch_size=16, **kwargs):
+    return _vit(1408, 40, 16, 48 / 11, patch_size, **kwargs)            # head_dim 88 -> NotImplementedError
+
+
+def vit_giant_rope(patch_size=16, **kwargs):
+    return _vit(1408, 40, 16, 48 / 11, patch_size, use_rope=True, **kwargs)
+
+
+def vit_gigantic(patch_size=16, **kwargs):
+    return _vit(1664, 48, 16, 4.0, patch_size, **kwargs)                # head_dim 104 -> NotImplementedError
+
+
+def vit_synthetic(patch_size=16, **kwargs):
+    return _vit(1, 1, 1, 4, patch_size, **kwargs)                       # head_dim 1 -> NotImplementedError
+
+
 VIT_EMBED_DIMS = {
-    "vit_tiny": 192, "vit_small": 384, "vit_base": 768, "vit_large": 1024, "vit_huge": 1280,
-    "vit_giant_xformers": 1408,
+    "vit_synthetic": 1, "vit_tiny": 192, "vit_small": 384, "vit_base": 768, "vit_large": 1024, "vit_huge": 1280,
+    "vit_giant": 1408, "vit_giant_xformers": 1408, "vit_gigantic": 1664, "vit_gigantic_xformers": 1664,
 }
