@@ -534,7 +534,8 @@ def test_every_reference_factory_name_resolves(dev):
     for n in names:
         assert callable(V.__dict__[n]), n
     for n in ("vit_giant", "vit_giant_rope", "vit_gigantic", "vit_synthetic"):
+        kw = {} if n.endswith("_rope") else {"use_rope": True}      # the *_rope factories pass use_rope themselves
         with pytest.raises(NotImplementedError):
-            V.__dict__[n](img_size=32, num_frames=4, use_rope=True)
+            V.__dict__[n](img_size=32, num_frames=4, **kw)
     m = V.vit_tiny(img_size=32, num_frames=4, use_rope=True)
     assert m.embed_dim == 192 and V.VIT_EMBED_DIMS["vit_gigantic"] == 1664
