@@ -461,6 +461,22 @@ def main():
     flops_timed = sum(step_flops(args.model, B, [m.shape[1] for m in masks_host[i][0]],
                                  [m.shape[1] for m in masks_host[i][1]])
                       for i in range(args.warmup, args.warmup + args.steps))
+    # data-parallel imbalance: every rank draws its own masks (reference: one collator per rank), K_enc / K_pred are
+    # truncated to the rank-local batch minimum, and the step synchronises at the gradient all-reduce -- so a step costs
+    # the SLOWEST rank's work.  ratio = sum_steps max_rank(flops) / sum_steps mean_rank(flops) bounds the weak-scaling
+    # efficiency any implementation of the reference's algorithm can reach on these draws (1 / ratio).
+    imbalance = None
+    if world > 1:
+        mine = torch.tensor([step_flops(args.model, B, [m.shape[1] for m in masks_host[i][0]],
+                                        [m.shape[1] for m in masks_host[i][1]])
+                             for i in range(args.warmup, args.warmup + args.steps)], dtype=torch.float64, device=dev)
+        allf = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allf, mine)
+        allf = torch.stack(allf)
+        ratio = float(allf.max(dim=0).values.sum() / allf.mean(dim=0).sum())
+        imbalance = dict(max_over_mean_step_flops=ratio, efficiency_bound=1.0 / ratio,
+                         note="per-rank mask draws (K truncated to the rank-local batch minimum) make per-step work differ "
+                              "across ranks; the all-reduce makes every step wait for the slowest rank")
     clips_s = world * B * args.steps / (ms_total / 1e3)
     tflops_gpu = flops_timed / (ms_total / 1e3) / 1e12          # per GPU (each rank does B clips)
 
@@ -651,7 +667,7 @@ def main():
                     tflops_per_gpu=tflops_gpu, frac_of_nominal_2250=tflops_gpu / 2250.0,
                     frac_of_measured_sustained=tflops_gpu / peaks["sustained"],
                     frac_of_measured_burst=tflops_gpu / peaks["burst"], loss=loss_val, clocks=clocks,
-                    gpu_launches=launches, e2e=e2e, roofline=roof, cpu_baseline=cpu, torch_cuda_baseline=tcb,
+                    gpu_launches=launches, dp_imbalance=imbalance, e2e=e2e, roofline=roof, cpu_baseline=cpu, torch_cuda_baseline=tcb,
                     all_configs=all_cfg)
         print(json.dumps(line), flush=True)
     if world > 1:

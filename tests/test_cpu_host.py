@@ -473,3 +473,22 @@ def test_mask_mirror_matches_reference_on_the_full_2048_token_grid():
         assert torch.equal(me[j], gold[f"vit_large.masks_enc.{j}"].long())
         assert torch.equal(mp[j], gold[f"vit_large.masks_pred.{j}"].long())
         assert me[j].dtype == torch.int64 and int(me[j].max()) < 2048
+
+
+def test_bucket_hook_merges_adjacent_block_ranges_and_covers_everything_once():
+    from vjepa2_b200.train import make_bucket_hook
+    depth, blk = 6, 1000
+    ranges = {-1: (0, 300)}
+    ranges.update({i: (300 + i * blk, 300 + (i + 1) * blk) for i in range(depth)})
+    ranges[depth] = (300 + depth * blk, 300 + depth * blk + 50)
+    order = [depth] + list(range(depth - 1, -1, -1)) + [-1]       # engine.encoder_backward's completion order
+    for bucket_elems, want_max in ((0, len(order)), (2500, 4), (10 ** 9, 1)):
+        got = []
+        hook = make_bucket_hook(ranges, bucket_elems * 4, lambda lo, hi: got.append((lo, hi)))
+        for k in order:
+            hook(k)
+        assert len(got) <= want_max
+        covered = sorted(got)
+        assert covered[0][0] == 0 and covered[-1][1] == ranges[depth][1]
+        assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))       # contiguous, no overlap, no gap
+    assert len(got) == 1

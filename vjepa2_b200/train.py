@@ -79,6 +79,25 @@ class GradBucketer:
         self._works = []
 
 
+def make_bucket_hook(ranges, bucket_bytes, submit, last_key=-1):
+    """on_block_done callback of the last backward pass.  `ranges[key]` = [lo, hi) of the flat fp32 gradient range that
+    is complete once engine.encoder_backward reports `key` (final norm, blocks depth-1 .. 0, then patch embed = last_key):
+    the encoder finishes from the END of the flat store towards its start, so consecutive finished ranges are adjacent and
+    are merged until a bucket holds at least bucket_bytes, then handed to submit(lo, hi)."""
+    state = {"lo": None, "hi": None}
+
+    def hook(key):
+        lo, hi = ranges[key]
+        if state["hi"] is None:
+            state["lo"], state["hi"] = lo, hi
+        else:
+            state["lo"], state["hi"] = min(state["lo"], lo), max(state["hi"], hi)
+        if key == last_key or (state["hi"] - state["lo"]) * 4 >= bucket_bytes:
+            submit(state["lo"], state["hi"])
+            state["lo"] = state["hi"] = None
+    return hook
+
+
 class FrozenTokenSync:
     """Which predictor mask tokens get an optimizer update this step (device agnostic, so testable with gloo).
 
@@ -187,7 +206,7 @@ class JepaTrainStep:
     def __init__(self, encoder, predictor, target_encoder=None, *, ipe=300, epochs=800, ipe_scale=1.25, warmup=40,
                  start_lr=1e-4, lr=5.25e-4, final_lr=5.25e-4, weight_decay=0.04, final_weight_decay=0.04,
                  ema=(0.99925, 0.99925), betas=(0.9, 0.999), eps=1e-8, loss_exp=1.0, mixed_precision=True,
-                 loss_scaling=True, process_group=None, overlap_target=None):
+                 loss_scaling=True, process_group=None, overlap_target=None, grad_sync=None, bucket_mb=None):
         if loss_exp != 1.0:
             raise NotImplementedError("vjepa2_b200: loss_exp must be 1.0 (L1), as in every shipped config")
         if not mixed_precision:
@@ -212,6 +231,13 @@ class JepaTrainStep:
         self.momentum = momentum_schedule(ema, ipe, epochs, ipe_scale)
         self.bucketer = GradBucketer(process_group)
         self.world = self.bucketer.world
+        import os
+        # gradient all-reduce schedule (train.py:279-281): "overlap" = per-bucket async all-reduce launched from the last
+        # backward pass; "end" = one all-reduce per model after backward (no SM contention with the persistent kernels)
+        self.grad_sync = grad_sync or os.environ.get("VJ_DDP_SYNC", "overlap")
+        if self.grad_sync not in ("overlap", "end"):
+            raise ValueError("grad_sync must be 'overlap' or 'end'")
+        self.bucket_bytes = int(bucket_mb if bucket_mb is not None else os.environ.get("VJ_DDP_BUCKET_MB", "0")) << 20
         # optimizer step() calls so far; the steps GradScaler skipped (found_inf) are counted on the device
         # (self.skipped), so the bias corrections use torch's count, applied_steps - skipped, without a host sync
         self.applied_steps = 0
@@ -272,6 +298,10 @@ class JepaTrainStep:
         self._enc_ranges[-1] = fs.range_of(self.enc_rt.pe_params)
 
     # ------------------------------------------------------------------------------------------
+    def _bucket_hook(self, efs):
+        return make_bucket_hook(self._enc_ranges, self.bucket_bytes,
+                                lambda lo, hi: self.bucketer.submit(efs.g32, lo, hi))
+
     def _set_frozen_mask_tokens(self, n_groups):
         """Group i uses mask token i % num_mask_tokens (wrappers.py:40, predictor.py:195); tokens no rank uses in this
         step are skipped by the optimizer (see FrozenTokenSync)."""
@@ -423,14 +453,16 @@ class JepaTrainStep:
                 # ---- backward
                 dzenc = engine.predictor_backward(pred_rt, sv_p, dz, pfs.g32, ws=ws)
                 del sv_p
-                if last and self.world > 1:
+                hook = None
+                if last and self.world > 1 and self.grad_sync == "overlap":
                     self.bucketer.submit(pfs.g32, 0, pfs.total)
-                    hook = lambda b, efs=efs: self.bucketer.submit(efs.g32, *self._enc_ranges[b])  # noqa: E731
-                else:
-                    hook = None
+                    hook = self._bucket_hook(efs)
                 engine.encoder_backward(enc_rt, sv_e, dzenc, efs.g32, ws=ws, on_block_done=hook)
                 del sv_e, zs, preds, dz, dzenc
                 ws._act.reset()                                   # this pass's activations are dead
+        if self.world > 1 and self.grad_sync == "end":                # one collective per model after backward
+            self.bucketer.submit(pfs.g32, 0, pfs.total)
+            self.bucketer.submit(efs.g32, 0, efs.total)
         self.bucketer.wait()
 
         # ---- unscale + inf check + AdamW (train.py:446-451; app/vjepa/utils.py:239), flat kernels
