@@ -206,6 +206,34 @@ int vj_scaler_update(float* scale, float* inv_scale, int32_t* growth_tracker, fl
 /* fp32 -> bf16 flat cast (weight shadow refresh) */
 int vj_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------ device-side MaskCollator
+ * src/masks/multiseq_multiblock3d.py:129-239 (_MaskGenerator.__call__) as one kernel, RNG-call-identical to the
+ * reference: the block extent comes from mt19937(seed) (seed = the generator's draw counter, :170-178), the block
+ * corners from the GLOBAL torch CPU generator, whose MT19937 state lives on the device in rng_state
+ * (VJ_MASK_RNG_WORDS uint32: state[624], left, next -- the fields of torch.get_rng_state()) and is advanced in place.
+ * masks_enc / masks_pred: device buffers of capacity B*frames*rows*cols int64, written DENSE as [B][K_enc] and
+ * [B][K_pred] (sorted token ids, truncated to the batch minimum / max_keep, :199-213; complement variants :214-231).
+ * counts[0..1] = K_enc, K_pred (device ints; the host reads them one step ahead of the step that uses the masks).
+ * scratch: vj_mask_collate_scratch bytes.  inv_block (:236-239) is a swap of the two outputs on the caller's side. */
+#define VJ_MASK_RNG_WORDS 626
+typedef struct {
+  int32_t frames, rows, cols;      /* token grid: duration, height, width (:104-105) */
+  int32_t num_blocks;              /* npred */
+  int32_t context_frames;          /* max_context_duration (:116-118) */
+  int32_t max_keep;                /* <= 0: none */
+  int32_t full_complement, pred_full_complement;
+  double temporal_lo, temporal_hi; /* temporal_pred_mask_scale */
+  double spatial_lo, spatial_hi;   /* spatial_pred_mask_scale */
+  double aspect_lo, aspect_hi;     /* aspect_ratio */
+} vj_mask_spec;
+size_t vj_mask_collate_scratch(const vj_mask_spec* spec, int64_t B);
+int vj_mask_collate(uint32_t* rng_state, const vj_mask_spec* spec, uint32_t seed, int64_t B, int64_t* masks_enc,
+                    int64_t* masks_pred, int32_t* counts, void* scratch, void* stream);
+
+/* Tuning / test switch of vj_gemm's kernel choice (same as the VJ_GEMM_2CTA environment variable): 0 = 1-CTA kernels
+ * only, 1 = automatic (CTA-pair kernel for M >= 1024), 2 = CTA-pair kernel for every shape.  Returns the old mode. */
+int vj_gemm_set_pair_mode(int mode);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), f"{s} declared in include/vjepa2_b200.h but not exported"
         assert s in _cabi.SIGNATURES, f"{s} has no ctypes prototype"
     assert set(_cabi.SIGNATURES) == set(syms)
-    assert lib.vj_abi_version() == 2
+    assert lib.vj_abi_version() == 3
 
 
 def test_product_path_has_no_cpu_fallback():
@@ -379,7 +379,7 @@ def test_gemm_args_struct_matches_header_field_for_field():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     pos = [doc.find(f'("{n}"') for n, _ in got]
     assert all(p >= 0 for p in pos) and pos == sorted(pos), "INTEGRATION.md GemmArgs snippet is out of sync"
-    assert _cabi.ABI_VERSION == 2
+    assert _cabi.ABI_VERSION == 3
 
 
 def test_stale_library_abi_is_rejected(monkeypatch):
@@ -388,7 +388,7 @@ def test_stale_library_abi_is_rejected(monkeypatch):
     monkeypatch.setattr(_cabi, "ABI_VERSION", 999)
     with pytest.raises(RuntimeError, match="ABI version"):
         _cabi.load()
-    monkeypatch.setattr(_cabi, "ABI_VERSION", 2)
+    monkeypatch.setattr(_cabi, "ABI_VERSION", 3)
     assert _cabi.load() is not None
 
 

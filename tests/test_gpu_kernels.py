@@ -469,3 +469,87 @@ def test_flat_optimizer_kernels(dev):
     assert relerr(t, 0.99 * t0 + 0.01 * p) < 1e-6 and torch.equal(sh, t.bfloat16())
     ops.ema_update(t, p, None, 0.0)
     assert torch.equal(t, p)
+
+
+# ----------------------------------------------------------------------------------------------- device-side MaskCollator
+def test_device_mask_collator_bit_exact_against_reference_goldens(dev, golden):
+    """csrc/maskgen.cu against index tensors the REAL reference produced (multiseq_multiblock3d.py:172-239): same global
+    torch RNG state in, same draw counters -> the same int64 indices, on both pre-training geometries."""
+    import vjepa_oracle as O
+    from vjepa2_b200.masks import DeviceMaskCollator
+    cfgs = [dict(m) for m in O.DEFAULT_MASK_CFG]
+    coll = DeviceMaskCollator(cfgs_mask=cfgs, dataset_fpcs=[16], crop_size=(256, 256), patch_size=(16, 16),
+                              tubelet_size=2, device=dev)
+    torch.manual_seed(239)
+    coll.seed_from_torch()
+    for it in range(3):
+        enc, pred = coll.draw(16, 6)
+        for j in range(2):
+            assert enc[j].is_cuda and enc[j].dtype == torch.int64 and enc[j].is_contiguous()
+            assert torch.equal(enc[j].cpu(), golden[f"mask.it{it}.enc{j}"])
+            assert torch.equal(pred[j].cpu(), golden[f"mask.it{it}.pred{j}"])
+    coll2 = DeviceMaskCollator(cfgs_mask=cfgs, dataset_fpcs=[64], crop_size=(384, 384), patch_size=(16, 16),
+                               tubelet_size=2, device=dev)
+    torch.manual_seed(7)
+    coll2.seed_from_torch()
+    enc, pred = coll2.draw(64, 2)                     # 32 x 24 x 24 = 18 432-token grid
+    for j in range(2):
+        assert torch.equal(enc[j].cpu(), golden[f"mask384.enc{j}"]) and torch.equal(pred[j].cpu(), golden[f"mask384.pred{j}"])
+
+
+@pytest.mark.parametrize("variant", ["shipped", "ranges", "max_keep", "full_complement", "pred_full_complement",
+                                     "inv_block", "temporal_keep", "crowded"])
+def test_device_mask_collator_follows_the_host_stream(dev, variant):
+    """Many consecutive draws against the (golden-pinned) host sampler: identical indices for every option of the YAML
+    mask block, an identical global-generator state afterwards (so host and device samplers can be swapped mid-run),
+    including the redraw of samples whose context came out empty ("crowded")."""
+    from vjepa2_b200.masks import DeviceMaskCollator, MaskCollator
+    base = dict(aspect_ratio=(0.75, 1.5), num_blocks=8, spatial_scale=(0.15, 0.15), temporal_scale=(1.0, 1.0))
+    cfgs = {
+        "shipped": [base, dict(base, num_blocks=2, spatial_scale=(0.7, 0.7))],
+        "ranges": [dict(aspect_ratio=(0.3, 3.0), num_blocks=3, spatial_scale=(0.2, 0.8), temporal_scale=(0.3, 1.0))],
+        "max_keep": [dict(base, max_keep=300)],
+        "full_complement": [dict(base, max_keep=500, full_complement=True)],
+        "pred_full_complement": [dict(base, num_blocks=2, spatial_scale=(0.3, 0.5), pred_full_complement=True)],
+        "inv_block": [dict(base, num_blocks=1, spatial_scale=(0.3, 0.4), inv_block=True)],
+        "temporal_keep": [dict(base, max_temporal_keep=0.5, temporal_scale=(0.5, 1.0))],
+        "crowded": [dict(aspect_ratio=(0.9, 1.1), num_blocks=6, spatial_scale=(0.55, 0.65), temporal_scale=(1.0, 1.0))],
+    }[variant]
+    geo = dict(dataset_fpcs=[8], crop_size=(64, 64)) if variant == "crowded" else dict(dataset_fpcs=[16], crop_size=(256, 256))
+    fpc = geo["dataset_fpcs"][0]
+    host = MaskCollator(cfgs_mask=cfgs, patch_size=(16, 16), tubelet_size=2, **geo)
+    devc = DeviceMaskCollator(cfgs_mask=cfgs, patch_size=(16, 16), tubelet_size=2, device=dev, **geo)
+    torch.manual_seed(1234)
+    devc.seed_from_torch()
+    steps = 40 if variant == "crowded" else 6
+    for it in range(steps):
+        B = 5 + it % 3
+        he, hp = host.draw(fpc, B)
+        de, dp = devc.draw(fpc, B)
+        for j in range(len(cfgs)):
+            assert de[j].shape == he[j].shape and dp[j].shape == hp[j].shape, (variant, it, j)
+            assert torch.equal(de[j].cpu(), he[j]) and torch.equal(dp[j].cpu(), hp[j]), (variant, it, j)
+    assert torch.equal(devc.torch_rng_state(), torch.get_rng_state())
+
+
+def test_device_mask_collator_pipelined_draws_keep_their_buffers(dev):
+    """enqueue() one step ahead of collect(): the views returned for step i stay intact while draw i+1 is produced."""
+    from vjepa2_b200.masks import DeviceMaskCollator, MaskCollator
+    cfgs = [dict(aspect_ratio=(0.75, 1.5), num_blocks=8, spatial_scale=(0.15, 0.15), temporal_scale=(1.0, 1.0))]
+    host = MaskCollator(cfgs_mask=cfgs, dataset_fpcs=[16], crop_size=(256, 256), patch_size=(16, 16), tubelet_size=2)
+    devc = DeviceMaskCollator(cfgs_mask=cfgs, dataset_fpcs=[16], crop_size=(256, 256), patch_size=(16, 16), tubelet_size=2,
+                              device=dev)
+    torch.manual_seed(99)
+    devc.seed_from_torch()
+    want = [host.draw(16, 4) for _ in range(5)]
+    devc.enqueue(16, 4)
+    held = []
+    for it in range(5):
+        enc, pred = devc.collect()
+        if it + 1 < 5:
+            devc.enqueue(16, 4)
+        held.append((enc[0], pred[0]))
+        torch.cuda.synchronize()
+        assert torch.equal(enc[0].cpu(), want[it][0][0]) and torch.equal(pred[0].cpu(), want[it][1][0])
+        if it > 0:      # the previous step's views are still what they were
+            assert torch.equal(held[it - 1][0].cpu(), want[it - 1][0][0])

@@ -7,12 +7,12 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvjepa2_b200.so")
 
-ABI_VERSION = 2          # vj_abi_version() of the library this binding (struct layouts, prototypes) was written for
+ABI_VERSION = 3          # vj_abi_version() of the library this binding (struct layouts, prototypes) was written for
 VJ_BF16, VJ_F32 = 0, 1
 EPI_BIAS, EPI_GELU, EPI_DGELU, EPI_RESIDUAL = 1, 2, 4, 8
 EPI_OUT_F32, EPI_RES_F32, EPI_ROUND_BF16, EPI_AUX_OUT, EPI_ROPE = 16, 32, 64, 128, 256
@@ -29,6 +29,18 @@ class GemmArgs(Structure):
         ("rope_table", c_void_p), ("rope_hd", c_int32), ("rope_D", c_int32),
     ]
 
+
+class MaskSpec(Structure):
+    _fields_ = [
+        ("frames", c_int32), ("rows", c_int32), ("cols", c_int32), ("num_blocks", c_int32),
+        ("context_frames", c_int32), ("max_keep", c_int32), ("full_complement", c_int32),
+        ("pred_full_complement", c_int32),
+        ("temporal_lo", c_double), ("temporal_hi", c_double), ("spatial_lo", c_double), ("spatial_hi", c_double),
+        ("aspect_lo", c_double), ("aspect_hi", c_double),
+    ]
+
+
+MASK_RNG_WORDS = 626
 
 # name -> (restype, argtypes); every symbol include/vjepa2_b200.h declares
 SIGNATURES = {
@@ -68,6 +80,10 @@ SIGNATURES = {
     "vj_scaler_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_float,
                                  c_void_p]),
     "vj_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "vj_mask_collate_scratch": (c_size_t, [POINTER(MaskSpec), c_int64]),
+    "vj_mask_collate": (c_int, [c_void_p, POINTER(MaskSpec), ctypes.c_uint32, c_int64, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    "vj_gemm_set_pair_mode": (c_int, [c_int]),
 }
 
 _lib = None

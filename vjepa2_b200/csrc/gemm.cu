@@ -1025,12 +1025,16 @@ static int launch_gemm2(const vj_gemm_args* g, int flags, cudaStream_t stream) {
 }
 
 // CTA-pair kernel: on by default for problems with enough 256-row blocks; VJ_GEMM_2CTA=0 forces the 1-CTA kernels
-static bool use_pair_kernel(long long M, long long N) {
-  static int mode = -1;
-  if (mode < 0) {
+static int g_pair_mode = -1;
+static int pair_mode() {
+  if (g_pair_mode < 0) {
     const char* s = getenv("VJ_GEMM_2CTA");
-    mode = (s && s[0] >= '0' && s[0] <= '2') ? s[0] - '0' : 1;      // 0 off, 1 auto, 2 every shape (tests)
+    g_pair_mode = (s && s[0] >= '0' && s[0] <= '2') ? s[0] - '0' : 1;      // 0 off, 1 auto, 2 every shape (tests)
   }
+  return g_pair_mode;
+}
+static bool use_pair_kernel(long long M, long long N) {
+  const int mode = pair_mode();
   return mode == 2 || (mode == 1 && M >= 1024 && N >= 128);
 }
 
@@ -1056,6 +1060,12 @@ static int pick_bn(long long N, long long M) {
 }
 
 }  // namespace vj
+
+extern "C" int vj_gemm_set_pair_mode(int mode) {
+  const int old = vj::pair_mode();
+  if (mode >= 0 && mode <= 2) vj::g_pair_mode = mode;
+  return old;
+}
 
 extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
   using namespace vj;

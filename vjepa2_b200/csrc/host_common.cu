@@ -79,7 +79,7 @@ int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uin
 }  // namespace vj
 
 extern "C" const char* vj_last_error(void) { return vj::g_err; }
-extern "C" int vj_abi_version(void) { return 2; }
+extern "C" int vj_abi_version(void) { return 3; }
 extern "C" int vj_device_info(int* sm, int* major, int* minor) {
   int dev = 0;
   VJ_CUDA(cudaGetDevice(&dev));

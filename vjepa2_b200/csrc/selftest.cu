@@ -315,6 +315,57 @@ static void test_attn(int B, int S, int H, int hd, bool bwd) {
   cudaFree(qkv); cudaFree(out); cudaFree(lse); cudaFree(oref); cudaFree(lref);
 }
 
+// ------------------------------------------------------------------ GEMM stress: CTA-pair kernel, back-to-back launches
+__global__ void diff_words_kernel(const unsigned* a, const unsigned* b, long long n, unsigned long long* bad) {
+  unsigned long long c = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    c += a[i] != b[i];
+  if (c) atomicAdd(bad, c);
+}
+
+// The pair kernel's cross-CTA handshakes (remote accumulator-release arrives, multicast commits) under the
+// conditions a training step creates: consecutive launches whose CTAs overlap on the SMs, no host sync in between.
+// Every launch must reproduce the 1-CTA kernel's output bit for bit (same k-block order, same epilogue).
+static void stress_gemm(const char* name, int M, int N, int K, int a_mn, int b_mn, int flags, int reps) {
+  const bool of32 = flags & VJ_EPI_OUT_F32;
+  const size_t ob = (size_t)M * N * (of32 ? 4 : 2);
+  bf16* A = dalloc<bf16>((size_t)M * K);
+  bf16* B = dalloc<bf16>((size_t)N * K);
+  float* bias = dalloc<float>(N);
+  bf16* side = dalloc<bf16>((size_t)M * N);
+  char* ref = dalloc<char>(ob);
+  char* out[2] = {dalloc<char>(ob), dalloc<char>(ob)};
+  bf16* aux[2] = {dalloc<bf16>((size_t)M * N), dalloc<bf16>((size_t)M * N)};
+  unsigned long long* bad = dalloc<unsigned long long>(1);
+  CK(cudaMemset(bad, 0, 8));
+  fill(A, (long long)M * K, 11, 1.0f); fill(B, (long long)N * K, 12, 0.05f); fillf(bias, N, 13, 1.0f);
+  fill(side, (long long)M * N, 14, 1.0f);
+  vj_gemm_args g;
+  memset(&g, 0, sizeof(g));
+  g.a = A; g.b = B; g.M = M; g.N = N; g.K = K; g.lda = a_mn ? M : K; g.ldb = b_mn ? N : K; g.ldo = N;
+  g.a_mn_major = a_mn; g.b_mn_major = b_mn; g.flags = flags; g.bias = bias; g.residual = side; g.ldr = N;
+  g.aux_in = side; g.ld_aux = N;
+  const int old = vj_gemm_set_pair_mode(0);
+  g.out = ref; g.aux_out = aux[0];
+  VJ(vj_gemm(&g, 0));
+  CK(cudaDeviceSynchronize());
+  vj_gemm_set_pair_mode(2);
+  for (int r = 0; r < reps; ++r) {
+    g.out = out[r & 1]; g.aux_out = aux[r & 1];
+    VJ(vj_gemm(&g, 0));
+    diff_words_kernel<<<296, 256>>>((const unsigned*)out[r & 1], (const unsigned*)ref, (long long)(ob / 4), bad);
+  }
+  CK(cudaDeviceSynchronize());
+  vj_gemm_set_pair_mode(old);
+  unsigned long long hb = 0;
+  CK(cudaMemcpy(&hb, bad, 8, cudaMemcpyDeviceToHost));
+  printf("[stress gemm] %-26s M=%d N=%d K=%d  %d back-to-back pair launches vs 1-CTA kernel: %llu differing words  %s\n", name,
+         M, N, K, reps, hb, hb ? "FAIL" : "ok");
+  if (hb) g_fail = 1;
+  cudaFree(A); cudaFree(B); cudaFree(bias); cudaFree(side); cudaFree(ref); cudaFree(out[0]); cudaFree(out[1]);
+  cudaFree(aux[0]); cudaFree(aux[1]); cudaFree(bad);
+}
+
 #ifdef VJ_GEMM_PROFILE
 extern "C" int vj_gemm_prof_read(unsigned long long* out8, int reset);
 #endif
@@ -520,6 +571,18 @@ int main(int argc, char** argv) {
     bench_gemm("fc2  bias+res", 49152, 1408, 6144, 0, 0, VJ_EPI_BIAS | VJ_EPI_RESIDUAL | RB);
     bench_gemm("dgelu none", 16384, 6144, 1408, 0, 1, 0);
     bench_gemm("dgelu", 16384, 6144, 1408, 0, 1, VJ_EPI_DGELU);
+  }
+  if (!strcmp(what, "stressgemm")) {   // CTA-pair GEMM: back-to-back launches, bitwise against the 1-CTA kernel
+    const int reps = argc > 2 ? atoi(argv[2]) : 200;
+    const int RB = VJ_EPI_ROUND_BF16;
+    stress_gemm("qkv fwd bias", 12096, 4224, 1408, 0, 0, VJ_EPI_BIAS, reps);
+    stress_gemm("fc1 fwd gelu+aux", 12096, 6144, 1408, 0, 0, VJ_EPI_BIAS | VJ_EPI_GELU | RB | VJ_EPI_AUX_OUT, reps);
+    stress_gemm("fc2 fwd +res", 12096, 1408, 6144, 0, 0, VJ_EPI_BIAS | VJ_EPI_RESIDUAL | RB, reps);
+    stress_gemm("proj fwd +res (short K)", 49152, 1408, 1408, 0, 0, VJ_EPI_BIAS | VJ_EPI_RESIDUAL | RB, reps / 2);
+    stress_gemm("fc2 dgrad dgelu", 12096, 6144, 1408, 0, 1, VJ_EPI_DGELU, reps);
+    stress_gemm("fc1 wgrad", 6144, 1408, 12096, 1, 1, VJ_EPI_OUT_F32, reps);
+    stress_gemm("pred fc1 (K=384)", 36000, 1536, 384, 0, 0, VJ_EPI_BIAS | VJ_EPI_GELU | RB, reps);
+    stress_gemm("ragged", 3001, 1416, 520, 0, 0, VJ_EPI_BIAS, reps);
   }
   if (!strcmp(what, "stressattn")) {   // back-to-back launches (CTAs of consecutive launches overlap on the SMs)
     const int reps = argc > 2 ? atoi(argv[2]) : 20;

@@ -201,3 +201,157 @@ class MaskCollator(object):
                 enc, pred = self.draw(fpc, len(group))
                 out.append((torch.utils.data.default_collate(group), enc, pred))
         return out
+
+
+# ---------------------------------------------------------------------------------------------- device-side collator
+def _mt_words_from_torch_state(state: torch.Tensor) -> torch.Tensor:
+    """torch.get_rng_state() (CPUGeneratorImplState: seed u64, left i32, seeded i32, next u64, state u64[624], ...)
+    -> the 626 uint32 words vj_mask_collate keeps on the device (state[624], left, next), as int32 storage."""
+    raw = state.numpy()
+    left = int(raw[8:12].view("<i4")[0])
+    nxt = int(raw[16:24].view("<u8")[0])
+    words = raw[24:24 + 624 * 8].view("<u8").astype("<u4")
+    import numpy as np
+    return torch.from_numpy(np.concatenate([words, np.array([left, nxt], dtype="<u4")]).view("<i4").copy())
+
+
+def _torch_state_from_mt_words(words: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    """Inverse of _mt_words_from_torch_state: patch left / next / state[] into a copy of a torch CPU RNG state."""
+    out = like.clone()
+    raw = out.numpy()
+    w = words.cpu().numpy().view("<u4")
+    raw[8:12].view("<i4")[0] = int(w[624])
+    raw[16:24].view("<u8")[0] = int(w[625])
+    raw[24:24 + 624 * 8].view("<u8")[:] = w[:624].astype("<u8")
+    return out
+
+
+class DeviceMaskCollator:
+    """MaskCollator whose sampling runs on the GPU (csrc/maskgen.cu), RNG-call-identical to the reference
+    (multiseq_multiblock3d.py:129-239): same constructor arguments, and -- started from the same global torch CPU
+    generator state and the same draw counters -- bit-identical (masks_enc, masks_pred) index tensors, produced in
+    device memory.  The Mersenne-Twister state of the global generator is uploaded once (`seed_from_torch`) and then
+    lives on the device; `torch_rng_state()` reads it back in torch's own format.
+
+    The kept / hidden counts set the launch geometry of the step that consumes the masks, so they have to reach the
+    host: `enqueue` launches the kernels of one draw on a side stream and starts a 16-byte async copy of the counts
+    into pinned memory; `collect` (called one step later) waits on that event only and returns views of the dense
+    device buffers.  No host synchronisation is added to the step."""
+
+    def __init__(self, cfgs_mask, dataset_fpcs, crop_size=(224, 224), patch_size=(16, 16), tubelet_size=2,
+                 device=None, depth=2):
+        from . import _cabi as C
+        crop = crop_size if isinstance(crop_size, tuple) else (crop_size,) * 2
+        patch = patch_size if isinstance(patch_size, tuple) else (patch_size,) * 2
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.type != "cuda":
+            raise RuntimeError("vjepa2_b200.DeviceMaskCollator: CUDA device only (the host-side sampler is MaskCollator)")
+        self.specs = [BlockMaskSpec.from_cfg(c) for c in cfgs_mask]
+        self.grids = {fpc: TokenGrid(fpc // tubelet_size, crop[0] // patch[0], crop[1] // patch[1]) for fpc in dataset_fpcs}
+        self._cspecs = {}
+        for fpc, g in self.grids.items():
+            self._cspecs[fpc] = []
+            for sp in self.specs:
+                cs = C.MaskSpec(
+                    frames=g.frames, rows=g.rows, cols=g.cols, num_blocks=sp.num_blocks,
+                    context_frames=max(1, int(g.frames * sp.max_temporal_keep)),
+                    max_keep=sp.max_keep if sp.max_keep is not None else 0,
+                    full_complement=int(sp.full_complement), pred_full_complement=int(sp.pred_full_complement),
+                    temporal_lo=sp.temporal_scale[0], temporal_hi=sp.temporal_scale[1],
+                    spatial_lo=sp.spatial_scale[0], spatial_hi=sp.spatial_scale[1],
+                    aspect_lo=sp.aspect_ratio[0], aspect_hi=sp.aspect_ratio[1])
+                self._cspecs[fpc].append(cs)
+        self._draws = {fpc: [-1] * len(self.specs) for fpc in dataset_fpcs}     # per-generator draw counters (:121-126)
+        self._rng = torch.zeros(C.MASK_RNG_WORDS, dtype=torch.int32, device=self.device)
+        self._seeded = False
+        self._like = None
+        self._stream = torch.cuda.Stream(self.device)
+        self._depth = depth
+        self._slots = []           # ring of output buffer sets
+        self._turn = 0
+        self._pending = []
+
+    # -- RNG state plumbing
+    def seed_from_torch(self, state=None):
+        """Take over the global torch CPU generator stream (default: its current state)."""
+        state = torch.get_rng_state() if state is None else state
+        self._like = state.clone()
+        words = _mt_words_from_torch_state(state)
+        with torch.cuda.stream(self._stream):
+            self._rng.copy_(words.to(self.device))
+        self._stream.synchronize()
+        self._seeded = True
+
+    def torch_rng_state(self):
+        """The device generator's state in torch.get_rng_state() format (for torch.set_rng_state / checkpoints)."""
+        self._stream.synchronize()
+        return _torch_state_from_mt_words(self._rng, self._like)
+
+    def step(self):
+        for fpc in self._draws:
+            self._draws[fpc] = [d + 1 for d in self._draws[fpc]]
+
+    # -- one draw = one kernel per mask spec, in the reference's order (generator 0 for the whole batch, then 1, ...)
+    def _slot(self, fpc, B):
+        """Output buffers rotate over depth + 1 sets: `depth` draws in flight plus the one the current step reads."""
+        n = self.grids[fpc].size
+        if len(self._slots) < self._depth + 1:
+            self._slots.append(None)
+            i = len(self._slots) - 1
+        else:
+            i = self._turn % (self._depth + 1)
+        self._turn += 1
+        s = self._slots[i]
+        if s is None or s["cap"] < B * n:
+            s = dict(cap=B * n,
+                     enc=[torch.empty(B * n, dtype=torch.int64, device=self.device) for _ in self.specs],
+                     pred=[torch.empty(B * n, dtype=torch.int64, device=self.device) for _ in self.specs],
+                     counts=torch.zeros(2 * len(self.specs), dtype=torch.int32, device=self.device),
+                     counts_host=torch.zeros(2 * len(self.specs), dtype=torch.int32).pin_memory(),
+                     scratch=torch.empty(B * n, dtype=torch.uint8, device=self.device),
+                     event=torch.cuda.Event())
+            self._slots[i] = s
+        return s
+
+    def enqueue(self, fpc, batch_size):
+        import ctypes
+        from . import _cabi as C
+        if not self._seeded:
+            self.seed_from_torch()
+        if len(self._pending) >= self._depth:
+            raise RuntimeError("DeviceMaskCollator: too many outstanding draws; call collect() first")
+        lib = C.load()
+        s = self._slot(fpc, batch_size)
+        # the set being overwritten was last read by work already queued on the caller's stream
+        self._stream.wait_stream(torch.cuda.current_stream(self.device))
+        st = self._stream.cuda_stream
+        for j, cs in enumerate(self._cspecs[fpc]):
+            self._draws[fpc][j] += 1
+            seed = self._draws[fpc][j] & 0xFFFFFFFF
+            C.check(lib.vj_mask_collate(self._rng.data_ptr(), ctypes.byref(cs), seed, batch_size, s["enc"][j].data_ptr(),
+                                        s["pred"][j].data_ptr(), s["counts"][2 * j:].data_ptr(), s["scratch"].data_ptr(),
+                                        st), "vj_mask_collate")
+        with torch.cuda.stream(self._stream):
+            s["counts_host"].copy_(s["counts"], non_blocking=True)
+            s["event"].record(self._stream)
+        self._pending.append((s, fpc, batch_size))
+
+    def collect(self):
+        """([masks_enc per spec], [masks_pred per spec]) of the oldest outstanding draw: int64 [B, K] device tensors.
+        The returned views stay valid until `depth` further draws have been enqueued."""
+        s, fpc, B = self._pending.pop(0)
+        s["event"].synchronize()
+        torch.cuda.current_stream(self.device).wait_event(s["event"])
+        k = s["counts_host"].tolist()
+        enc, pred = [], []
+        for j, sp in enumerate(self.specs):
+            e = s["enc"][j][:B * k[2 * j]].view(B, k[2 * j])
+            p = s["pred"][j][:B * k[2 * j + 1]].view(B, k[2 * j + 1])
+            enc.append(p if sp.inv_block else e)
+            pred.append(e if sp.inv_block else p)
+        return enc, pred
+
+    def draw(self, fpc, batch_size):
+        """Synchronous convenience (tests): enqueue + collect."""
+        self.enqueue(fpc, batch_size)
+        return self.collect()
