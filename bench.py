@@ -306,6 +306,8 @@ def main():
     ap.add_argument("--batch", type=int, default=24)
     ap.add_argument("--frames", type=int, default=16, help="frames per clip (16 = pretrain configs, 64 = cooldown)")
     ap.add_argument("--crop", type=int, default=256, help="crop size (256 pretrain, 384 cooldown)")
+    ap.add_argument("--rank-local-masks", action="store_true",
+                    help="seed the mask stream with 239 + rank instead of the reference's rank-independent seed")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-torch-baseline", action="store_true", help="skip the reference's PyTorch-eager CUDA arm")
@@ -328,7 +330,9 @@ def main():
                            f"{'pretrain-256px-16f' if args.frames == 16 else 'cooldown-384px-64f'}.yaml shapes), "
                            f"batch {args.batch}/GPU, multiblock3d masks (8x0.15 + 2x0.7), predictor depth 12 / 384",
                   global_batch=args.batch * world, tokens_per_clip=NTOK, parallelism=f"dp{world}",
-                  l2_policy="working set (>= 2 GB of bf16 weights + activations per step) exceeds the 126 MB L2; no flush")
+                  l2_policy="working set (>= 2 GB of bf16 weights + activations per step) exceeds the 126 MB L2; no flush",
+                  mask_stream="rank-local seed 239 + rank" if args.rank_local_masks else
+                  "config seed 239 on every rank (reference: train.py:147-148), fresh draw per step; clips rank-local")
 
     def log(msg):
         print(f"[bench r{rank}] {msg}", file=sys.stderr, flush=True)
@@ -377,6 +381,9 @@ def main():
             uniform_power=True, use_mask_tokens=True, num_mask_tokens=6, zero_init_mask_tokens=True, use_sdpa=True,
             use_rope=True, use_activation_checkpointing=True)
     step = T.JepaTrainStep(encoder, predictor, **OPT)     # world > 1: broadcasts rank 0's parameters (DDP construction)
+    if world > 1:
+        config["grad_allreduce"] = (f"{step.grad_comm} ({'copy engines over peer-mapped symmetric memory' if step.grad_comm == 'peer' else 'torch.distributed all_reduce'}), "
+                                    f"{step.grad_sync}, buckets >= {step.bucket_bytes >> 20} MB")
     log(f"models built in {time.time() - t0:.1f}s; encoder params "
         f"{sum(p.numel() for p in step.encoder.parameters()) / 1e6:.1f}M")
 
@@ -385,7 +392,12 @@ def main():
     total = args.warmup + args.steps + 1
     collator = MaskCollator(cfgs_mask=MASK_CFG, dataset_fpcs=[FRAMES], crop_size=(CROP, CROP), patch_size=(PATCH, PATCH),
                             tubelet_size=TUB)
-    torch.manual_seed(239 + rank)                      # config seed 239; rank-local mask / clip streams
+    # Mask stream: the reference seeds EVERY rank with the same config seed (app/vjepa/train.py:147-148, no rank offset)
+    # and its collator runs in DataLoader workers whose seeds derive from that generator (base_seed + worker_id), so all
+    # ranks draw the SAME (masks_enc, masks_pred) each iteration -- K_enc / K_pred, hence the per-step work, are equal
+    # across ranks.  --rank-local-masks gives each rank its own stream instead (then every step waits for the rank
+    # with the largest draw: dp_imbalance).  Clips are rank-local in both modes.
+    torch.manual_seed(239 + (rank if args.rank_local_masks else 0))
     masks_host = make_masks(collator, B, total)
     gclip = torch.Generator().manual_seed(1000 + rank)
     clips_host = torch.randn(B, 3, FRAMES, CROP, CROP, generator=gclip).pin_memory()
@@ -475,8 +487,11 @@ def main():
         allf = torch.stack(allf)
         ratio = float(allf.max(dim=0).values.sum() / allf.mean(dim=0).sum())
         imbalance = dict(max_over_mean_step_flops=ratio, efficiency_bound=1.0 / ratio,
-                         note="per-rank mask draws (K truncated to the rank-local batch minimum) make per-step work differ "
-                              "across ranks; the all-reduce makes every step wait for the slowest rank")
+                         mask_stream="rank-local (239 + rank)" if args.rank_local_masks else
+                         "shared: every rank seeded with the config seed, as app/vjepa/train.py:147-148 does",
+                         note="with rank-local mask draws K_enc / K_pred (truncated to the rank-local batch minimum) "
+                              "differ across ranks and the all-reduce makes every step wait for the slowest rank; the "
+                              "reference's seeding gives every rank the same draw, hence a ratio of 1")
     clips_s = world * B * args.steps / (ms_total / 1e3)
     tflops_gpu = flops_timed / (ms_total / 1e3) / 1e12          # per GPU (each rank does B clips)
 

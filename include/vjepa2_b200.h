@@ -230,6 +230,21 @@ size_t vj_mask_collate_scratch(const vj_mask_spec* spec, int64_t B);
 int vj_mask_collate(uint32_t* rng_state, const vj_mask_spec* spec, uint32_t seed, int64_t B, int64_t* masks_enc,
                     int64_t* masks_pred, int32_t* counts, void* scratch, void* stream);
 
+/* ------------------------------------------------------------------ data-parallel gradient all-reduce, device side
+ * app/vjepa/train.py:279-281 (DistributedDataParallel's gradient mean).  The bytes move on the copy engines between
+ * peer-mapped (symmetric) buffers, issued by the host side (vjepa2_b200/train.py: PeerGradReducer); these are the two
+ * kernels that need an SM.  vj_ptr_list carries up to VJ_MAX_PEERS device pointers by value.
+ * vj_peer_barrier: flags.ptr[p] = rank p's flag array (uint32[VJ_MAX_PEERS], zero-initialised, mapped into this
+ * process); publishes `epoch` (monotonically increasing per call, same sequence on every rank) to every peer and waits
+ * until every peer has published an epoch >= it.  One warp; traps after ~20 s instead of hanging.
+ * vj_sum_into: dst[i] += srcs.ptr[0][i] + ... + srcs.ptr[n_src-1][i] (fp32, in that order), n % 4 == 0. */
+#define VJ_MAX_PEERS 16
+typedef struct {
+  void* ptr[VJ_MAX_PEERS];
+} vj_ptr_list;
+int vj_peer_barrier(const vj_ptr_list* flags, int rank, int world, uint32_t epoch, void* stream);
+int vj_sum_into(float* dst, const vj_ptr_list* srcs, int n_src, int64_t n, void* stream);
+
 /* Tuning / test switch of vj_gemm's kernel choice (same as the VJ_GEMM_2CTA environment variable): 0 = 1-CTA kernels
  * only, 1 = automatic (CTA-pair kernel for M >= 1024), 2 = CTA-pair kernel for every shape.  Returns the old mode. */
 int vj_gemm_set_pair_mode(int mode);

@@ -41,6 +41,12 @@ class MaskSpec(Structure):
 
 
 MASK_RNG_WORDS = 626
+MAX_PEERS = 16
+
+
+class PtrList(Structure):
+    _fields_ = [("ptr", c_void_p * MAX_PEERS)]
+
 
 # name -> (restype, argtypes); every symbol include/vjepa2_b200.h declares
 SIGNATURES = {
@@ -83,6 +89,8 @@ SIGNATURES = {
     "vj_mask_collate_scratch": (c_size_t, [POINTER(MaskSpec), c_int64]),
     "vj_mask_collate": (c_int, [c_void_p, POINTER(MaskSpec), ctypes.c_uint32, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
+    "vj_peer_barrier": (c_int, [POINTER(PtrList), c_int, c_int, ctypes.c_uint32, c_void_p]),
+    "vj_sum_into": (c_int, [c_void_p, POINTER(PtrList), c_int, c_int64, c_void_p]),
     "vj_gemm_set_pair_mode": (c_int, [c_int]),
 }
 

@@ -16,6 +16,7 @@ NCCL as soon as the last backward pass has produced them (DDP semantics, train.p
 from __future__ import annotations
 
 import copy
+import ctypes
 
 import torch
 import torch.distributed as dist
@@ -77,6 +78,105 @@ class GradBucketer:
         for w in self._works:
             w.wait()
         self._works = []
+
+
+class PeerGradReducer:
+    """Gradient all-reduce (train.py:279-281) over peer-mapped memory with the COPY ENGINES doing the transfers.
+
+    Why not NCCL here: the backward pass is a train of persistent one-CTA-per-SM kernels that hold the whole register
+    file, so an NCCL kernel and a GEMM cannot share an SM; every overlapped NCCL bucket stalls the (statically
+    scheduled) compute kernel it meets.  Measured on 2 B200s (profiles/r02e_*): 303 ms at N=1, 314 ms with the
+    overlapped NCCL all-reduce, 314 ms with one exposed all-reduce after backward (6.8 ms stand-alone).
+
+    Here the flat fp32 gradient buffers live in symmetric memory (torch.distributed._symmetric_memory: every rank maps
+    every other rank's buffer).  Per bucket [lo, hi), on a side stream, rank r owning slice r of the bucket:
+        wait(compute produced the bucket) -> barrier -> PULL slice r of every peer into local staging (DMA, NVLink)
+        -> g[slice r] += staged (vj_sum_into, the only SM work: ~1 ms per step in total) -> PUSH slice r into every
+        peer's buffer (DMA) -> barrier.
+    The barrier is a one-warp kernel (vj_peer_barrier: release/acquire flags in symmetric memory) that fits beside a
+    GEMM CTA.  Slice r is summed by rank r only, in rank order, and broadcast: all ranks hold identical bits."""
+
+    def __init__(self, group, device):
+        import torch.distributed._symmetric_memory as symm
+        from . import _cabi as C
+        self._symm, self._C = symm, C
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > C.MAX_PEERS:
+            raise RuntimeError(f"PeerGradReducer: world size {self.world} > {C.MAX_PEERS}")
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device, priority=-1)
+        self._flags = symm.empty(C.MAX_PEERS, dtype=torch.int32, device=self.device)
+        self._flags.zero_()
+        torch.cuda.synchronize(self.device)
+        hdl = symm.rendezvous(self._flags, self.group)
+        self._flag_list = C.PtrList()
+        for p in range(self.world):
+            self._flag_list.ptr[p] = int(hdl.buffer_ptrs[p])
+        self._flags_hdl = hdl
+        hdl.barrier()                               # every rank's flags are zeroed and mapped before the first epoch
+        torch.cuda.synchronize(self.device)
+        self._epoch = 0
+        self._bufs = {}                             # data_ptr -> (local tensor, [peer views])
+        self._staging = None
+        self._done = None
+
+    def alloc(self, numel):
+        """A zeroed flat fp32 gradient buffer in symmetric memory, mapped by every rank (collective call)."""
+        t = self._symm.empty(int(numel), dtype=torch.float32, device=self.device)
+        t.zero_()
+        torch.cuda.synchronize(self.device)
+        hdl = self._symm.rendezvous(t, self.group)
+        views = [t if p == self.rank else hdl.get_buffer(p, (int(numel),), torch.float32) for p in range(self.world)]
+        self._bufs[t.data_ptr()] = (t, views, hdl)
+        return t
+
+    def _barrier(self):
+        self._epoch += 1
+        self._C.check(self._C.load().vj_peer_barrier(ctypes.byref(self._flag_list), self.rank, self.world,
+                                                     self._epoch & 0x7FFFFFFF, self.stream.cuda_stream), "vj_peer_barrier")
+
+    def submit(self, flat, start, end):
+        """All-reduce flat[start:end] (flat from alloc()); ordered after the work queued so far on the current stream."""
+        if self.world == 1 or end <= start:
+            return
+        local, views, _ = self._bufs[flat.data_ptr()]
+        W, r = self.world, self.rank
+        n = end - start
+        per = ((n + W - 1) // W + 1023) // 1024 * 1024         # slice length (multiple of 1024 elements)
+        lo = min(end, start + r * per)
+        hi = min(end, lo + per)
+        m = hi - lo
+        if self._staging is None or self._staging.shape[1] < per:
+            self.stream.synchronize()
+            self._staging = torch.empty(W - 1, per, dtype=torch.float32, device=self.device)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        st = self.stream
+        st.wait_event(ready)
+        with torch.cuda.stream(st):
+            self._barrier()                                     # the bucket is final on every rank
+            if m > 0:
+                peers = [p for p in range(W) if p != r]
+                for k, p in enumerate(peers):                    # pull (copy engine)
+                    self._staging[k, :m].copy_(views[p][lo:hi], non_blocking=True)
+                srcs = self._C.PtrList()
+                for k in range(W - 1):
+                    srcs.ptr[k] = self._staging[k].data_ptr()
+                mm = (m + 3) // 4 * 4                            # slices are 1024-aligned inside 1024-padded buffers
+                self._C.check(self._C.load().vj_sum_into(local[lo:].data_ptr(), ctypes.byref(srcs), W - 1, mm,
+                                                         st.cuda_stream), "vj_sum_into")
+                for p in peers:                                  # push (copy engine)
+                    views[p][lo:hi].copy_(local[lo:hi], non_blocking=True)
+            self._barrier()                                     # every slice of the bucket has landed everywhere
+            self._done = torch.cuda.Event()
+            self._done.record(st)
+
+    def wait(self):
+        if self._done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._done)
+            self._done = None
 
 
 def make_bucket_hook(ranges, bucket_bytes, submit, last_key=-1):
@@ -237,7 +337,7 @@ class JepaTrainStep:
         self.grad_sync = grad_sync or os.environ.get("VJ_DDP_SYNC", "overlap")
         if self.grad_sync not in ("overlap", "end"):
             raise ValueError("grad_sync must be 'overlap' or 'end'")
-        self.bucket_bytes = int(bucket_mb if bucket_mb is not None else os.environ.get("VJ_DDP_BUCKET_MB", "0")) << 20
+        self._bucket_mb = bucket_mb if bucket_mb is not None else os.environ.get("VJ_DDP_BUCKET_MB")
         # optimizer step() calls so far; the steps GradScaler skipped (found_inf) are counted on the device
         # (self.skipped), so the bias corrections use torch's count, applied_steps - skipped, without a host sync
         self.applied_steps = 0
@@ -250,6 +350,38 @@ class JepaTrainStep:
         for m in (self.encoder, self.predictor, self.target_encoder):
             m._manual_shadows = True
         dev = self.enc_rt.fs.device
+        # gradient all-reduce transport: "peer" = copy engines over peer-mapped symmetric memory (PeerGradReducer, the
+        # default on CUDA with world > 1), "nccl" = torch.distributed all_reduce (GradBucketer; also the gloo path on CPU)
+        self.grad_comm = os.environ.get("VJ_DDP_COMM", "peer") if (self.world > 1 and dev.type == "cuda") else "nccl"
+        if self.grad_comm not in ("peer", "nccl"):
+            raise ValueError("VJ_DDP_COMM must be 'peer' or 'nccl'")
+        # bucket size: per-block ranges are merged up to this many bytes (NCCL: one bucket per block; the peer path
+        # pays two cross-GPU barriers per bucket, so it takes larger ones)
+        self.bucket_bytes = int(self._bucket_mb if self._bucket_mb is not None else (192 if self.grad_comm == "peer" else 0)) << 20
+        self.peer = None
+        if self.grad_comm == "peer":
+            if self.enc_rt.fs.g32 is not None or self.pred_rt.fs.g32 is not None:
+                raise RuntimeError("vjepa2_b200: gradient buffers already exist; build JepaTrainStep before the first "
+                                   "backward so they can live in symmetric memory (or set VJ_DDP_COMM=nccl)")
+            # symmetric memory needs peer access between all ranks of the group (one NVLink / NVSwitch box); every rank
+            # must take the same path, so the outcome of the set-up is agreed on (MIN over ranks) before it is used
+            peer, bufs, why = None, [], ""
+            try:
+                peer = PeerGradReducer(process_group, dev)
+                bufs = [peer.alloc(fs.total) for fs in (self.enc_rt.fs, self.pred_rt.fs)]
+            except Exception as ex:                                # noqa: BLE001 -- any failure means "use NCCL"
+                peer, why = None, f"{type(ex).__name__}: {str(ex)[:200]}"
+            ok = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=process_group)
+            if int(ok.item()) == 1:
+                self.peer = peer
+                self.enc_rt.fs.g32, self.pred_rt.fs.g32 = bufs
+            else:
+                import warnings
+                warnings.warn("vjepa2_b200: peer-mapped gradient all-reduce unavailable on this group (" + (why or "another "
+                              "rank failed") + "); using the NCCL all-reduce", RuntimeWarning)
+                self.grad_comm = "nccl"
+                self.bucket_bytes = int(self._bucket_mb if self._bucket_mb is not None else 0) << 20
         self.enc_rt.fs.ensure_grads()
         self.pred_rt.fs.ensure_grads()
         self.enc_rt.fs.ensure_adam()
@@ -298,9 +430,12 @@ class JepaTrainStep:
         self._enc_ranges[-1] = fs.range_of(self.enc_rt.pe_params)
 
     # ------------------------------------------------------------------------------------------
+    def _reducer(self):
+        return self.peer if self.peer is not None else self.bucketer
+
     def _bucket_hook(self, efs):
-        return make_bucket_hook(self._enc_ranges, self.bucket_bytes,
-                                lambda lo, hi: self.bucketer.submit(efs.g32, lo, hi))
+        red = self._reducer()
+        return make_bucket_hook(self._enc_ranges, self.bucket_bytes, lambda lo, hi: red.submit(efs.g32, lo, hi))
 
     def _set_frozen_mask_tokens(self, n_groups):
         """Group i uses mask token i % num_mask_tokens (wrappers.py:40, predictor.py:195); tokens no rank uses in this
@@ -455,15 +590,15 @@ class JepaTrainStep:
                 del sv_p
                 hook = None
                 if last and self.world > 1 and self.grad_sync == "overlap":
-                    self.bucketer.submit(pfs.g32, 0, pfs.total)
+                    self._reducer().submit(pfs.g32, 0, pfs.total)
                     hook = self._bucket_hook(efs)
                 engine.encoder_backward(enc_rt, sv_e, dzenc, efs.g32, ws=ws, on_block_done=hook)
                 del sv_e, zs, preds, dz, dzenc
                 ws._act.reset()                                   # this pass's activations are dead
         if self.world > 1 and self.grad_sync == "end":                # one collective per model after backward
-            self.bucketer.submit(pfs.g32, 0, pfs.total)
-            self.bucketer.submit(efs.g32, 0, efs.total)
-        self.bucketer.wait()
+            self._reducer().submit(pfs.g32, 0, pfs.total)
+            self._reducer().submit(efs.g32, 0, efs.total)
+        self._reducer().wait()
 
         # ---- unscale + inf check + AdamW (train.py:446-451; app/vjepa/utils.py:239), flat kernels
         ops.grad_check(efs.g32, self.found_inf, st)
