@@ -88,15 +88,20 @@ int vj_gemm(const vj_gemm_args* a, void* stream);
 /* ------------------------------------------------------------------ LayerNorm
  * nn.LayerNorm(eps=1e-6) norm1/norm2/norm/predictor_norm (modules.py:558,562;
  * vision_transformer.py:211; predictor.py:233) and F.layer_norm without affine, eps 1e-5
- * (train.py:417; gamma/beta NULL).  Statistics in fp32.  mean/rstd may be NULL in forward. */
+ * (train.py:417; gamma/beta NULL).  Statistics in fp32.  mean/rstd may be NULL in forward.
+ * ldy: row pitch of y in elements (0 = D).  With ldy > D (a multiple of 8 more) the pad columns [D, ldy) of every
+ * row are set to 1.0: vj_gemm's VJ_EPI_BIAS_GRAD reads them as the ones-column that yields a bias gradient. */
 int vj_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y, int y_dtype,
-                     float* mean, float* rstd, int64_t rows, int64_t D, float eps, void* stream);
-/* dx = LN'(dy) (+ dres if given, same dtype as dx); dgamma/dbeta (fp32 [D]) are ACCUMULATED (+=).
- * scratch: at least vj_layernorm_bwd_scratch(rows, D) bytes. */
+                     float* mean, float* rstd, int64_t rows, int64_t D, int64_t ldy, float eps, void* stream);
+/* dx = LN'(dy) (+ dres if given, same dtype as dx), one pass over dy / x / dres that also ACCUMULATES (+=) the column
+ * sums dgamma = sum dy*xhat, dbeta = sum dy and dbias = sum dres (fp32 [D] each, any may be NULL): dres is the
+ * gradient of the residual branch's Linear output, so dbias is that Linear's bias gradient (fc2 in norm2's backward,
+ * proj in norm1's).  Deterministic (per-CTA partials in scratch, added in CTA order by a second small kernel).
+ * scratch: at least vj_layernorm_bwd_scratch(rows, D) bytes when any column sum is requested. */
 size_t vj_layernorm_bwd_scratch(int64_t rows, int64_t D);
 int vj_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
                      const float* mean, const float* rstd, const void* dres, void* dx, int dx_dtype,
-                     float* dgamma, float* dbeta, void* scratch, int64_t rows, int64_t D, void* stream);
+                     float* dgamma, float* dbeta, float* dbias, void* scratch, int64_t rows, int64_t D, void* stream);
 
 /* ------------------------------------------------------------------ 3-axis RoPE
  * rotate_queries_or_keys + separate_positions (modules.py:26-50, 311-365).

@@ -208,7 +208,9 @@ def test_attention_rows_sum_to_one_full_size(dev):
 
 
 # ----------------------------------------------------------------------------------------------- LayerNorm
-@pytest.mark.parametrize("rows,D,xd,yd", [(1000, 1408, BF16, BF16), (77, 384, F32, BF16), (513, 128, BF16, F32), (9, 64, F32, F32)])
+@pytest.mark.parametrize("rows,D,xd,yd", [(1000, 1408, BF16, BF16), (77, 384, F32, BF16), (513, 128, BF16, F32), (9, 64, F32, F32),
+                                          (12096, 1408, BF16, BF16), (5000, 1024, BF16, BF16), (3001, 1280, BF16, BF16),
+                                          (40000, 384, F32, BF16), (700, 2048, BF16, BF16)])
 def test_layernorm_fwd_bwd(dev, rows, D, xd, yd):
     from vjepa2_b200 import ops
     x = randn(rows, D, seed=1, dtype=xd).to(dev)
@@ -228,9 +230,23 @@ def test_layernorm_fwd_bwd(dev, rows, D, xd, yd):
     dx = torch.empty(rows, D, dtype=xd, device=dev)
     dg = torch.ones(D, device=dev)
     db = torch.ones(D, device=dev)
-    ops.layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres=dres, dgamma=dg, dbeta=db)
+    dbias = torch.full((D,), 2.0, device=dev)
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres=dres, dgamma=dg, dbeta=db, dbias=dbias)
     assert relerr(dx, xr.grad + dres.float()) < (5e-3 if xd == BF16 else 1e-4)
     assert relerr(dg - 1, gr.grad) < 1e-4 and relerr(db - 1, br.grad) < 1e-4
+    assert relerr(dbias - 2, dres.float().sum(0)) < 1e-4          # fused bias gradient: column sum of dres, accumulated
+    # deterministic: a second call adds exactly the same sums; without column outputs only dx is produced
+    dg2, db2, dbias2 = torch.ones(D, device=dev), torch.ones(D, device=dev), torch.full((D,), 2.0, device=dev)
+    dx2 = torch.empty_like(dx)
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, dx2, dres=dres, dgamma=dg2, dbeta=db2, dbias=dbias2)
+    assert torch.equal(dx2, dx) and torch.equal(dg2, dg) and torch.equal(db2, db) and torch.equal(dbias2, dbias)
+    dx3 = torch.empty_like(dx)
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, dx3)
+    assert relerr(dx3, xr.grad) < (5e-3 if xd == BF16 else 1e-4)
+    # padded output (bias-gradient ones-column of the wgrad GEMM): pad columns hold 1, the rest is unchanged
+    yp = torch.zeros(rows, D + 8, dtype=yd, device=dev)
+    ops.layernorm_fwd(x, gamma, beta, yp, None, None, 1e-6)
+    assert torch.equal(yp[:, :D], y) and bool((yp[:, D:] == 1).all())
     # non-affine variant (train.py:417), in place
     h = x.float().clone()
     ops.layernorm_fwd(h, None, None, h, None, None, 1e-5)

@@ -55,10 +55,10 @@ SIGNATURES = {
     "vj_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "vj_gemm": (c_int, [POINTER(GemmArgs), c_void_p]),
     "vj_layernorm_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
-                                 c_int64, c_int64, c_float, c_void_p]),
+                                 c_int64, c_int64, c_int64, c_float, c_void_p]),
     "vj_layernorm_bwd_scratch": (c_size_t, [c_int64, c_int64]),
     "vj_layernorm_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
+                                 c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
     "vj_rope_table": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vj_rope_apply": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_void_p]),
     "vj_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

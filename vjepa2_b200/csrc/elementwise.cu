@@ -87,22 +87,39 @@ __device__ __forceinline__ void store8t(void* base, long long off, const float (
   }
 }
 
+// Forward: the NEXT row of a warp is fetched before the current one is reduced (two rows of 128-bit loads in flight
+// per lane), so the load latency of row i+1 hides behind the two warp reductions and the store of row i.
+// ldy >= D is the row pitch of y; the pad columns [D, ldy) are written with 1.0 -- the wgrad GEMM that consumes y as
+// its MN-major B operand then produces the bias gradient as one extra output column (VJ_EPI_BIAS_GRAD).
 template <bool XF32, bool YF32, int NV>
-__global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, 3) ln_fwd_kernel(const void* __restrict__ x, const float* __restrict__ gamma,
                                                      const float* __restrict__ beta, void* __restrict__ y,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                     long long rows, int D, float eps) {
+                                                     long long rows, int D, long long ldy, float eps) {
   const int lane = threadIdx.x & 31;
   const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const long long nw = (long long)gridDim.x * 8;
   const int nvec = D >> 3;
+  const int npad = (int)(ldy - D) >> 3;
   const float inv_d = 1.0f / D;
-  for (long long row = wid; row < rows; row += nw) {
-    RawVec<XF32> raw[NV];
+  RawVec<XF32> nxt[NV];
+  if (wid < rows) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int vi = lane + i * 32;
-      if (vi < nvec) raw[i].load(x, row * D + vi * 8);
+      if (vi < nvec) nxt[i].load(x, wid * D + vi * 8);
+    }
+  }
+  for (long long row = wid; row < rows; row += nw) {
+    RawVec<XF32> raw[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) raw[i] = nxt[i];
+    if (row + nw < rows) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) nxt[i].load(x, (row + nw) * D + vi * 8);
+      }
     }
     float s = 0.f;
 #pragma unroll
@@ -151,79 +168,173 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const void* __restrict__
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] = (v[j] - mean) * rstd;
         }
-        store8t<YF32>(y, row * D + vi * 8, o);
+        store8t<YF32>(y, row * ldy + vi * 8, o);
       }
+    }
+    if (lane < npad) {
+      const float ones[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+      store8t<YF32>(y, row * ldy + D + lane * 8, ones);
     }
   }
 }
 
-// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres), g = dy * gamma
-template <bool DYF32, bool XF32, bool DXF32, int NV>
-__global__ void __launch_bounds__(256, 3) ln_bwd_dx_kernel(const void* __restrict__ dy, const void* __restrict__ x,
-                                                        const float* __restrict__ gamma,
-                                                        const float* __restrict__ mean_in,
-                                                        const float* __restrict__ rstd_in,
-                                                        const void* __restrict__ dres, void* __restrict__ dx,
-                                                        long long rows, int D) {
-  const int lane = threadIdx.x & 31;
-  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  const long long nw = (long long)gridDim.x * 8;
+// Backward, one pass over dy / x / dres:  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres), g = dy * gamma,
+// AND the column sums dbeta = sum_r dy, dgamma = sum_r dy * xhat, dbias = sum_r dres (the bias gradient of the Linear
+// that produced the residual branch: dres is d(fc2 output) in LN2's backward and d(proj output) in LN1's) -- no second
+// read of dy and x, no separate bias-gradient launches.
+// CTA = RG row groups x WPR warps.  A thread owns the SAME 8 columns of every row its group visits, so the column sums
+// stay in 24 registers for the whole kernel; the two row sums go warp shuffle -> shared memory across the WPR warps
+// (double buffered: one __syncthreads per iteration, R rows per group and iteration).  Per-CTA column partials go to
+// scratch and are added in CTA order by ln_bwd_final_kernel (no atomics: deterministic).
+constexpr int LNB_THREADS = 384;
+constexpr int LNB_MAX_CTAS = 384;
+
+// (A variant that stages the rows through a shared-memory ring filled by cp.async.bulk was measured slower -- 201 vs
+// 150 us at 49152 x 1408: the kernel is close to instruction-issue-bound (~200 instructions per thread and row), and
+// the extra LDS + mbarrier polling cost more than the deeper prefetch gained.)
+template <bool DYF32, bool XF32, bool DXF32, int R>
+__global__ void __launch_bounds__(LNB_THREADS, 2) ln_bwd_fused_kernel(
+    const void* __restrict__ dy, const void* __restrict__ x, const float* __restrict__ gamma,
+    const float* __restrict__ mean_in, const float* __restrict__ rstd_in, const void* __restrict__ dres,
+    void* __restrict__ dx, float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta,
+    float* __restrict__ dbias, long long rows, int D, int WPR, int RG, int iters) {
+  __shared__ float s_red[2][LNB_THREADS / 32][2 * R];
+  __shared__ float s_col[3][LN_MAXV * 256];
+  const int t = threadIdx.x, lane = t & 31, wl = t >> 5;
+  const int rg = wl / WPR, w = wl - rg * WPR;
+  const int ct = w * 32 + lane;
   const int nvec = D >> 3;
+  const bool live = rg < RG && ct < nvec;
+  const int col = ct * 8;
   const float inv_d = 1.0f / D;
-  for (long long row = wid; row < rows; row += nw) {
-    RawVec<DYF32> rdy[NV];
-    RawVec<XF32> rx[NV];
+  const bool want_cols = dgamma || dbeta || dbias;
+  float gm[8];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-        rdy[i].load(dy, row * D + vi * 8);
-        rx[i].load(x, row * D + vi * 8);
+  for (int j = 0; j < 8; ++j) gm[j] = 1.f;
+  if (live && gamma) load8(gamma, VJ_F32, col, gm);
+  float acc_b[8], acc_g[8], acc_r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc_b[j] = acc_g[j] = acc_r[j] = 0.f;
+  int buf = 0;
+  for (int it = 0; it < iters; ++it, buf ^= 1) {
+    const long long base = (((long long)it * gridDim.x + blockIdx.x) * RG + rg) * R;
+    RawVec<DYF32> rdy[R];
+    RawVec<XF32> rx[R];
+    RawVec<DXF32> rr[R];
+    float mu[R], rs[R];
+#pragma unroll
+    for (int u = 0; u < R; ++u) {
+      const long long row = base + u;
+      const bool ok = live && row < rows;
+      mu[u] = 0.f; rs[u] = 0.f;
+      if (ok) {
+        rdy[u].load(dy, row * D + col);
+        rx[u].load(x, row * D + col);
+        if (dres) rr[u].load(dres, row * D + col);
+        mu[u] = __ldg(mean_in + row);
+        rs[u] = __ldg(rstd_in + row);
       }
     }
-    const float mean = mean_in[row], rstd = rstd_in[row];
-    float s1 = 0.f, s2 = 0.f;
+    float s1[R], s2[R];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-        float dv[8], xv[8], gm[8];
-        rdy[i].get(dv);
-        rx[i].get(xv);
-        if (gamma) load8(gamma, VJ_F32, vi * 8, gm);
+    for (int u = 0; u < R; ++u) {
+      s1[u] = s2[u] = 0.f;
+      if (live && base + u < rows) {
+        float dv[8], xv[8];
+        rdy[u].get(dv);
+        rx[u].get(xv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float g = gamma ? dv[j] * gm[j] : dv[j];
-          s1 += g;
-          s2 = fmaf(g, (xv[j] - mean) * rstd, s2);
+          const float g = dv[j] * gm[j];
+          s1[u] += g;
+          s2[u] = fmaf(g, (xv[j] - mu[u]) * rs[u], s2[u]);
+        }
+      }
+      s1[u] = warp_sum(s1[u]);
+      s2[u] = warp_sum(s2[u]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int u = 0; u < R; ++u) { s_red[buf][wl][2 * u] = s1[u]; s_red[buf][wl][2 * u + 1] = s2[u]; }
+    }
+    __syncthreads();
+    if (live) {
+#pragma unroll
+      for (int u = 0; u < R; ++u) {
+        const long long row = base + u;
+        if (row < rows) {
+          float c1 = 0.f, c2 = 0.f;
+          for (int k = 0; k < WPR; ++k) { c1 += s_red[buf][rg * WPR + k][2 * u]; c2 += s_red[buf][rg * WPR + k][2 * u + 1]; }
+          c1 *= inv_d; c2 *= inv_d;
+          float dv[8], xv[8], o[8];
+          rdy[u].get(dv);
+          rx[u].get(xv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = (xv[j] - mu[u]) * rs[u];
+            o[j] = rs[u] * (dv[j] * gm[j] - c1 - xh * c2);
+            acc_b[j] += dv[j];
+            acc_g[j] = fmaf(dv[j], xh, acc_g[j]);
+          }
+          if (dres) {
+            float r[8];
+            rr[u].get(r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j] += r[j]; acc_r[j] += r[j]; }
+          }
+          store8t<DXF32>(dx, row * D + col, o);
         }
       }
     }
-    const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
+  }
+  if (!want_cols) return;
+  // ---- column sums of this CTA: row groups add into shared memory one after the other (fixed order)
+  for (int g = 0; g < RG; ++g) {
+    if (live && rg == g) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int vi = lane + i * 32;
-      if (vi < nvec) {
-        float dv[8], xv[8], gm[8], o[8];
-        rdy[i].get(dv);
-        rx[i].get(xv);
-        if (gamma) load8(gamma, VJ_F32, vi * 8, gm);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float g = gamma ? dv[j] * gm[j] : dv[j];
-          o[j] = rstd * (g - c1 - (xv[j] - mean) * rstd * c2);
-        }
-        if (dres) {
-          RawVec<DXF32> rr;
-          rr.load(dres, row * D + vi * 8);
-          float r[8];
-          rr.get(r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
-        }
-        store8t<DXF32>(dx, row * D + vi * 8, o);
+      for (int j = 0; j < 8; ++j) {
+        if (g == 0) { s_col[0][col + j] = acc_b[j]; s_col[1][col + j] = acc_g[j]; s_col[2][col + j] = acc_r[j]; }
+        else { s_col[0][col + j] += acc_b[j]; s_col[1][col + j] += acc_g[j]; s_col[2][col + j] += acc_r[j]; }
       }
     }
+    __syncthreads();
+  }
+  const int n3 = 3 * D;
+  float* mine = part + (long long)blockIdx.x * n3;
+  for (int j = t; j < n3; j += (int)blockDim.x) mine[j] = s_col[j / D][j - (j / D) * D];
+}
+
+// Adds the per-CTA column partials of ln_bwd_fused_kernel ([P][3][D], CTA order) into dbeta / dgamma / dbias.
+// block (16 columns, 16 partial groups): every thread sums P/16 partials with independent loads, the 16 group sums
+// are combined in shared memory in group order -- deterministic, ~2 us.
+__global__ void __launch_bounds__(256) ln_bwd_final_kernel(const float* __restrict__ part, int P, int D,
+                                                           float* __restrict__ dbeta, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbias) {
+  __shared__ float sm[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int n3 = 3 * D;
+  const int j = blockIdx.x * 16 + tx;
+  float s = 0.f;
+  if (j < n3) {
+    const int per = (P + 15) / 16;
+    const int k0 = ty * per, k1 = min(P, k0 + per);
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+      const float a = __ldcg(part + (long long)k * n3 + j), b = __ldcg(part + (long long)(k + 1) * n3 + j);
+      const float c = __ldcg(part + (long long)(k + 2) * n3 + j), d = __ldcg(part + (long long)(k + 3) * n3 + j);
+      s += a; s += b; s += c; s += d;
+    }
+    for (; k < k1; ++k) s += __ldcg(part + (long long)k * n3 + j);
+  }
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && j < n3) {
+    float r = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) r += sm[g][tx];
+    const int q = j / D, c = j - q * D;
+    float* out = q == 0 ? dbeta : q == 1 ? dgamma : dbias;
+    if (out) out[c] += r;
   }
 }
 
@@ -861,89 +972,101 @@ static int check_rowvec(const char* who, int64_t rows, int64_t D) {
 
 template <bool XF32, bool YF32>
 static void ln_fwd_launch(int nv, unsigned grid, cudaStream_t st, const void* x, const float* gamma, const float* beta,
-                          void* y, float* mean, float* rstd, long long rows, int D, float eps) {
+                          void* y, float* mean, float* rstd, long long rows, int D, long long ldy, float eps) {
 #define VJ_LN_CASE(NV_) \
-  case NV_: ln_fwd_kernel<XF32, YF32, NV_><<<grid, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, D, eps); break;
+  case NV_: ln_fwd_kernel<XF32, YF32, NV_><<<grid, 256, 0, st>>>(x, gamma, beta, y, mean, rstd, rows, D, ldy, eps); break;
   switch (nv) { VJ_LN_CASE(1) VJ_LN_CASE(2) VJ_LN_CASE(4) VJ_LN_CASE(6) VJ_LN_CASE(8) }
 #undef VJ_LN_CASE
 }
 
 extern "C" int vj_layernorm_fwd(const void* x, int x_dtype, const float* gamma, const float* beta, void* y,
-                                int y_dtype, float* mean, float* rstd, int64_t rows, int64_t D, float eps,
+                                int y_dtype, float* mean, float* rstd, int64_t rows, int64_t D, int64_t ldy, float eps,
                                 void* stream) {
   if (check_rowvec("vj_layernorm_fwd", rows, D)) return -1;
   VJ_CHECK(D <= LN_MAXV * 256, "vj_layernorm_fwd: D=%lld exceeds %d", (long long)D, LN_MAXV * 256);
   VJ_CHECK(x && y, "vj_layernorm_fwd: null pointer");
+  if (ldy == 0) ldy = D;
+  VJ_CHECK(ldy >= D && (ldy - D) % 8 == 0 && ldy - D <= 256, "vj_layernorm_fwd: bad output pitch %lld for D=%lld",
+           (long long)ldy, (long long)D);
+  VJ_CHECK(ldy == D || x != y, "vj_layernorm_fwd: a padded output cannot be written in place");
   if (rows == 0) return 0;
   const int nv = ln_pick_nv(D);
   const unsigned grid = ln_grid(rows);
   cudaStream_t st = STREAM(stream);
   const bool xf = x_dtype == VJ_F32, yf = y_dtype == VJ_F32;
-  if (!xf && !yf) ln_fwd_launch<false, false>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, eps);
-  else if (!xf && yf) ln_fwd_launch<false, true>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, eps);
-  else if (xf && !yf) ln_fwd_launch<true, false>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, eps);
-  else ln_fwd_launch<true, true>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, eps);
+  if (!xf && !yf) ln_fwd_launch<false, false>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, ldy, eps);
+  else if (!xf && yf) ln_fwd_launch<false, true>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, ldy, eps);
+  else if (xf && !yf) ln_fwd_launch<true, false>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, ldy, eps);
+  else ln_fwd_launch<true, true>(nv, grid, st, x, gamma, beta, y, mean, rstd, rows, (int)D, ldy, eps);
   VJ_LAUNCH_CHECK();
   return 0;
 }
 
+// launch geometry of ln_bwd_fused_kernel: WPR warps cover one row (8 columns per thread), RG rows groups per CTA
+struct LnBwdGeo { int WPR, RG, R, grid, iters; };
+static LnBwdGeo ln_bwd_geo(long long rows, long long D, bool any_f32) {
+  LnBwdGeo g;
+  g.WPR = (int)((D / 8 + 31) / 32);
+  g.RG = (LNB_THREADS / 32) / g.WPR;
+  if (g.RG < 1) g.RG = 1;
+  g.R = any_f32 ? 1 : 2;
+  const long long per_cta = (long long)g.RG * g.R;
+  long long want = (rows + per_cta - 1) / per_cta;
+  long long cap = 2ll * sm_count();
+  if (cap > LNB_MAX_CTAS) cap = LNB_MAX_CTAS;
+  g.grid = (int)(want < cap ? want : cap);
+  if (g.grid < 1) g.grid = 1;
+  g.iters = (int)((rows + per_cta * g.grid - 1) / (per_cta * g.grid));
+  return g;
+}
+
 template <bool DYF32, bool XF32, bool DXF32>
-static void ln_bwd_launch(int nv, unsigned grid, cudaStream_t st, const void* dy, const void* x, const float* gamma,
-                          const float* mean, const float* rstd, const void* dres, void* dx, long long rows, int D) {
-#define VJ_LN_CASE(NV_) \
-  case NV_: ln_bwd_dx_kernel<DYF32, XF32, DXF32, NV_><<<grid, 256, 0, st>>>(dy, x, gamma, mean, rstd, dres, dx, rows, D); break;
-  switch (nv) { VJ_LN_CASE(1) VJ_LN_CASE(2) VJ_LN_CASE(4) VJ_LN_CASE(6) VJ_LN_CASE(8) }
-#undef VJ_LN_CASE
+static int ln_bwd_launch(const LnBwdGeo& g, cudaStream_t st, const void* dy, const void* x, const float* gamma,
+                         const float* mean, const float* rstd, const void* dres, void* dx, float* part, float* dgamma,
+                         float* dbeta, float* dbias, long long rows, int D) {
+  constexpr int R = (DYF32 || XF32 || DXF32) ? 1 : 2;
+  ln_bwd_fused_kernel<DYF32, XF32, DXF32, R><<<g.grid, g.WPR * g.RG * 32, 0, st>>>(
+      dy, x, gamma, mean, rstd, dres, dx, part, dgamma, dbeta, dbias, rows, D, g.WPR, g.RG, g.iters);
+  return 0;
 }
 
 extern "C" size_t vj_layernorm_bwd_scratch(int64_t rows, int64_t D) {
-  return (size_t)2 * col_chunks(rows) * (size_t)D * sizeof(float);
+  (void)rows;
+  return (size_t)LNB_MAX_CTAS * 3 * (size_t)D * sizeof(float);
 }
 
 extern "C" int vj_layernorm_bwd(const void* dy, int dy_dtype, const void* x, int x_dtype, const float* gamma,
                                 const float* mean, const float* rstd, const void* dres, void* dx, int dx_dtype,
-                                float* dgamma, float* dbeta, void* scratch, int64_t rows, int64_t D, void* stream) {
+                                float* dgamma, float* dbeta, float* dbias, void* scratch, int64_t rows, int64_t D,
+                                void* stream) {
   if (check_rowvec("vj_layernorm_bwd", rows, D)) return -1;
   VJ_CHECK(D <= LN_MAXV * 256, "vj_layernorm_bwd: D=%lld exceeds %d", (long long)D, LN_MAXV * 256);
   VJ_CHECK(dy && x && mean && rstd && dx, "vj_layernorm_bwd: null pointer");
+  VJ_CHECK(!dbias || dres, "vj_layernorm_bwd: dbias is the column sum of dres, which is null");
+  if (dgamma || dbeta || dbias) VJ_CHECK(scratch != nullptr, "vj_layernorm_bwd: scratch required for dgamma / dbeta / dbias");
   if (rows == 0) return 0;
-  {
-    const int nv = ln_pick_nv(D);
-    const unsigned grid = ln_grid(rows);
-    cudaStream_t st = STREAM(stream);
-    const int key = (dy_dtype == VJ_F32 ? 4 : 0) | (x_dtype == VJ_F32 ? 2 : 0) | (dx_dtype == VJ_F32 ? 1 : 0);
-    switch (key) {   // the dtype combinations the engine produces (encoder bf16 stream, predictor fp32 stream)
-      case 0: ln_bwd_launch<false, false, false>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
-      case 1: ln_bwd_launch<false, false, true>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
-      case 2: ln_bwd_launch<false, true, false>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
-      case 3: ln_bwd_launch<false, true, true>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
-      case 4: ln_bwd_launch<true, false, false>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
-      case 5: ln_bwd_launch<true, false, true>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
-      case 6: ln_bwd_launch<true, true, false>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
-      default: ln_bwd_launch<true, true, true>(nv, grid, st, dy, x, gamma, mean, rstd, dres, dx, rows, (int)D); break;
-    }
+  const bool f32 = dy_dtype == VJ_F32 || x_dtype == VJ_F32 || dx_dtype == VJ_F32;
+  const LnBwdGeo g = ln_bwd_geo(rows, D, f32);
+  cudaStream_t st = STREAM(stream);
+  float* part = reinterpret_cast<float*>(scratch);
+  const int key = (dy_dtype == VJ_F32 ? 4 : 0) | (x_dtype == VJ_F32 ? 2 : 0) | (dx_dtype == VJ_F32 ? 1 : 0);
+#define VJ_LNB(A_, B_, C_) \
+  if (ln_bwd_launch<A_, B_, C_>(g, st, dy, x, gamma, mean, rstd, dres, dx, part, dgamma, dbeta, dbias, rows, (int)D)) return -2
+  switch (key) {   // the dtype combinations the engine produces (encoder bf16 stream, predictor fp32 stream)
+    case 0: VJ_LNB(false, false, false); break;
+    case 1: VJ_LNB(false, false, true); break;
+    case 2: VJ_LNB(false, true, false); break;
+    case 3: VJ_LNB(false, true, true); break;
+    case 4: VJ_LNB(true, false, false); break;
+    case 5: VJ_LNB(true, false, true); break;
+    case 6: VJ_LNB(true, true, false); break;
+    default: VJ_LNB(true, true, true); break;
   }
+#undef VJ_LNB
   VJ_LAUNCH_CHECK();
-  if (dgamma || dbeta) {
-    VJ_CHECK(scratch != nullptr, "vj_layernorm_bwd: scratch required for dgamma/dbeta");
-    const int chunks = col_chunks(rows);
-    const long long rpc = (rows + chunks - 1) / chunks;
-    float* ps = reinterpret_cast<float*>(scratch);
-    float* px = ps + (size_t)chunks * D;
-    if (colw_ok(D)) {
-      dim3 grid((unsigned)((D + 255) / 256), (unsigned)chunks), block(32, 8);
-      colreduce_wide_kernel<true><<<grid, block, 0, STREAM(stream)>>>(dy, dy_dtype, x, x_dtype, mean, rstd, ps, px,
-                                                                     dbeta, dgamma, rows, (int)D, rpc, 1);
-      VJ_LAUNCH_CHECK();
-    } else {
-      dim3 grid((unsigned)((D + 63) / 64), (unsigned)chunks), block(32, 8);
-      colreduce_kernel<true><<<grid, block, 0, STREAM(stream)>>>(dy, dy_dtype, x, x_dtype, mean, rstd, ps, px, rows,
-                                                                (int)D, rpc);
-      VJ_LAUNCH_CHECK();
-      if (dbeta) colreduce_final_kernel<<<(unsigned)((D + 255) / 256), 256, 0, STREAM(stream)>>>(ps, dbeta, chunks, (int)D, 1);
-      if (dgamma) colreduce_final_kernel<<<(unsigned)((D + 255) / 256), 256, 0, STREAM(stream)>>>(px, dgamma, chunks, (int)D, 1);
-      VJ_LAUNCH_CHECK();
-    }
+  if (dgamma || dbeta || dbias) {
+    ln_bwd_final_kernel<<<(unsigned)((3 * D + 15) / 16), 256, 0, st>>>(part, g.grid, (int)D, dbeta, dgamma, dbias);
+    VJ_LAUNCH_CHECK();
   }
   return 0;
 }

@@ -366,6 +366,63 @@ static void stress_gemm(const char* name, int M, int N, int K, int a_mn, int b_m
   cudaFree(aux[0]); cudaFree(aux[1]); cudaFree(bad);
 }
 
+// ------------------------------------------------------------------ bandwidth-class micro benchmarks (algorithmic GB/s)
+static void bench_ln(long long rows, int D, int xdt, int ydt) {
+  const size_t xs = xdt == VJ_F32 ? 4 : 2, ys = ydt == VJ_F32 ? 4 : 2;
+  void* x = dalloc<char>((size_t)rows * D * xs);
+  void* y = dalloc<char>((size_t)rows * D * ys);
+  void* dy = dalloc<char>((size_t)rows * D * 2);
+  void* dres = dalloc<char>((size_t)rows * D * xs);
+  void* dx = dalloc<char>((size_t)rows * D * xs);
+  float* gamma = dalloc<float>(D); float* beta = dalloc<float>(D);
+  float* mean = dalloc<float>(rows); float* rstd = dalloc<float>(rows);
+  float* dg = dalloc<float>(3 * D);
+  void* scratch = dalloc<char>(vj_layernorm_bwd_scratch(rows, D));
+  if (xdt == VJ_F32) fillf((float*)x, rows * D, 1, 1.0f); else fill((bf16*)x, rows * D, 1, 1.0f);
+  fill((bf16*)dy, rows * D, 2, 1.0f);
+  if (xdt == VJ_F32) fillf((float*)dres, rows * D, 3, 1.0f); else fill((bf16*)dres, rows * D, 3, 1.0f);
+  fillf(gamma, D, 4, 1.0f); fillf(beta, D, 5, 1.0f);
+  CK(cudaMemset(dg, 0, 3 * D * 4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 20;
+  float ms;
+  for (int i = 0; i < 3; ++i) VJ(vj_layernorm_fwd(x, xdt, gamma, beta, y, ydt, mean, rstd, rows, D, 0, 1e-6f, 0));
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; ++i) VJ(vj_layernorm_fwd(x, xdt, gamma, beta, y, ydt, mean, rstd, rows, D, 0, 1e-6f, 0));
+  cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
+  double bytes = (double)rows * D * (xs + ys);
+  printf("[bench ln fwd] rows=%lld D=%d x%zu y%zu  %.1f us  %.0f GB/s\n", rows, D, xs, ys, ms * 1e3, bytes / ms * 1e-6);
+  for (int i = 0; i < 3; ++i)
+    VJ(vj_layernorm_bwd(dy, VJ_BF16, x, xdt, gamma, mean, rstd, dres, dx, xdt, dg, dg + D, dg + 2 * D, scratch, rows, D, 0));
+  cudaEventRecord(e0);
+  for (int i = 0; i < iters; ++i)
+    VJ(vj_layernorm_bwd(dy, VJ_BF16, x, xdt, gamma, mean, rstd, dres, dx, xdt, dg, dg + D, dg + 2 * D, scratch, rows, D, 0));
+  cudaEventRecord(e1); CK(cudaEventSynchronize(e1)); cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
+  bytes = (double)rows * D * (2 + 3 * xs);
+  printf("[bench ln bwd] rows=%lld D=%d (dx + dgamma/dbeta/dbias)  %.1f us  %.0f GB/s\n", rows, D, ms * 1e3, bytes / ms * 1e-6);
+  cudaFree(x); cudaFree(y); cudaFree(dy); cudaFree(dres); cudaFree(dx); cudaFree(gamma); cudaFree(beta); cudaFree(mean);
+  cudaFree(rstd); cudaFree(dg); cudaFree(scratch);
+}
+
+static void bench_colsum(long long rows, int D) {
+  bf16* x = dalloc<bf16>((size_t)rows * D);
+  float* out = dalloc<float>(D);
+  void* scratch = dalloc<char>(vj_colsum_scratch(rows, D));
+  fill(x, rows * D, 1, 1.0f);
+  CK(cudaMemset(out, 0, D * 4));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  for (int i = 0; i < 3; ++i) VJ(vj_colsum(x, VJ_BF16, out, 1, scratch, rows, D, 0));
+  cudaEventRecord(e0);
+  const int iters = 20;
+  for (int i = 0; i < iters; ++i) VJ(vj_colsum(x, VJ_BF16, out, 1, scratch, rows, D, 0));
+  cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= iters;
+  printf("[bench colsum] rows=%lld D=%d bf16  %.1f us  %.0f GB/s\n", rows, D, ms * 1e3, (double)rows * D * 2 / ms * 1e-6);
+  cudaFree(x); cudaFree(out); cudaFree(scratch);
+}
+
 #ifdef VJ_GEMM_PROFILE
 extern "C" int vj_gemm_prof_read(unsigned long long* out8, int reset);
 #endif
@@ -583,6 +640,16 @@ int main(int argc, char** argv) {
     stress_gemm("fc1 wgrad", 6144, 1408, 12096, 1, 1, VJ_EPI_OUT_F32, reps);
     stress_gemm("pred fc1 (K=384)", 36000, 1536, 384, 0, 0, VJ_EPI_BIAS | VJ_EPI_GELU | RB, reps);
     stress_gemm("ragged", 3001, 1416, 520, 0, 0, VJ_EPI_BIAS, reps);
+  }
+  if (!strcmp(what, "benchbw")) {      // bandwidth class at step shapes (B=24: target 49152 rows, context ~12096, predictor ~36000)
+    bench_ln(49152, 1408, VJ_BF16, VJ_BF16);
+    bench_ln(12096, 1408, VJ_BF16, VJ_BF16);
+    bench_ln(12096, 1024, VJ_BF16, VJ_BF16);
+    bench_ln(12096, 1280, VJ_BF16, VJ_BF16);
+    bench_ln(36000, 384, VJ_F32, VJ_BF16);
+    bench_colsum(12096, 6144);
+    bench_colsum(12096, 4224);
+    bench_colsum(36000, 1536);
   }
   if (!strcmp(what, "stressattn")) {   // back-to-back launches (CTAs of consecutive launches overlap on the SMs)
     const int reps = argc > 2 ? atoi(argv[2]) : 20;

@@ -142,26 +142,26 @@ def block_backward(h: BlockH, g: BlockG, saved, dx2, dx0, B, S, heads, hd, rope,
     dh = T((M, Hm), BF16)
     ops.gemm(d2, h.fc2_w, dh, M, Hm, D, b_mn=True, dgelu_aux=hpre, st=st)                 # dgrad fc2 * gelu'
     ops.gemm(d2, act, g.fc2_w, D, Hm, M, a_mn=True, b_mn=True, residual=g.fc2_w, st=st)   # wgrad fc2 (+=)
-    ops.colsum(d2, g.fc2_b, True, st, T)
     dln2 = T((M, D), BF16)
     ops.gemm(dh, h.fc1_w, dln2, M, D, Hm, b_mn=True, st=st)                               # dgrad fc1
     ops.gemm(dh, ln2, g.fc1_w, Hm, D, M, a_mn=True, b_mn=True, residual=g.fc1_w, st=st)   # wgrad fc1
     ops.colsum(dh, g.fc1_b, True, st, T)
     dx1 = T((M, D), dx2.dtype)
-    ops.layernorm_bwd(dln2, x1, h.n2w, mean2, rstd2, dx1, dres=dx2, dgamma=g.n2w, dbeta=g.n2b, st=st, alloc=T)
+    # norm2 backward also sums its dres = d(fc2 output) over the rows: the fc2 bias gradient
+    ops.layernorm_bwd(dln2, x1, h.n2w, mean2, rstd2, dx1, dres=dx2, dgamma=g.n2w, dbeta=g.n2b, dbias=g.fc2_b, st=st, alloc=T)
     # ---- attention: x1 = x + proj(attn(rope(qkv(LN1(x)))))
     d1 = _as_bf16(dx1, st, ws)
     datt = T((M, D), BF16)
     ops.gemm(d1, h.proj_w, datt, M, D, D, b_mn=True, st=st)
     ops.gemm(d1, att, g.proj_w, D, D, M, a_mn=True, b_mn=True, residual=g.proj_w, st=st)
-    ops.colsum(d1, g.proj_b, True, st, T)
     dqkv = T((M, 3 * D), BF16)
     _attn_bwd_segs(qkv, att, datt, lse, dqkv, segs, heads, hd, st, ws, rope)              # + fused adjoint RoPE
     dln1 = T((M, D), BF16)
     ops.gemm(dqkv, h.qkv_w, dln1, M, D, 3 * D, b_mn=True, st=st)
     ops.gemm(dqkv, ln1, g.qkv_w, 3 * D, D, M, a_mn=True, b_mn=True, residual=g.qkv_w, st=st)
     ops.colsum(dqkv, g.qkv_b, True, st, T)
-    ops.layernorm_bwd(dln1, x, h.n1w, mean1, rstd1, dx0, dres=dx1, dgamma=g.n1w, dbeta=g.n1b, st=st, alloc=T)
+    # norm1 backward: dres = d(proj output) -> proj bias gradient
+    ops.layernorm_bwd(dln1, x, h.n1w, mean1, rstd1, dx0, dres=dx1, dgamma=g.n1w, dbeta=g.n1b, dbias=g.proj_b, st=st, alloc=T)
     ws.release(mk)
     return dx0
 

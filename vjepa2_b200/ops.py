@@ -97,9 +97,12 @@ def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, bias=None, gelu=False, d
 
 # ------------------------------------------------------------------------------ LayerNorm
 def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-6, st=None):
+    """y may be wider than x ([rows, D + pad], pad % 8 == 0): the pad columns are set to 1 (bias-gradient ones-column
+    of the wgrad GEMM that reads y as its B operand)."""
     rows, D = x.shape
+    ldy = y.shape[1] if y.dim() == 2 else D
     _counting_check(C.load().vj_layernorm_fwd(x.data_ptr(), _dt(x), _p(gamma), _p(beta), y.data_ptr(), _dt(y), _p(mean),
-                                      _p(rstd), rows, D, eps, st if st is not None else stream()),
+                                      _p(rstd), rows, D, ldy, eps, st if st is not None else stream()),
             "vj_layernorm_fwd")
     return y
 
@@ -110,16 +113,17 @@ def _scratch(nbytes, device, alloc):
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres=None, dgamma=None, dbeta=None, st=None, alloc=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dres=None, dgamma=None, dbeta=None, dbias=None, st=None, alloc=None):
+    """dbias (fp32 [D], +=): column sum of dres = bias gradient of the Linear whose output the residual branch added."""
     rows, D = x.shape
     scratch = None
-    if dgamma is not None or dbeta is not None:
+    if dgamma is not None or dbeta is not None or dbias is not None:
         scratch = _scratch(C.load().vj_layernorm_bwd_scratch(rows, D), x.device, alloc)
     if dres is not None and dres.dtype != dx.dtype:
         raise TypeError("layernorm_bwd: dres must have dx's dtype")
     _counting_check(C.load().vj_layernorm_bwd(dy.data_ptr(), _dt(dy), x.data_ptr(), _dt(x), _p(gamma), mean.data_ptr(),
                                       rstd.data_ptr(), _p(dres), dx.data_ptr(), _dt(dx), _p(dgamma), _p(dbeta),
-                                      _p(scratch), rows, D, st if st is not None else stream()),
+                                      _p(dbias), _p(scratch), rows, D, st if st is not None else stream()),
             "vj_layernorm_bwd")
     return dx
 
