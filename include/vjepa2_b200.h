@@ -60,8 +60,12 @@ enum {
   VJ_EPI_RES_F32 = 32,   /* residual is fp32 (else bf16) */
   VJ_EPI_ROUND_BF16 = 64,/* round v to bf16 before gelu/residual (mirrors autocast's bf16 Linear output) */
   VJ_EPI_AUX_OUT = 128,  /* also write the pre-activation v as bf16 to aux_out */
-  VJ_EPI_ROPE = 256      /* qkv projection: apply the 3-axis RoPE map to columns < 2*rope_D (q and k thirds)
+  VJ_EPI_ROPE = 256,     /* qkv projection: apply the 3-axis RoPE map to columns < 2*rope_D (q and k thirds)
                             after bias, using rope_table[m] (vj_rope_table layout); v passes through */
+  VJ_EPI_BIAS_GRAD = 512 /* weight-gradient GEMM (A, B MN-major, fp32 out): B has 8 more columns than N, all 1.0 (ldb >=
+                            N + 8, written by vj_layernorm_fwd's padded output), so accumulator column N of row m is
+                            sum_k A[k][m] -- the bias gradient of the same Linear; bias_grad[m] += it.  Costs 8 extra
+                            MMA columns instead of a column-sum pass over A.  CTA-pair kernel only (M >= 1024). */
 };
 
 typedef struct {
@@ -81,6 +85,7 @@ typedef struct {
   const void* rope_table; /* fp16 [M][2][rope_hd] (VJ_EPI_ROPE) */
   int32_t rope_hd;        /* head dim (32, 64 or 80) */
   int32_t rope_D;         /* model width: N == 3*rope_D */
+  float* bias_grad;       /* fp32 [M] (VJ_EPI_BIAS_GRAD), accumulated */
 } vj_gemm_args;
 
 int vj_gemm(const vj_gemm_args* a, void* stream);

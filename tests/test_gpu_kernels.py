@@ -149,6 +149,26 @@ def test_gemm_pair_kernel_wgrad_accumulate(dev, Nw, Kw, tok):
     assert relerr(g, ref) < 2e-5
 
 
+@pytest.mark.parametrize("Nw,Kw,tok", [(4224, 1408, 3001), (6144, 1408, 12096), (1536, 384, 9000), (1152, 136, 700)])
+def test_gemm_wgrad_bias_gradient_from_ones_column(dev, Nw, Kw, tok):
+    """VJ_EPI_BIAS_GRAD: x carries 8 pad columns of ones (LayerNorm's padded output), so the weight-gradient GEMM
+    dW += dy^T x also returns db += sum_tok dy as accumulator column Kw -- replaces a column-sum pass over dy."""
+    from vjepa2_b200 import ops
+    dy = randn(tok, Nw, seed=1, dtype=BF16).to(dev)
+    xp = torch.ones(tok, Kw + 8, dtype=BF16, device=dev)
+    xp[:, :Kw] = randn(tok, Kw, seed=2, dtype=BF16).to(dev)
+    g0 = randn(Nw, Kw, seed=3).to(dev)
+    b0 = randn(Nw, seed=4).to(dev)
+    g, b = g0.clone(), b0.clone()
+    ops.gemm(dy, xp[:, :Kw], g, Nw, Kw, tok, a_mn=True, b_mn=True, residual=g, bias_grad=b)
+    assert relerr(g, g0 + dy.float().t() @ xp[:, :Kw].float()) < 3e-5      # fp32 accumulation over up to 12k tokens
+    assert relerr(b - b0, dy.float().sum(0)) < 3e-5
+    # the same GEMM without the option leaves identical weight-gradient bits (split-K shapes excepted: atomics order)
+    g2 = g0.clone()
+    ops.gemm(dy, xp[:, :Kw], g2, Nw, Kw, tok, a_mn=True, b_mn=True, residual=g2)
+    assert relerr(g2, g) < 1e-6
+
+
 def test_gemm_pair_and_single_cta_kernels_agree_bitwise(dev):
     """Same tile arithmetic (k-blocks of 64 in order, fp32 accumulate, identical epilogue): forcing the 1-CTA kernels
     through a fresh process-level switch is not possible in-process, so compare M = 1023 (1-CTA) with the first 1023

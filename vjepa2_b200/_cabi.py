@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libvjepa2_b200.so")
 ABI_VERSION = 3          # vj_abi_version() of the library this binding (struct layouts, prototypes) was written for
 VJ_BF16, VJ_F32 = 0, 1
 EPI_BIAS, EPI_GELU, EPI_DGELU, EPI_RESIDUAL = 1, 2, 4, 8
-EPI_OUT_F32, EPI_RES_F32, EPI_ROUND_BF16, EPI_AUX_OUT, EPI_ROPE = 16, 32, 64, 128, 256
+EPI_OUT_F32, EPI_RES_F32, EPI_ROUND_BF16, EPI_AUX_OUT, EPI_ROPE, EPI_BIAS_GRAD = 16, 32, 64, 128, 256, 512
 
 
 class GemmArgs(Structure):
@@ -27,6 +27,7 @@ class GemmArgs(Structure):
         ("bias", c_void_p), ("residual", c_void_p), ("ldr", c_int64),
         ("aux_out", c_void_p), ("aux_in", c_void_p), ("ld_aux", c_int64),
         ("rope_table", c_void_p), ("rope_hd", c_int32), ("rope_D", c_int32),
+        ("bias_grad", c_void_p),
     ]
 
 

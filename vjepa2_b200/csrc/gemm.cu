@@ -49,6 +49,8 @@ struct GemmEpi {
   const __half* rope;
   int rope_hd, rope_D;
   int flags;
+  float* bias_grad;      // VJ_EPI_BIAS_GRAD: += accumulator column n_out of every row
+  int n_out;             // output columns (the kernel's N counts the ones-column block as well)
 };
 
 template <int BN, bool AUX>
@@ -590,6 +592,7 @@ static int launch_gemm(const vj_gemm_args* g, int flags, cudaStream_t stream) {
   e.bias = g->bias; e.residual = g->residual; e.aux_in = g->aux_in;
   e.ldr = g->ldr; e.ld_aux = g->ld_aux; e.flags = flags;
   e.rope = reinterpret_cast<const __half*>(g->rope_table); e.rope_hd = g->rope_hd; e.rope_D = g->rope_D;
+  e.bias_grad = nullptr; e.n_out = (int)g->N;
 
   auto kern = gemm_kernel<BN, A_MN, B_MN, AUX>;
   static bool attr_set = false;
@@ -895,13 +898,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             } else {
               epilogue_math<false>(epi, acc, cur, col0, nlim, v, pre);
             }
+            if ((epi.flags & VJ_EPI_BIAS_GRAD) && row_ok && epi.n_out >= col0 && epi.n_out < col0 + 32) {
+              // the ones-column of B: accumulator column n_out of this row is sum_k A[k][row] (n_out % 8 == 0)
+              const int o = epi.n_out - col0;
+              const float bg = o == 0 ? v[0] : o == 8 ? v[8] : o == 16 ? v[16] : v[24];
+              atomicAdd(epi.bias_grad + row, bg);
+            }
             if (out_f32) stage_f32x32(stg_out, lane, v);
             else stage_bf16x32(stg_out, lane, hh, v);
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (reduce) tma_reduce_add_2d(&tmOut, stg_out, gcol, row0);
+            if (gcol >= epi.n_out) {}                      // the ones-block has no output columns
+            else if (reduce) tma_reduce_add_2d(&tmOut, stg_out, gcol, row0);
             else tma_store_2d(&tmOut, stg_out, gcol, row0);
             if (want_aux) tma_store_2d(&tmAux, stg_aux, gcol, row0);
             bulk_commit();
@@ -947,6 +957,8 @@ static int launch_gemm2(const vj_gemm_args* g, int flags, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<AUX>;
   constexpr int BN = Cfg::BN;
   CUtensorMap tmA, tmB, tmOut, tmAux;
+  // VJ_EPI_BIAS_GRAD: the MMAs run over N + 8 columns of B (the last 8 are the ones-block); the output keeps N
+  const int64_t Nmma = g->N + ((flags & VJ_EPI_BIAS_GRAD) ? 8 : 0);
   {
     const uint64_t dimsK[2] = {(uint64_t)g->K, (uint64_t)g->M};
     const uint64_t dimsM[2] = {(uint64_t)g->M, (uint64_t)g->K};
@@ -957,8 +969,8 @@ static int launch_gemm2(const vj_gemm_args* g, int flags, cudaStream_t stream) {
     if (r) return r;
   }
   {
-    const uint64_t dimsK[2] = {(uint64_t)g->K, (uint64_t)g->N};
-    const uint64_t dimsN[2] = {(uint64_t)g->N, (uint64_t)g->K};
+    const uint64_t dimsK[2] = {(uint64_t)g->K, (uint64_t)Nmma};
+    const uint64_t dimsN[2] = {(uint64_t)Nmma, (uint64_t)g->K};
     const uint64_t str[1] = {(uint64_t)g->ldb * 2};
     const uint32_t boxK[2] = {64, (uint32_t)BN / 2};
     const uint32_t boxN[2] = {64, GEMM_BK};
@@ -984,6 +996,7 @@ static int launch_gemm2(const vj_gemm_args* g, int flags, cudaStream_t stream) {
   e.bias = g->bias; e.residual = g->residual; e.aux_in = g->aux_in;
   e.ldr = g->ldr; e.ld_aux = g->ld_aux; e.flags = flags;
   e.rope = reinterpret_cast<const __half*>(g->rope_table); e.rope_hd = g->rope_hd; e.rope_D = g->rope_D;
+  e.bias_grad = g->bias_grad; e.n_out = (int)g->N;
 
   auto kern = gemm2_kernel<A_MN, B_MN, AUX>;
   static int pairs = 0;
@@ -992,7 +1005,7 @@ static int launch_gemm2(const vj_gemm_args* g, int flags, cudaStream_t stream) {
     pairs = max_pairs_cached(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
   }
   const int num_m = (int)((g->M + 2 * GEMM_BM - 1) / (2 * GEMM_BM));
-  const int num_n = (int)((g->N + BN - 1) / BN);
+  const int num_n = (int)((Nmma + BN - 1) / BN);
   const int tiles = num_m * num_n;
   const int num_kb = (int)((g->K + GEMM_BK - 1) / GEMM_BK);
   int splits = 1;
@@ -1020,7 +1033,7 @@ static int launch_gemm2(const vj_gemm_args* g, int flags, cudaStream_t stream) {
   at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  VJ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmAux, e, (int)g->M, (int)g->N, (int)g->K, splits));
+  VJ_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, tmAux, e, (int)g->M, (int)Nmma, (int)g->K, splits));
   return 0;
 }
 
@@ -1090,6 +1103,15 @@ extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
     VJ_CHECK(g->rope_table && (g->rope_hd == 32 || g->rope_hd == 64 || g->rope_hd == 80) && g->rope_D > 0 && g->rope_D % g->rope_hd == 0 &&
                  g->N == 3 * (int64_t)g->rope_D && g->rope_D % 16 == 0,
              "vj_gemm: bad ROPE arguments (hd=%d D=%d N=%lld)", g->rope_hd, g->rope_D, (long long)g->N);
+  }
+  if (flags & VJ_EPI_BIAS_GRAD) {
+    VJ_CHECK(g->bias_grad != nullptr, "vj_gemm: BIAS_GRAD without bias_grad pointer");
+    VJ_CHECK(g->a_mn_major && g->b_mn_major && (flags & VJ_EPI_OUT_F32) &&
+                 !(flags & (VJ_EPI_BIAS | VJ_EPI_GELU | VJ_EPI_DGELU | VJ_EPI_ROUND_BF16 | VJ_EPI_AUX_OUT | VJ_EPI_ROPE)),
+             "vj_gemm: BIAS_GRAD is a weight-gradient option (A and B MN-major, fp32 output, no other epilogue)");
+    VJ_CHECK(g->ldb >= g->N + 8, "vj_gemm: BIAS_GRAD needs 8 pad columns of ones in B (ldb=%lld, N=%lld)", (long long)g->ldb,
+             (long long)g->N);
+    VJ_CHECK(use_pair_kernel(g->M, g->N), "vj_gemm: BIAS_GRAD is only implemented in the CTA-pair kernel (M >= 1024)");
   }
   // fp32 "out += acc": residual aliases out with the same pitch -> TMA reduce-add, no read in the epilogue
   if ((flags & VJ_EPI_RESIDUAL) && g->residual == g->out) {

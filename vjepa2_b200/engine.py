@@ -102,19 +102,22 @@ def block_forward(h: BlockH, x, x_out, B, S, heads, hd, rope, save, st, ws):
         stats = A((4, M), F32)
         mean1, rstd1, mean2, rstd2 = stats[0], stats[1], stats[2], stats[3]
         hpre = A((M, Hm), BF16)
-    ln1 = A((M, D), BF16)
+    # saved LayerNorm outputs carry 8 pad columns of ones when the qkv / fc1 weight-gradient GEMMs can turn them into
+    # the bias gradients (ops.bias_grad_pad); the forward GEMMs read the [:, :D] view
+    pad = ops.bias_grad_pad(D, 3 * D, Hm) if save else 0
+    ln1 = A((M, D + pad), BF16)
     ops.layernorm_fwd(x, h.n1w, h.n1b, ln1, mean1, rstd1, 1e-6, st)
     qkv = A((M, 3 * D), BF16)
-    ops.gemm(ln1, h.qkv_w, qkv, M, 3 * D, D, bias=h.qkv_b, rope=(rope, hd, D), st=st)     # qkv + fused 3-axis RoPE
+    ops.gemm(ln1[:, :D], h.qkv_w, qkv, M, 3 * D, D, bias=h.qkv_b, rope=(rope, hd, D), st=st)     # qkv + fused 3-axis RoPE
     att = A((M, D), BF16)
     lse = A((sum(b * s for b, s in segs) * heads,), F32)
     _attn_fwd_segs(qkv, att, lse, segs, heads, hd, st)
     x1 = A((M, D), x.dtype)
     ops.gemm(att, h.proj_w, x1, M, D, D, bias=h.proj_b, residual=x, round_bf16=True, st=st)
-    ln2 = A((M, D), BF16)
+    ln2 = A((M, D + pad), BF16)
     ops.layernorm_fwd(x1, h.n2w, h.n2b, ln2, mean2, rstd2, 1e-6, st)
     act = A((M, Hm), BF16)
-    ops.gemm(ln2, h.fc1_w, act, M, Hm, D, bias=h.fc1_b, gelu=True, round_bf16=True, aux_out=hpre, st=st)
+    ops.gemm(ln2[:, :D], h.fc1_w, act, M, Hm, D, bias=h.fc1_b, gelu=True, round_bf16=True, aux_out=hpre, st=st)
     ops.gemm(act, h.fc2_w, x_out, M, D, Hm, bias=h.fc2_b, residual=x1, round_bf16=True, st=st)
     return (x, mean1, rstd1, ln1, qkv, att, lse, x1, mean2, rstd2, ln2, hpre, act) if save else None
 
@@ -144,8 +147,12 @@ def block_backward(h: BlockH, g: BlockG, saved, dx2, dx0, B, S, heads, hd, rope,
     ops.gemm(d2, act, g.fc2_w, D, Hm, M, a_mn=True, b_mn=True, residual=g.fc2_w, st=st)   # wgrad fc2 (+=)
     dln2 = T((M, D), BF16)
     ops.gemm(dh, h.fc1_w, dln2, M, D, Hm, b_mn=True, st=st)                               # dgrad fc1
-    ops.gemm(dh, ln2, g.fc1_w, Hm, D, M, a_mn=True, b_mn=True, residual=g.fc1_w, st=st)   # wgrad fc1
-    ops.colsum(dh, g.fc1_b, True, st, T)
+    padded = ln2.shape[1] > D                 # ones-columns present: the wgrad GEMM also yields the bias gradient
+    if padded:
+        ops.gemm(dh, ln2[:, :D], g.fc1_w, Hm, D, M, a_mn=True, b_mn=True, residual=g.fc1_w, bias_grad=g.fc1_b, st=st)
+    else:
+        ops.gemm(dh, ln2, g.fc1_w, Hm, D, M, a_mn=True, b_mn=True, residual=g.fc1_w, st=st)   # wgrad fc1
+        ops.colsum(dh, g.fc1_b, True, st, T)
     dx1 = T((M, D), dx2.dtype)
     # norm2 backward also sums its dres = d(fc2 output) over the rows: the fc2 bias gradient
     ops.layernorm_bwd(dln2, x1, h.n2w, mean2, rstd2, dx1, dres=dx2, dgamma=g.n2w, dbeta=g.n2b, dbias=g.fc2_b, st=st, alloc=T)
@@ -158,8 +165,11 @@ def block_backward(h: BlockH, g: BlockG, saved, dx2, dx0, B, S, heads, hd, rope,
     _attn_bwd_segs(qkv, att, datt, lse, dqkv, segs, heads, hd, st, ws, rope)              # + fused adjoint RoPE
     dln1 = T((M, D), BF16)
     ops.gemm(dqkv, h.qkv_w, dln1, M, D, 3 * D, b_mn=True, st=st)
-    ops.gemm(dqkv, ln1, g.qkv_w, 3 * D, D, M, a_mn=True, b_mn=True, residual=g.qkv_w, st=st)
-    ops.colsum(dqkv, g.qkv_b, True, st, T)
+    if padded:
+        ops.gemm(dqkv, ln1[:, :D], g.qkv_w, 3 * D, D, M, a_mn=True, b_mn=True, residual=g.qkv_w, bias_grad=g.qkv_b, st=st)
+    else:
+        ops.gemm(dqkv, ln1, g.qkv_w, 3 * D, D, M, a_mn=True, b_mn=True, residual=g.qkv_w, st=st)
+        ops.colsum(dqkv, g.qkv_b, True, st, T)
     # norm1 backward: dres = d(proj output) -> proj bias gradient
     ops.layernorm_bwd(dln1, x, h.n1w, mean1, rstd1, dx0, dres=dx1, dgamma=g.n1w, dbeta=g.n1b, dbias=g.proj_b, st=st, alloc=T)
     ws.release(mk)

@@ -3,6 +3,7 @@ function here enqueues hand-written sm_100a kernels on the current CUDA stream."
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -56,7 +57,7 @@ _gemm_args = C.GemmArgs()
 
 
 def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, bias=None, gelu=False, dgelu_aux=None, residual=None,
-         aux_out=None, round_bf16=False, rope=None, st=None):
+         aux_out=None, round_bf16=False, rope=None, bias_grad=None, st=None):
     """out[M,N] = epi(A[M,K] @ B[N,K]^T).  a/b: 2-D bf16 views whose last dim is contiguous
     (a: [M,K] or, if a_mn, [K,M]; b likewise).  out: bf16 or fp32 [M,N]."""
     g = _gemm_args
@@ -80,6 +81,9 @@ def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, bias=None, gelu=False, d
     if rope is not None:                    # (table, head_dim, D): fused 3-axis RoPE on the q/k thirds
         flags |= C.EPI_ROPE
         g.rope_table, g.rope_hd, g.rope_D = rope[0].data_ptr(), rope[1], rope[2]
+    if bias_grad is not None:               # wgrad only: b carries 8 pad columns of ones (layernorm_fwd padded output)
+        flags |= C.EPI_BIAS_GRAD
+    g.bias_grad = _p(bias_grad)
     g.a, g.b, g.out = a.data_ptr(), b.data_ptr(), out.data_ptr()
     g.M, g.N, g.K = M, N, K
     g.lda, g.ldb, g.ldo = a.stride(0), b.stride(0), out.stride(0)
@@ -93,6 +97,19 @@ def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, bias=None, gelu=False, d
     g.ld_aux = aux.stride(0) if aux is not None else 0
     _counting_check(C.load().vj_gemm(ctypes.byref(g), st if st is not None else stream()), "vj_gemm")
     return out
+
+
+def bias_grad_pad(D, *out_dims):
+    """Pad columns (0 or 8) the LayerNorm output of width D needs so that the wgrad GEMMs reading it produce their bias
+    gradients (VJ_EPI_BIAS_GRAD): only when the ones-block rides in the last, partly filled 256-column tile (no extra
+    tile) and every wgrad is large enough for the CTA-pair kernel."""
+    if D % 256 == 0 or D % 256 + 8 > 256 or any(m < 1024 for m in out_dims):
+        return 0
+    if os.environ.get("VJ_BIAS_GRAD_PAD", "1") == "0":          # A/B switch: column-sum kernels instead
+        return 0
+    if C.load().vj_gemm_set_pair_mode(-1) == 0:
+        return 0
+    return 8
 
 
 # ------------------------------------------------------------------------------ LayerNorm
