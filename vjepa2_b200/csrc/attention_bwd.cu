@@ -406,14 +406,20 @@ struct AttnBwd2Cfg {
 // exponentials per 128 x 128 tile = 1024 MUFU cycles of a ~1475-cycle math phase): 0 none (default), 1 = one pair in
 // 8, 2 = one in 4, 4 = one in 2.  Measured on B200 (VJ_ATTN_BWD_POLY): every non-zero share is 1-6 % SLOWER, i.e. the
 // phase is bound by the issue / LDS mix, not by MUFU throughput; kept as an experiment switch.
-template <int HD, int POLY>
-__global__ void __launch_bounds__(320, 1)
+// NP = compute threads per key row: each owns 128 / NP query columns of the S^T / dP^T tile (NP * 4 compute warps).
+// NP = 2 is the default; NP = 4 (16 warps, 96 registers) doubles the warps per scheduler (ncu of NP = 2 at d = 32: issue
+// slots 29 % busy, 2 warps per scheduler) and shortens the math phase, but not the tile (see launch_attn_bwd).
+template <int HD, int POLY, int NP>
+__global__ void __launch_bounds__(NP * 128 + 64, 1)
 attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__ TMapPair tmDO,
                  const __grid_constant__ CUtensorMap tmDQ, const float* __restrict__ lse,
                  const float* __restrict__ delta, bf16* __restrict__ dqkv, const __half* __restrict__ rope, int S, int H,
                  int D, float scale, float scale_log2, int n_kt, int n_items) {
   using Cfg = AttnBwd2Cfg<HD>;
-  constexpr int HO = HD / 2;                               // output columns per compute thread
+  constexpr int HO = HD / NP;                              // output columns per compute thread
+  constexpr int CW = 128 / NP;                             // S^T / dP^T columns per compute thread
+  constexpr int NCT = NP * 128;                            // compute threads
+  constexpr int W_PROD = NP * 4, W_MMA = NP * 4 + 1;
   constexpr int NST = Cfg::QDO_STAGES;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -450,12 +456,12 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
     mbar_init(kv_empty, 1);
     for (int i = 0; i < NST; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(sdp_free, 8);
-    mbar_init(pds_full, 8);
+    mbar_init(sdp_free, NP * 4);
+    mbar_init(pds_full, NP * 4);
     mbar_init(dq_full, 1);
     mbar_fence_init();
   }
-  if (warp == 8) {
+  if (warp == W_PROD) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -464,7 +470,7 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == W_PROD) {
     // ---------------------------------------------------------------- TMA producer
     if (elect_one()) {
       tma_prefetch_desc(&tmQKV.m[0]);
@@ -486,7 +492,7 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // ---------------------------------------------------------------- MMA issuer
     //   S,dP(0) | sdp_free(0): S,dP(1) | pds_full(0): dV,dK,dQ(0) | sdp_free(1): S,dP(2) | pds_full(1): dV,dK,dQ(1) ...
     // (at the last tile of an item the order flips: the next item's S,dP need its K, V, whose smem is only
@@ -542,12 +548,14 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
   } else {
     // ---------------------------------------------------------------- compute warps
     const int r = threadIdx.x & 127;                        // key row == TMEM lane
-    const int half = threadIdx.x >> 7;                      // query columns [64*half, 64*half + 64)
+    const int part = threadIdx.x >> 7;                      // query columns [CW*part, CW*part + CW)
     const int lane = threadIdx.x & 31;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const uint32_t s_col = smem_u32(smem + Cfg::OFF_LSE);
-    const uint32_t pt_row = smem_u32(sPT) + half * 16384 + r * 128;     // this thread's 64 columns = atom `half`
-    const uint32_t ds_row = smem_u32(sDS) + half * 16384 + r * 128;
+    // this thread's CW columns of the bf16 P^T / dS^T tiles: 64-column atoms of 128-byte rows, 16-byte chunks
+    const int pds_atom = (part * CW) >> 6, pds_cb = ((part * CW) & 63) >> 3;
+    const uint32_t pt_row = smem_u32(sPT) + pds_atom * 16384 + r * 128;
+    const uint32_t ds_row = smem_u32(sDS) + pds_atom * 16384 + r * 128;
     const int swz = r & 7;
     const uint64_t sc2 = f32x2_pack(scale_log2, scale_log2), s2 = f32x2_pack(scale, scale);
     long long bp2 = 0, bp3 = 0, bp4 = 0, bp5 = 0, bp6 = 0, bp7 = 0, bp8 = 0, bp1 = 0, bp10 = 0, bp11 = 0, bp12 = 0, bp13 = 0;
@@ -558,11 +566,11 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
     // dQ tile (TMEM) -> fp32 staging tile; lane r == query row r of the tile
     auto stage_dq = [&]() {
       uint32_t o[HO];
-      tmem_ld_n<HO>(lane_addr + Cfg::COL_DQ + half * HO, o);
+      tmem_ld_n<HO>(lane_addr + Cfg::COL_DQ + part * HO, o);
       tmem_ld_wait();
-      // 128-byte swizzled atoms of 32 fp32: HD = 64 -> atom = half (8 chunks); HD = 32 -> one atom, 4 chunks each
-      const uint32_t rowp = smem_u32(sDQ) + (HO == 32 ? half * 16384 : 0) + r * 128;
-      const int cbase = HO == 32 ? 0 : half * 4;
+      // 128-byte swizzled atoms of 32 fp32 columns; this thread's HO columns start at column part * HO
+      const uint32_t rowp = smem_u32(sDQ) + ((part * HO) >> 5) * 16384 + r * 128;
+      const int cbase = ((part * HO) & 31) >> 2;
 #pragma unroll
       for (int u = 0; u < HO / 4; ++u)
         st_shared_v4(rowp + (((cbase + u) ^ swz) << 4), o[u * 4], o[u * 4 + 1], o[u * 4 + 2], o[u * 4 + 3]);
@@ -586,7 +594,7 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
       // (fetch only issues the loads -- no arithmetic on the values, an in-order warp would stall on it)
       float col_l = 0.f, col_d = 0.f;
       auto fetch_cols = [&](int j) {
-        if (half == 0 && j < n_q) {
+        if (part == 0 && j < n_q) {
           const int q = j * Cfg::BT + r;
           if (q < S) {
             col_l = __ldg(lse_bh + q);
@@ -598,7 +606,7 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
         }
       };
       auto put_cols = [&](int j, int Gj) {
-        if (half == 0 && j < n_q) {
+        if (part == 0 && j < n_q) {
           const uint32_t dst = s_col + (Gj & 1) * 1024;
           st_shared_f32(dst + r * 4, -col_l);
           st_shared_f32(dst + 512 + r * 4, -col_d * scale);
@@ -607,7 +615,7 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
       BP_T0(c13);
       fetch_cols(0);
       put_cols(0, G);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
       BP_ADD(bp13, c13);
       for (int i = 0; i < n_q; ++i, ++G) {
         const uint32_t s_par = s_col + (G & 1) * 1024;
@@ -617,11 +625,12 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
         if (i == 0) { BP_ADD(bp1, c2); } else { BP_ADD(bp2, c2); }
         tc_fence_after();
         BP_T0(c3);
-        uint32_t sv[64], dv[64];
-        tmem_ld32(lane_addr + Cfg::COL_ST + half * 64, reinterpret_cast<uint32_t(&)[32]>(sv[0]));
-        tmem_ld32(lane_addr + Cfg::COL_ST + half * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
-        tmem_ld32(lane_addr + Cfg::COL_DPT + half * 64, reinterpret_cast<uint32_t(&)[32]>(dv[0]));
-        tmem_ld32(lane_addr + Cfg::COL_DPT + half * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(dv[32]));
+        uint32_t sv[CW], dv[CW];
+#pragma unroll
+        for (int c = 0; c < CW; c += 32) {
+          tmem_ld32(lane_addr + Cfg::COL_ST + part * CW + c, reinterpret_cast<uint32_t(&)[32]>(sv[c]));
+          tmem_ld32(lane_addr + Cfg::COL_DPT + part * CW + c, reinterpret_cast<uint32_t(&)[32]>(dv[c]));
+        }
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
@@ -631,12 +640,12 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
         // P = exp2(s*scale*log2e - lse), dS = P * (dP - delta) * scale, on packed fp32 pairs.  Rows of keys >= S
         // and columns of queries >= S need no masking: their K / V / Q / dO rows are TMA zero-fill and lse = +inf
         // there, so every product they reach is an exact zero or lands in a dK / dV row that is never stored.
-        uint32_t pp[32], dd[32];
+        uint32_t pp[CW / 2], dd[CW / 2];
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
+        for (int j = 0; j < CW; j += 4) {
           uint32_t nl[4], nd[4];
-          ld_shared_v4(s_par + (half * 64 + j) * 4, nl);
-          ld_shared_v4(s_par + 512 + (half * 64 + j) * 4, nd);
+          ld_shared_v4(s_par + (part * CW + j) * 4, nl);
+          ld_shared_v4(s_par + 512 + (part * CW + j) * 4, nd);
 #pragma unroll
           for (int e = 0; e < 4; e += 2) {
             const uint64_t x = f32x2_fma(f32x2_pack(__uint_as_float(sv[j + e]), __uint_as_float(sv[j + e + 1])), sc2,
@@ -668,7 +677,7 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
           BP_T0(c8);
           put_cols(i + 1, G + 1);
           if (threadIdx.x == 128) bulk_wait_read0_bwd();
-          asm volatile("bar.sync 1, 256;" ::: "memory");
+          asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
           BP_ADD(bp8, c8);
         }
         if (i > 0) {
@@ -682,11 +691,11 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
           BP_ADD(bp6, c6);
         }
         BP_T0(c7);
-        // 8 x 16-byte chunks per buffer: chunk u of this thread's 128-byte row lands at u ^ (r & 7)
+        // CW / 8 16-byte chunks per buffer: chunk c of a 128-byte row lands at c ^ (r & 7)
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          st_shared_v4(pt_row + ((u ^ swz) << 4), pp[u * 4], pp[u * 4 + 1], pp[u * 4 + 2], pp[u * 4 + 3]);
-          st_shared_v4(ds_row + ((u ^ swz) << 4), dd[u * 4], dd[u * 4 + 1], dd[u * 4 + 2], dd[u * 4 + 3]);
+        for (int u = 0; u < CW / 8; ++u) {
+          st_shared_v4(pt_row + (((pds_cb + u) ^ swz) << 4), pp[u * 4], pp[u * 4 + 1], pp[u * 4 + 2], pp[u * 4 + 3]);
+          st_shared_v4(ds_row + (((pds_cb + u) ^ swz) << 4), dd[u * 4], dd[u * 4 + 1], dd[u * 4 + 2], dd[u * 4 + 3]);
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -695,7 +704,7 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
         BP_ADD(bp7, c7);
         if (i > 0) {
           BP_T0(c9);
-          asm volatile("bar.sync 2, 256;" ::: "memory");   // every thread's part of the staged dQ tile is fenced
+          asm volatile("bar.sync 2, %0;" ::"n"(NCT) : "memory");   // every thread's part of the staged dQ tile is fenced
           if (threadIdx.x == 128) reduce_dq(i - 1);        // (the thread that waits on the bulk group above)
           BP_ADD(bp8, c9);
         }
@@ -708,25 +717,25 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
       tc_fence_after();
       constexpr int NV = HO / 8;
       uint32_t a[HO], c[HO];
-      tmem_ld_n<HO>(lane_addr + Cfg::COL_DK + half * HO, a);
-      tmem_ld_n<HO>(lane_addr + Cfg::COL_DV + half * HO, c);
+      tmem_ld_n<HO>(lane_addr + Cfg::COL_DK + part * HO, a);
+      tmem_ld_n<HO>(lane_addr + Cfg::COL_DV + part * HO, c);
       tmem_ld_wait();
       BP_T0(c12);
       if (threadIdx.x == 128) bulk_wait_read0_bwd();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory");
       BP_ADD(bp12, c12);
       stage_dq();
       tc_fence_before();                                    // the next item's MMAs overwrite dQ / dK / dV in TMEM
       // (fence + barrier come BEFORE the dK / dV global stores: the proxy fence is a full MEMBAR and would wait
       //  for those stores to be acknowledged)
       fence_proxy_async_smem();
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      asm volatile("bar.sync 2, %0;" ::"n"(NCT) : "memory");
       if (threadIdx.x == 128) reduce_dq(n_q - 1);
       const int key = k0 + r;
       if (key < S) {
-        bf16* dk_row = dqkv + ((long long)b * S + key) * 3 * D + D + h * HD + half * HO;
+        bf16* dk_row = dqkv + ((long long)b * S + key) * 3 * D + D + h * HD + part * HO;
         bf16* dv_row = dk_row + D;
-        const __half* tr = rope ? rope + ((long long)b * S + key) * 2 * HD + half * HO : nullptr;
+        const __half* tr = rope ? rope + ((long long)b * S + key) * 2 * HD + part * HO : nullptr;
 #pragma unroll
         for (int jj = 0; jj < NV; ++jj) {
           const int j = jj * 8;
@@ -772,7 +781,7 @@ attn_bwd2_kernel(const __grid_constant__ TMapPair tmQKV, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  if (warp == W_PROD) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
 template <int HD>
@@ -823,20 +832,30 @@ static int launch_attn_bwd(const void* qkv, const void* out, const void* dout, c
       const char* e = getenv("VJ_ATTN_BWD_POLY");
       poly = (e && e[0] >= '0' && e[0] <= '4') ? e[0] - '0' : 0;   // measured: no share wins here (profiles/)
     }
-    auto kern = poly == 0 ? attn_bwd2_kernel<HD, 0> : poly == 1 ? attn_bwd2_kernel<HD, 1>
-              : poly <= 3 ? attn_bwd2_kernel<HD, 2> : attn_bwd2_kernel<HD, 4>;
-    static bool attr_set[5] = {false, false, false, false, false};
-    if (!attr_set[poly]) {
+    static int parts = -1;
+    if (parts < 0) {
+      // compute threads per key row: 2 (8 warps, default) or 4 (16 warps).  Measured on B200 (profiles/r02m_*): the math
+      // phase drops from ~1400 to ~1160 cycles per 128 x 128 tile (MUFU floor 1024) but barriers and waits grow by as
+      // much: 0.586 vs 0.576 ms at d = 32, S = 1448 -- the phases are serialised by the tile barriers, not by warps
+      const char* e = getenv("VJ_ATTN_BWD_PARTS");
+      parts = (e && e[0] == '4') ? 4 : 2;
+    }
+    auto kern = parts == 4 ? (poly == 0 ? attn_bwd2_kernel<HD, 0, 4> : poly == 1 ? attn_bwd2_kernel<HD, 1, 4>
+                              : poly <= 3 ? attn_bwd2_kernel<HD, 2, 4> : attn_bwd2_kernel<HD, 4, 4>)
+                           : (poly == 0 ? attn_bwd2_kernel<HD, 0, 2> : poly == 1 ? attn_bwd2_kernel<HD, 1, 2>
+                              : poly <= 3 ? attn_bwd2_kernel<HD, 2, 2> : attn_bwd2_kernel<HD, 4, 2>);
+    static bool attr_set[2][5] = {{false, false, false, false, false}, {false, false, false, false, false}};
+    if (!attr_set[parts == 4][poly]) {
       VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg2::SMEM_BYTES));
-      attr_set[poly] = true;
+      attr_set[parts == 4][poly] = true;
     }
     const int n_kt = (S + Cfg2::BT - 1) / Cfg2::BT;
     const long long n_items = (long long)n_kt * H * B;
     VJ_CHECK(n_items < (1ll << 30), "vj_attn_bwd: too many (key tile, head, sample) work items");
     const int pgrid = (int)(n_items < sm_count() ? n_items : sm_count());      // persistent: one CTA per SM
-    kern<<<pgrid, 320, Cfg2::SMEM_BYTES, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, reinterpret_cast<bf16*>(dqkv),
-                                                  reinterpret_cast<const __half*>(rope), S, H, D, scale,
-                                                  scale * 1.4426950408889634f, n_kt, (int)n_items);
+    kern<<<pgrid, parts * 128 + 64, Cfg2::SMEM_BYTES, stream>>>(tmQKV, tmDO, tmDQ, lse, delta, reinterpret_cast<bf16*>(dqkv),
+                                                                reinterpret_cast<const __half*>(rope), S, H, D, scale,
+                                                                scale * 1.4426950408889634f, n_kt, (int)n_items);
   }
   VJ_LAUNCH_CHECK();
   {

@@ -89,8 +89,10 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 }
 template <int N>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
-  static_assert(N == 16 || N == 32 || N == 40, "unsupported column count");
-  if constexpr (N == 16) {
+  static_assert(N == 8 || N == 16 || N == 32 || N == 40, "unsupported column count");
+  if constexpr (N == 8) {
+    tmem_ld8(taddr, r);
+  } else if constexpr (N == 16) {
     tmem_ld16(taddr, r);
   } else if constexpr (N == 32) {
     tmem_ld32(taddr, r);
@@ -106,8 +108,10 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
 }
 template <int N>
 __device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]) {
-  static_assert(N == 16 || N == 32 || N == 40, "unsupported column count");
-  if constexpr (N == 16) {
+  static_assert(N == 8 || N == 16 || N == 32 || N == 40, "unsupported column count");
+  if constexpr (N == 8) {
+    tmem_ld8(taddr, r);
+  } else if constexpr (N == 16) {
     tmem_st16(taddr, r);
   } else if constexpr (N == 32) {
     tmem_st32(taddr, r);
