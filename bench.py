@@ -530,6 +530,47 @@ def main():
                    h2d_gbs_measured=h2d_gbs,
                    note="H2D of step i+1 overlaps compute of step i (side stream, pinned host memory)")
 
+    # ---- e2e with the DEVICE-side mask collator (csrc/maskgen.cu): same public API, same mask draws (RNG-call-identical to
+    #      the host sampler: checked below), but the index tensors are produced on the GPU one step ahead; only the
+    #      clips cross PCIe.  Reported next to `e2e`, never instead of it.
+    if n_e2e:
+        from vjepa2_b200.masks import DeviceMaskCollator
+        base = args.warmup
+        dmc = DeviceMaskCollator(cfgs_mask=MASK_CFG, dataset_fpcs=[FRAMES], crop_size=(CROP, CROP), patch_size=(PATCH, PATCH),
+                                 tubelet_size=TUB, device=dev)
+        torch.manual_seed(239 + (rank if args.rank_local_masks else 0))
+        dmc.seed_from_torch()
+        for _ in range(base):                                    # replay the draws of the warm-up steps
+            dmc.draw(FRAMES, B)
+        chk_e, chk_p = dmc.draw(FRAMES, B)
+        same = all(torch.equal(a.cpu(), b) for a, b in zip(chk_e + chk_p, masks_host[base][0] + masks_host[base][1]))
+        if not same:
+            raise SystemExit("bench.py: device-side mask collator diverged from the host sampler")
+        feeder2 = T.HostFeeder(dev)
+        barrier()
+        t_start = time.perf_counter()
+        dmc.enqueue(FRAMES, B)                                   # draw base + 1 ... (the check above consumed draw `base`)
+        feeder2.prefetch([clips_host], [[]], [[]])
+        for i in range(n_e2e):
+            c, _, _ = feeder2.get()
+            me_d, mp_d = dmc.collect()
+            if i + 1 < n_e2e:
+                dmc.enqueue(FRAMES, B)
+                feeder2.prefetch([clips_host], [[]], [[]])
+            l, _, _ = step.step(c, [me_d], [mp_d])
+            feeder2.release()
+            _ = float(l.item())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t_start
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e["device_mask_collator"] = dict(
+            value=world * B * n_e2e / float(tt.item()), unit="clips/s", ms_per_step=1e3 * float(tt.item()) / n_e2e,
+            h2d_bytes_per_step=clips_host.numel() * 4, d2h_bytes_per_step=4 + 16,
+            note="masks drawn on the GPU by vj_mask_collate one step ahead (bit-identical to the host sampler, checked); "
+                 "D2H = loss + the four K counts")
+
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): per-launch CUDA events, one instrumented step
     #      (every rank runs the step -- it contains the gradient all-reduce -- rank 0 instruments it)
     import vjepa2_b200.engine as eng

@@ -346,7 +346,9 @@ def test_wrappers_fan_out_protocol():
 def _header_struct_fields(name):
     txt = open(os.path.join(ROOT, "include", "vjepa2_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    body = re.search(r"typedef\s+struct\s*\{(.*?)\}\s*" + name + r"\s*;", txt, flags=re.S).group(1)
+    end = re.search(r"\}\s*" + name + r"\s*;", txt).start()
+    start = [m.end() for m in re.finditer(r"typedef\s+struct\s*\{", txt[:end])][-1]     # the struct that closes there
+    body = txt[start:end]
     fields = []
     for decl in body.split(";"):
         decl = decl.strip()
@@ -380,6 +382,36 @@ def test_gemm_args_struct_matches_header_field_for_field():
     pos = [doc.find(f'("{n}"') for n, _ in got]
     assert all(p >= 0 for p in pos) and pos == sorted(pos), "INTEGRATION.md GemmArgs snippet is out of sync"
     assert _cabi.ABI_VERSION == 3
+
+
+def test_mask_spec_struct_matches_header_field_for_field():
+    import ctypes
+    from vjepa2_b200 import _cabi
+    want = _header_struct_fields("vj_mask_spec")
+    got = _cabi.MaskSpec._fields_
+    assert [n for n, _ in want] == [n for n, _ in got]
+    for (n, ctype), (_, ct) in zip(want, got):
+        assert ct is {"int32_t": ctypes.c_int32, "double": ctypes.c_double}[ctype], n
+    assert _cabi.MASK_RNG_WORDS == 626 and ctypes.sizeof(_cabi.PtrList) == 8 * _cabi.MAX_PEERS
+    hdr = open(os.path.join(ROOT, "include", "vjepa2_b200.h")).read()
+    assert "#define VJ_MASK_RNG_WORDS 626" in hdr and f"#define VJ_MAX_PEERS {_cabi.MAX_PEERS}" in hdr
+
+
+def test_device_mask_collator_rng_state_conversion_round_trips():
+    """torch.get_rng_state() <-> the 626 words vj_mask_collate keeps on the device (host-side plumbing, no GPU)."""
+    from vjepa2_b200 import masks as M
+    torch.manual_seed(5)
+    for _ in range(700):                                  # cross a refill of the 624-word state
+        torch.randint(0, 9, (1,))
+    st = torch.get_rng_state()
+    w = M._mt_words_from_torch_state(st)
+    assert w.numel() == 626 and w.dtype == torch.int32
+    assert torch.equal(M._torch_state_from_mt_words(w, st), st)
+    # the words really are the generator: restoring them into a scrambled state reproduces the stream
+    want = [int(torch.randint(0, 1000, (1,))) for _ in range(5)]
+    torch.manual_seed(99)
+    torch.set_rng_state(M._torch_state_from_mt_words(w, torch.get_rng_state()))
+    assert [int(torch.randint(0, 1000, (1,))) for _ in range(5)] == want
 
 
 def test_stale_library_abi_is_rejected(monkeypatch):
