@@ -156,12 +156,14 @@ def test_train_step_vs_oracle_and_golden(dev, golden):
         if k.startswith("step.genc."):
             p = dict(enc.named_parameters())[k[len("step.genc."):]]
             got = efs.grad_view(efs.g32, p) / 65536.0
-            # 1-D parameters (LN affine, biases) are long cancelling sums of bf16 terms: 5e-2; matrices: 3e-2
-            assert relerr(got, v) < (5e-2 if v.dim() == 1 else 3e-2), (k, relerr(got, v))
+            # against the fp32 reference; measured on B200: <= 3.0e-2 (1-D: long cancelling sums of bf16 terms) and
+            # <= 2.8e-2 (matrices) at this toy width -- the bf16-autocast reference itself is 1.5-1.8e-2 off fp32 at full
+            # width, where ours is 1.0-1.1e-2 (tests/test_gpu_fullwidth.py, profiles/r02n_fullwidth_parity.json)
+            assert relerr(got, v) < 3.5e-2, (k, relerr(got, v))
         if k.startswith("step.gpred."):
             p = dict(pred.named_parameters())[k[len("step.gpred."):]]
             got = pfs.grad_view(pfs.g32, p) / 65536.0
-            assert relerr(got, v) < (5e-2 if v.dim() == 1 else 3e-2), (k, relerr(got, v))
+            assert relerr(got, v) < 3.5e-2, (k, relerr(got, v))
 
     loss1, _, _ = step.step(cd, med, mpd)
     ref1 = O.train_step(st, clips, me, mp)
@@ -177,7 +179,7 @@ def test_train_step_vs_oracle_and_golden(dev, golden):
             # Adam's first updates are ~lr*sign(g): elements whose |g| is below the bf16 noise floor may flip,
             # so the UPDATE is only loosely comparable; the weights themselves are tight.
             upd, upd_ref = sd_e[n].cpu() - w0_enc[n], v - w0_enc[n]
-            assert relerr(upd, upd_ref) < 0.6, (k, relerr(upd, upd_ref))
+            assert relerr(upd, upd_ref) < 0.2, (k, relerr(upd, upd_ref))      # measured <= 0.11
         if k.startswith("step.after.tgt."):
             n = k[len("step.after.tgt."):]
             assert relerr(sd_t[n], v) < 1e-2, k
@@ -356,7 +358,7 @@ def test_checkpoint_moments_vs_reference_golden(dev, golden_infer):
     for k, v in golden_infer.items():
         if k.startswith("opt.enc.exp_avg_sq."):
             got = sd["state"][idx[k[len("opt.enc.exp_avg_sq."):]]]["exp_avg_sq"]
-            assert relerr(got, v) < 1e-1, (k, relerr(got, v))          # squares: twice the gradient tolerance
+            assert relerr(got, v) < 6e-2, (k, relerr(got, v))          # squares: twice the gradient error (measured 2.8e-2)
         elif k.startswith("opt.enc.exp_avg."):
             # two bf16-noise gradients (<= 3e-2 / 5e-2 each, the second one at slightly different weights)
             got = sd["state"][idx[k[len("opt.enc.exp_avg."):]]]["exp_avg"]
