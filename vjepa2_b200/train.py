@@ -80,6 +80,16 @@ class GradBucketer:
         self._works = []
 
 
+class _NoReducer:
+    """VJ_DDP_COMM=none: measures what the replicas cost WITHOUT any gradient exchange (never a training mode)."""
+
+    def submit(self, flat, start, end):
+        pass
+
+    def wait(self):
+        pass
+
+
 class PeerGradReducer:
     """Gradient all-reduce (train.py:279-281) over peer-mapped memory with the COPY ENGINES doing the transfers.
 
@@ -353,11 +363,12 @@ class JepaTrainStep:
         # gradient all-reduce transport: "peer" = copy engines over peer-mapped symmetric memory (PeerGradReducer, the
         # default on CUDA with world > 1), "nccl" = torch.distributed all_reduce (GradBucketer; also the gloo path on CPU)
         self.grad_comm = os.environ.get("VJ_DDP_COMM", "peer") if (self.world > 1 and dev.type == "cuda") else "nccl"
-        if self.grad_comm not in ("peer", "nccl"):
-            raise ValueError("VJ_DDP_COMM must be 'peer' or 'nccl'")
+        if self.grad_comm not in ("peer", "nccl", "none"):
+            raise ValueError("VJ_DDP_COMM must be 'peer' or 'nccl' ('none' = no gradient exchange at all: a timing "
+                             "diagnostic that lets the replicas diverge)")
         # bucket size: per-block ranges are merged up to this many bytes (NCCL: one bucket per block; the peer path
         # pays two cross-GPU barriers per bucket, so it takes larger ones)
-        self.bucket_bytes = int(self._bucket_mb if self._bucket_mb is not None else (192 if self.grad_comm == "peer" else 0)) << 20
+        self.bucket_bytes = int(self._bucket_mb if self._bucket_mb is not None else (64 if self.grad_comm == "peer" else 0)) << 20
         self.peer = None
         if self.grad_comm == "peer":
             if self.enc_rt.fs.g32 is not None or self.pred_rt.fs.g32 is not None:
@@ -431,6 +442,8 @@ class JepaTrainStep:
 
     # ------------------------------------------------------------------------------------------
     def _reducer(self):
+        if self.grad_comm == "none":
+            return _NoReducer()
         return self.peer if self.peer is not None else self.bucketer
 
     def _bucket_hook(self, efs):
