@@ -213,6 +213,8 @@ int vj_adam_prepare(float* bias_c, int32_t* skipped, const float* found_inf, int
  * `growth` every `interval` clean steps; writes inv_scale = 1/(scale*world), clears found_inf. */
 int vj_scaler_update(float* scale, float* inv_scale, int32_t* growth_tracker, float* found_inf, float growth,
                      float backoff, int interval, float world, void* stream);
+/* p[0..n) = value (optimizer.zero_grad() of the flat gradient buffers, train.py:454; loss accumulator reset) */
+int vj_fill_f32(float* p, int64_t n, float value, void* stream);
 /* fp32 -> bf16 flat cast (weight shadow refresh) */
 int vj_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
 

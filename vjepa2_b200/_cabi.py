@@ -86,6 +86,7 @@ SIGNATURES = {
     "vj_adam_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_int, ctypes.c_double, ctypes.c_double, c_void_p]),
     "vj_scaler_update": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_int, c_float,
                                  c_void_p]),
+    "vj_fill_f32": (c_int, [c_void_p, c_int64, c_float, c_void_p]),
     "vj_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "vj_mask_collate_scratch": (c_size_t, [POINTER(MaskSpec), c_int64]),
     "vj_mask_collate": (c_int, [c_void_p, POINTER(MaskSpec), ctypes.c_uint32, c_int64, c_void_p, c_void_p, c_void_p,

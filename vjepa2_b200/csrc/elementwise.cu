@@ -1243,6 +1243,24 @@ extern "C" int vj_adam_prepare(float* bias_c, int32_t* skipped, const float* fou
   return 0;
 }
 
+__global__ void __launch_bounds__(256) fill_f32_kernel(float* __restrict__ p, long long n, float v) {
+  const long long n4 = n >> 2;
+  const float4 v4 = make_float4(v, v, v, v);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) reinterpret_cast<float4*>(p)[i] = v4;
+  const long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+extern "C" int vj_fill_f32(float* p, int64_t n, float value, void* stream) {
+  VJ_CHECK(p != nullptr && n >= 0, "vj_fill_f32: bad arguments");
+  VJ_CHECK((reinterpret_cast<uintptr_t>(p) & 15) == 0, "vj_fill_f32: pointer must be 16-byte aligned");
+  if (n == 0) return 0;
+  fill_f32_kernel<<<flat_grid(n / 4 + 1), 256, 0, STREAM(stream)>>>(p, n, value);
+  VJ_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int vj_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
   VJ_CHECK(src && dst && n > 0, "vj_cast_f32_bf16: bad arguments");
   cast_kernel<<<flat_grid(n / 4), 256, 0, STREAM(stream)>>>(src, reinterpret_cast<bf16*>(dst), n / 4, n);

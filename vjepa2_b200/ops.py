@@ -311,6 +311,12 @@ def scaler_update(scale, inv_scale, growth_tracker, found_inf, world=1.0, growth
                                       st if st is not None else stream()), "vj_scaler_update")
 
 
+def fill_f32(t, value=0.0, st=None):
+    """t[...] = value for a contiguous fp32 tensor (zero_grad of the flat gradient buffers)."""
+    _counting_check(C.load().vj_fill_f32(t.data_ptr(), t.numel(), float(value), st if st is not None else stream()), "vj_fill_f32")
+    return t
+
+
 def cast_f32_bf16(src, dst, st=None):
     _counting_check(C.load().vj_cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(),
                                       st if st is not None else stream()), "vj_cast_f32_bf16")

@@ -536,9 +536,9 @@ class JepaTrainStep:
             if fs._versions is None:                              # load_state_dict since the last step: masters changed
                 fs.refresh_shadows()
         self._set_frozen_mask_tokens(len(clips))
-        efs.g32.zero_()                                           # optimizer.zero_grad() (train.py:454)
-        pfs.g32.zero_()
-        self.loss_accum.zero_()
+        ops.fill_f32(efs.g32, 0.0, st)                            # optimizer.zero_grad() (train.py:454)
+        ops.fill_f32(pfs.g32, 0.0, st)
+        ops.fill_f32(self.loss_accum, 0.0, st)
         ws = self.ws
         ws.reset()
         n_pairs = sum(len(m) for m in masks_enc)
