@@ -268,6 +268,125 @@ __device__ __forceinline__ void epilogue_math(const GemmEpi& e, const uint32_t (
   }
 }
 
+// ---------------------------------------------------------------- 16-column epilogue unit (16-epilogue-warp variant)
+// Half the registers of the 32-column unit (accumulator 16 + results 16 + pre-activation 16 + side operands 16), so
+// that 16 epilogue warps fit the 120 registers setmaxnreg can give them (see Gemm2Cfg).
+//   bf16 residual -> v[0..1];  fp32 residual -> v[0..3];  bf16 dGELU operand -> v[2..3];  RoPE cos -> v[0..1], sin -> v[2..3]
+struct EpiSide16 {
+  uint4 v[4];
+};
+
+__device__ __forceinline__ void epilogue_fetch16(const GemmEpi& e, EpiSide16& s, long long row, int col0, int N) {
+  const int flags = e.flags;
+  if (flags & VJ_EPI_RESIDUAL) {
+    if (flags & VJ_EPI_RES_F32) {
+      const float* rp = reinterpret_cast<const float*>(e.residual) + row * e.ldr + col0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (col0 + i * 4 < N) s.v[i] = *reinterpret_cast<const uint4*>(rp + i * 4);
+    } else {
+      const bf16* rp = reinterpret_cast<const bf16*>(e.residual) + row * e.ldr + col0;
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        if (col0 + i * 8 < N) s.v[i] = *reinterpret_cast<const uint4*>(rp + i * 8);
+    }
+  }
+  if (flags & VJ_EPI_DGELU) {
+    const bf16* ap = reinterpret_cast<const bf16*>(e.aux_in) + row * e.ld_aux + col0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (col0 + i * 8 < N) s.v[2 + i] = *reinterpret_cast<const uint4*>(ap + i * 8);
+  }
+  if ((flags & VJ_EPI_ROPE) && col0 < N && col0 < 2 * e.rope_D) {
+    const __half* tr = e.rope + row * 2 * e.rope_hd + (col0 % e.rope_D) % e.rope_hd;     // a 16-column unit never straddles a head
+    s.v[0] = *reinterpret_cast<const uint4*>(tr);
+    s.v[1] = *reinterpret_cast<const uint4*>(tr + 8);
+    s.v[2] = *reinterpret_cast<const uint4*>(tr + e.rope_hd);
+    s.v[3] = *reinterpret_cast<const uint4*>(tr + e.rope_hd + 8);
+  }
+}
+
+template <bool WANT_PRE>
+__device__ __forceinline__ void epilogue_math16(const GemmEpi& e, const uint32_t (&acc)[16], const EpiSide16& s, int col0,
+                                                int N, float (&v)[16], float (&pre)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(acc[i]);
+  const int flags = e.flags;
+  if (flags & VJ_EPI_BIAS) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      if (col0 + i < N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + col0 + i));
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    }
+  }
+  if ((flags & VJ_EPI_ROPE) && col0 < N && col0 < 2 * e.rope_D) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = bf16_round(v[i]);
+    rope_pairs8(v, s.v[0], s.v[2]);
+    rope_pairs8(v + 8, s.v[1], s.v[3]);
+  }
+  if (WANT_PRE) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pre[i] = v[i];
+  }
+  if (flags & VJ_EPI_ROUND_BF16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = bf16_round(v[i]);
+  }
+  if (flags & VJ_EPI_GELU) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i]);
+  }
+  if (flags & VJ_EPI_DGELU) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint4 u = s.v[2 + i];
+      v[i * 8] *= dgelu_fast(bf16_lo(u.x)); v[i * 8 + 1] *= dgelu_fast(bf16_hi(u.x));
+      v[i * 8 + 2] *= dgelu_fast(bf16_lo(u.y)); v[i * 8 + 3] *= dgelu_fast(bf16_hi(u.y));
+      v[i * 8 + 4] *= dgelu_fast(bf16_lo(u.z)); v[i * 8 + 5] *= dgelu_fast(bf16_hi(u.z));
+      v[i * 8 + 6] *= dgelu_fast(bf16_lo(u.w)); v[i * 8 + 7] *= dgelu_fast(bf16_hi(u.w));
+    }
+  }
+  if (flags & VJ_EPI_RESIDUAL) {
+    if (flags & VJ_EPI_RES_F32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = s.v[i];
+        v[i * 4] += __uint_as_float(u.x); v[i * 4 + 1] += __uint_as_float(u.y);
+        v[i * 4 + 2] += __uint_as_float(u.z); v[i * 4 + 3] += __uint_as_float(u.w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint4 u = s.v[i];
+        v[i * 8] += bf16_lo(u.x); v[i * 8 + 1] += bf16_hi(u.x); v[i * 8 + 2] += bf16_lo(u.y); v[i * 8 + 3] += bf16_hi(u.y);
+        v[i * 8 + 4] += bf16_lo(u.z); v[i * 8 + 5] += bf16_hi(u.z); v[i * 8 + 6] += bf16_lo(u.w); v[i * 8 + 7] += bf16_hi(u.w);
+      }
+    }
+  }
+}
+
+// 16 columns of row `lane` into a [32 rows][128 B] swizzled staging block: bf16 -> chunks 2u, 2u+1; fp32 -> chunks 4u..4u+3
+__device__ __forceinline__ void stage_bf16x16(uint8_t* stg, int lane, int unit, const float (&v)[16]) {
+  uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint4 u;
+    u.x = pack_bf16x2(v[i * 8], v[i * 8 + 1]); u.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
+    u.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]); u.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
+    *reinterpret_cast<uint4*>(rowp + (((unit * 2 + i) ^ (lane & 7)) << 4)) = u;
+  }
+}
+__device__ __forceinline__ void stage_f32x16(uint8_t* stg, int lane, int unit, const float (&v)[16]) {
+  uint8_t* rowp = stg + lane * 128;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(rowp + (((unit * 4 + i) ^ (lane & 7)) << 4)) =
+        make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+}
+
 // row `lane` of a [32 rows][128 B] staging block, 128-byte swizzle: 16-B chunk c of row r lives at c ^ (r & 7)
 __device__ __forceinline__ void stage_bf16x32(uint8_t* stg, int lane, int half, const float (&v)[32]) {
   uint8_t* rowp = stg + lane * 128;
@@ -684,14 +803,20 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
       : "memory");
 }
 
-template <bool AUX>
+// EW = epilogue warps per CTA: 8 (default) or 16.  The 16-warp variant is for shapes whose epilogue, not the MMA
+// mainloop, sets the pace (short K: the predictor's K = 384 GEMMs): four warps per scheduler instead of two hide the
+// tcgen05.ld / LDG / MUFU latencies of the per-row epilogue chain (ncu of the 8-warp epilogue: issue slots 41 % busy).
+// 640 threads start at 96 registers (61 440 for the CTA); setmaxnreg hands registers from the producer / MMA warpgroup (-> 32, frees 8 192) to the four
+// epilogue warpgroups (-> 112, takes exactly those 8 192), which therefore work on 16-column units.  Costs staging space: EW x 4 KB (x 2 with AUX).
+template <bool AUX, int EW = 8>
 struct Gemm2Cfg {
+  static constexpr int THREADS = (4 + EW) * 32;
   static constexpr int BN = 256;
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;          // this CTA's 128 rows
   static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;         // this CTA's half of the B tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;          // 32 KB
   static constexpr int STG_PER_WARP = (AUX ? 2 : 1) * GEMM_STG_BYTES;
-  static constexpr int STG_TOTAL = 8 * STG_PER_WARP;
+  static constexpr int STG_TOTAL = EW * STG_PER_WARP;
   static constexpr int STAGES_RAW = (227 * 1024 - STG_TOTAL - 2048) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = 256;
@@ -701,12 +826,12 @@ struct Gemm2Cfg {
   static constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
 };
 
-template <bool A_MN, bool B_MN, bool AUX>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <bool A_MN, bool B_MN, bool AUX, int EW>
+__global__ void __launch_bounds__((4 + EW) * 32, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAux, GemmEpi epi, int M,
              int N, int K, int splits) {
-  using Cfg = Gemm2Cfg<AUX>;
+  using Cfg = Gemm2Cfg<AUX, EW>;
   constexpr int BN = Cfg::BN;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -742,7 +867,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], 16);
+      mbar_init(&tempty[s], 2 * EW);
     }
     mbar_fence_init();
   }
@@ -760,6 +885,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (both CTAs)
+    if constexpr (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");     // register hand-over (see Gemm2Cfg)
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
@@ -799,6 +925,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (leader CTA only)
+    if constexpr (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
     if (leader) {
       int stage = 0;
       uint32_t phase = 0;
@@ -837,8 +964,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 4) {
+    if constexpr (EW == 16) asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");     // warps 2, 3: same warpgroup as 0, 1
+  } else {
     // ------------------------------------------------ epilogue (both CTAs, each on its own 128 rows)
+    if constexpr (EW == 16) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int q = warp & 3;
     const int ew = warp - 4;
     const int eg = ew >> 2;
@@ -851,6 +981,70 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint8_t* stg_aux = stg_out + GEMM_STG_BYTES;
     const uint32_t tempty_leader0 = mapa_shared(smem_u32(&tempty[0]), 0);
     const uint32_t tempty_leader1 = mapa_shared(smem_u32(&tempty[1]), 0);
+    if constexpr (EW == 16) {
+      // ---- 16 epilogue warps, 16-column units: warpgroup eg owns the 128-byte column groups g = eg, eg + 4, ...
+      int local16 = 0;
+      for (int work = pair; work < num_work; work += num_pairs, ++local16) {
+        const int tile = work % num_tiles;
+        int mb, nb;
+        tile_coords(tile, num_m, num_n, mb, nb);
+        const int as = local16 & 1;
+        const uint32_t aphase = (local16 >> 1) & 1;
+        const int row0 = mb * 2 * GEMM_BM + (int)rank * GEMM_BM + q * 32;
+        const long long row = (long long)row0 + lane;
+        const bool row_ok = row < M;
+        const int n0 = nb * BN;
+        const int nlim = min(N, n0 + BN);
+        mbar_wait(&tfull[as], aphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::ACC_STRIDE;
+        if (row0 < M) {
+#pragma unroll 1
+          for (int g = eg; g < ngroups; g += 4) {
+            const int gcol = n0 + g * gw;
+            if (gcol >= N) break;
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            const int units = gw / 16;
+#pragma unroll 1
+            for (int u = 0; u < units; ++u) {
+              const int col0 = gcol + u * 16;
+              if (col0 >= nlim) break;
+              EpiSide16 side;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) side.v[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (row_ok) epilogue_fetch16(epi, side, row, col0, nlim);
+              uint32_t acc[16];
+              tmem_ld16(taddr + g * gw + u * 16, acc);
+              tmem_ld_wait();
+              float v[16], pre[16];
+              if (want_aux) {
+                epilogue_math16<true>(epi, acc, side, col0, nlim, v, pre);
+                stage_bf16x16(stg_aux, lane, u, pre);
+              } else {
+                epilogue_math16<false>(epi, acc, side, col0, nlim, v, pre);
+              }
+              if ((epi.flags & VJ_EPI_BIAS_GRAD) && row_ok && epi.n_out >= col0 && epi.n_out < col0 + 16)
+                atomicAdd(epi.bias_grad + row, epi.n_out == col0 ? v[0] : v[8]);
+              if (out_f32) stage_f32x16(stg_out, lane, u, v);
+              else stage_bf16x16(stg_out, lane, u, v);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (gcol >= epi.n_out) {}
+              else if (reduce) tma_reduce_add_2d(&tmOut, stg_out, gcol, row0);
+              else tma_store_2d(&tmOut, stg_out, gcol, row0);
+              if (want_aux) tma_store_2d(&tmAux, stg_aux, gcol, row0);
+              bulk_commit();
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(as ? tempty_leader1 : tempty_leader0);
+      }
+    } else {
     int local = 0;
     for (int work = pair; work < num_work; work += num_pairs, ++local) {
       const int tile = work % num_tiles;
@@ -922,6 +1116,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(as ? tempty_leader1 : tempty_leader0);
     }
+    }
     if (lane == 0) bulk_wait_all0();
   }
 
@@ -933,11 +1128,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                  : "memory");
 }
 
-static int max_pairs_cached(const void* kern, int smem_bytes) {
+static int max_pairs_cached(const void* kern, int smem_bytes, int threads) {
   // co-resident CTA pairs for this kernel (74 on a B200: one pair per TPC)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * (unsigned)sm_count());
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
@@ -952,9 +1147,9 @@ static int max_pairs_cached(const void* kern, int smem_bytes) {
   return n;
 }
 
-template <bool A_MN, bool B_MN, bool AUX>
+template <bool A_MN, bool B_MN, bool AUX, int EW>
 static int launch_gemm2(const vj_gemm_args* g, int flags, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<AUX>;
+  using Cfg = Gemm2Cfg<AUX, EW>;
   constexpr int BN = Cfg::BN;
   CUtensorMap tmA, tmB, tmOut, tmAux;
   // VJ_EPI_BIAS_GRAD: the MMAs run over N + 8 columns of B (the last 8 are the ones-block); the output keeps N
@@ -998,11 +1193,11 @@ static int launch_gemm2(const vj_gemm_args* g, int flags, cudaStream_t stream) {
   e.rope = reinterpret_cast<const __half*>(g->rope_table); e.rope_hd = g->rope_hd; e.rope_D = g->rope_D;
   e.bias_grad = g->bias_grad; e.n_out = (int)g->N;
 
-  auto kern = gemm2_kernel<A_MN, B_MN, AUX>;
+  auto kern = gemm2_kernel<A_MN, B_MN, AUX, EW>;
   static int pairs = 0;
   if (pairs == 0) {
     VJ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    pairs = max_pairs_cached(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES);
+    pairs = max_pairs_cached(reinterpret_cast<const void*>(kern), Cfg::SMEM_BYTES, Cfg::THREADS);
   }
   const int num_m = (int)((g->M + 2 * GEMM_BM - 1) / (2 * GEMM_BM));
   const int num_n = (int)((Nmma + BN - 1) / BN);
@@ -1025,7 +1220,7 @@ static int launch_gemm2(const vj_gemm_args* g, int flags, cudaStream_t stream) {
   const int npairs = work < pairs ? (int)work : pairs;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * (unsigned)npairs);
-  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.blockDim = dim3((unsigned)Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute at[1];
@@ -1045,6 +1240,22 @@ static int pair_mode() {
     g_pair_mode = (s && s[0] >= '0' && s[0] <= '2') ? s[0] - '0' : 1;      // 0 off, 1 auto, 2 every shape (tests)
   }
   return g_pair_mode;
+}
+// 16 epilogue warps (Gemm2Cfg): VJ_GEMM_EPI16 = 0 never, 1 every K-major-A shape (tests), unset = short-K shapes
+static bool use_wide_epilogue(const vj_gemm_args* g, int flags) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* s = getenv("VJ_GEMM_EPI16");
+    mode = (s && (s[0] == '0' || s[0] == '1')) ? s[0] - '0' : 2;
+  }
+  if (mode != 2) return mode == 1;
+  // measured on one B200 (profiles/r02y_epi16_ab.txt): K = 384 -- qkv + RoPE 0.119 -> 0.097 ms, fc1 + GELU + aux 0.153 ->
+  // 0.118, fc2-dgrad * GELU' 0.153 -> 0.141; K = 1408 -- qkv + RoPE 0.451 -> 0.429, proj + residual 0.167 -> 0.160,
+  // GELU' 0.230 -> 0.225, but plain / bias-only shapes lose 2-3 % (one pipeline stage less) and the AUX variant 9 % (three
+  // stages): short K always, mid K only with a side-operand epilogue and without AUX
+  if (g->K <= 512) return true;
+  const bool side = (flags & (VJ_EPI_ROPE | VJ_EPI_DGELU)) != 0 || ((flags & VJ_EPI_RESIDUAL) && !(flags & EPI_INTERNAL_REDUCE));
+  return side && !(flags & VJ_EPI_AUX_OUT) && g->K <= 2048;
 }
 static bool use_pair_kernel(long long M, long long N) {
   const int mode = pair_mode();
@@ -1123,13 +1334,16 @@ extern "C" int vj_gemm(const vj_gemm_args* g, void* stream_) {
   const bool amn = g->a_mn_major != 0, bmn = g->b_mn_major != 0;
   VJ_CHECK(!(amn && !bmn), "vj_gemm: (A MN-major, B K-major) is not instantiated");
   if (use_pair_kernel(g->M, g->N)) {
+    const bool wide = use_wide_epilogue(g, flags);
     if (flags & VJ_EPI_AUX_OUT) {
       VJ_CHECK(!amn && !bmn, "vj_gemm: AUX_OUT is only instantiated for K-major operands");
-      return launch_gemm2<false, false, true>(g, flags, stream);
+      return wide ? launch_gemm2<false, false, true, 16>(g, flags, stream) : launch_gemm2<false, false, true, 8>(g, flags, stream);
     }
-    if (!amn && !bmn) return launch_gemm2<false, false, false>(g, flags, stream);
-    if (!amn && bmn) return launch_gemm2<false, true, false>(g, flags, stream);
-    return launch_gemm2<true, true, false>(g, flags, stream);
+    if (!amn && !bmn)
+      return wide ? launch_gemm2<false, false, false, 16>(g, flags, stream) : launch_gemm2<false, false, false, 8>(g, flags, stream);
+    if (!amn && bmn)
+      return wide ? launch_gemm2<false, true, false, 16>(g, flags, stream) : launch_gemm2<false, true, false, 8>(g, flags, stream);
+    return launch_gemm2<true, true, false, 8>(g, flags, stream);
   }
   const int bn = pick_bn(g->N, g->M);
   if (flags & VJ_EPI_AUX_OUT) {

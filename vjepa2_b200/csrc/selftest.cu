@@ -440,7 +440,7 @@ static void bench_gemm(const char* name, long long M, long long N, long long K, 
   vj_gemm_args g;
   memset(&g, 0, sizeof(g));
   g.a = A; g.b = B; g.out = out; g.M = M; g.N = N; g.K = K; g.lda = a_mn ? M : K; g.ldb = b_mn ? N : K; g.ldo = N;
-  const bool accumulate = (flags & VJ_EPI_RESIDUAL) && of32 && (flags & VJ_EPI_RES_F32);
+  const bool accumulate = (flags & VJ_EPI_RESIDUAL) && of32 && (flags & VJ_EPI_RES_F32) && !(flags & VJ_EPI_ROUND_BF16);
   g.a_mn_major = a_mn; g.b_mn_major = b_mn; g.flags = flags; g.bias = bias; g.residual = accumulate ? out : side; g.ldr = N;
   g.aux_out = side; g.aux_in = side; g.ld_aux = N;
   if (flags & VJ_EPI_ROPE) { g.rope_table = side; g.rope_hd = 64; g.rope_D = (int)(N / 3); }   // zero table: timing only
@@ -650,6 +650,17 @@ int main(int argc, char** argv) {
     bench_colsum(12096, 6144);
     bench_colsum(12096, 4224);
     bench_colsum(36000, 1536);
+  }
+  if (!strcmp(what, "benchpred")) {     // the predictor's short-K GEMMs (dim 384, hidden 1536, ~55k tokens per step pass)
+    const int RB = VJ_EPI_ROUND_BF16;
+    bench_gemm("pred qkv bias+rope", 55296, 1152, 384, 0, 0, VJ_EPI_BIAS | VJ_EPI_ROPE);
+    bench_gemm("pred proj +res f32", 55296, 384, 384, 0, 0, VJ_EPI_BIAS | VJ_EPI_RESIDUAL | VJ_EPI_RES_F32 | VJ_EPI_OUT_F32 | RB);
+    bench_gemm("pred fc1 gelu+aux", 55296, 1536, 384, 0, 0, VJ_EPI_BIAS | VJ_EPI_GELU | RB | VJ_EPI_AUX_OUT);
+    bench_gemm("pred fc2 +res f32", 55296, 384, 1536, 0, 0, VJ_EPI_BIAS | VJ_EPI_RESIDUAL | VJ_EPI_RES_F32 | VJ_EPI_OUT_F32 | RB);
+    bench_gemm("pred fc2 dgrad dgelu", 55296, 1536, 384, 0, 1, VJ_EPI_DGELU);
+    bench_gemm("pred fc1 dgrad", 55296, 384, 1536, 0, 1, 0);
+    bench_gemm("pred qkv dgrad", 55296, 384, 1152, 0, 1, 0);
+    bench_gemm("pred proj dgrad", 55296, 384, 384, 0, 1, 0);
   }
   if (!strcmp(what, "stressattn")) {   // back-to-back launches (CTAs of consecutive launches overlap on the SMs)
     const int reps = argc > 2 ? atoi(argv[2]) : 20;
