@@ -260,6 +260,9 @@ int vj_sum_into(float* dst, const vj_ptr_list* srcs, int n_src, int64_t n, void*
 /* Tuning / test switch of vj_gemm's kernel choice (same as the VJ_GEMM_2CTA environment variable): 0 = 1-CTA kernels
  * only, 1 = automatic (CTA-pair kernel for M >= 1024), 2 = CTA-pair kernel for every shape.  Returns the old mode. */
 int vj_gemm_set_pair_mode(int mode);
+/* Same for the CTA-pair kernel's epilogue width (VJ_GEMM_EPI16): 0 = 8 epilogue warps always, 1 = 16 epilogue warps for
+ * every K-major-A shape, 2 = automatic (short K, or K <= 2048 with a side-operand epilogue).  Returns the old mode. */
+int vj_gemm_set_epi16_mode(int mode);
 
 #ifdef __cplusplus
 }

@@ -169,6 +169,46 @@ def test_gemm_wgrad_bias_gradient_from_ones_column(dev, Nw, Kw, tok):
     assert relerr(g2, g) < 1e-6
 
 
+@pytest.mark.parametrize("M,N,K", [(1300, 1408, 1408), (4097, 1152, 384), (2049, 384, 1536), (1024, 1536, 384)])
+def test_gemm_pair_kernel_16_epilogue_warps_agree_bitwise_with_8(dev, M, N, K):
+    """gemm2_kernel<..., EW = 16> (640 threads, setmaxnreg, 16-column epilogue units) computes every element with the same
+    operations in the same order as the 8-warp epilogue: forced on and off, all epilogues give identical bits."""
+    from vjepa2_b200 import _cabi, ops
+    lib = _cabi.load()
+    a = randn(M, K, seed=1, dtype=BF16).to(dev)
+    w = randn(N, K, seed=2, dtype=BF16, scale=0.05).to(dev)
+    wt = w.t().contiguous()                       # [K, N]: the MN-major B operand of a dgrad
+    bias = randn(N, seed=3).to(dev)
+    res = randn(M, N, seed=4, dtype=BF16).to(dev)
+    res32 = res.float()
+    aux = randn(M, N, seed=5, dtype=BF16, scale=2.0).to(dev)
+    hd, D = 64, N // 3
+    table = (torch.rand(M, 2, hd, generator=torch.Generator().manual_seed(6)) * 2 - 1).half().to(dev) if N % 192 == 0 else None
+
+    def run():
+        outs = []
+        o = torch.empty(M, N, dtype=BF16, device=dev); ops.gemm(a, w, o, M, N, K, bias=bias); outs.append(o)
+        o = torch.empty(M, N, dtype=BF16, device=dev); h = torch.empty(M, N, dtype=BF16, device=dev)
+        ops.gemm(a, w, o, M, N, K, bias=bias, gelu=True, round_bf16=True, aux_out=h); outs += [o, h]
+        o = torch.empty(M, N, dtype=BF16, device=dev); ops.gemm(a, w, o, M, N, K, bias=bias, residual=res, round_bf16=True); outs.append(o)
+        o = torch.empty(M, N, dtype=F32, device=dev); ops.gemm(a, w, o, M, N, K, bias=bias, residual=res32, round_bf16=True); outs.append(o)
+        o = torch.empty(M, N, dtype=BF16, device=dev); ops.gemm(a, wt, o, M, N, K, b_mn=True, dgelu_aux=aux); outs.append(o)
+        if table is not None:
+            o = torch.empty(M, N, dtype=BF16, device=dev); ops.gemm(a, w, o, M, N, K, bias=bias, rope=(table, hd, D)); outs.append(o)
+        torch.cuda.synchronize()
+        return outs
+
+    old = lib.vj_gemm_set_epi16_mode(0)
+    try:
+        narrow = run()
+        lib.vj_gemm_set_epi16_mode(1)
+        wide = run()
+    finally:
+        lib.vj_gemm_set_epi16_mode(old)
+    for i, (x, y) in enumerate(zip(narrow, wide)):
+        assert torch.equal(x, y), (i, relerr(x, y))
+
+
 def test_gemm_pair_and_single_cta_kernels_agree_bitwise(dev):
     """Same tile arithmetic (k-blocks of 64 in order, fp32 accumulate, identical epilogue): forcing the 1-CTA kernels
     through a fresh process-level switch is not possible in-process, so compare M = 1023 (1-CTA) with the first 1023

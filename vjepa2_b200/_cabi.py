@@ -94,6 +94,7 @@ SIGNATURES = {
     "vj_peer_barrier": (c_int, [POINTER(PtrList), c_int, c_int, ctypes.c_uint32, c_void_p]),
     "vj_sum_into": (c_int, [c_void_p, POINTER(PtrList), c_int, c_int64, c_void_p]),
     "vj_gemm_set_pair_mode": (c_int, [c_int]),
+    "vj_gemm_set_epi16_mode": (c_int, [c_int]),
 }
 
 _lib = None

@@ -1242,12 +1242,16 @@ static int pair_mode() {
   return g_pair_mode;
 }
 // 16 epilogue warps (Gemm2Cfg): VJ_GEMM_EPI16 = 0 never, 1 every K-major-A shape (tests), unset = short-K shapes
-static bool use_wide_epilogue(const vj_gemm_args* g, int flags) {
-  static int mode = -1;
-  if (mode < 0) {
+static int g_epi16_mode = -1;
+static int epi16_mode() {
+  if (g_epi16_mode < 0) {
     const char* s = getenv("VJ_GEMM_EPI16");
-    mode = (s && (s[0] == '0' || s[0] == '1')) ? s[0] - '0' : 2;
+    g_epi16_mode = (s && (s[0] == '0' || s[0] == '1')) ? s[0] - '0' : 2;
   }
+  return g_epi16_mode;
+}
+static bool use_wide_epilogue(const vj_gemm_args* g, int flags) {
+  const int mode = epi16_mode();
   if (mode != 2) return mode == 1;
   // measured on one B200 (profiles/r02y_epi16_ab.txt): K = 384 -- qkv + RoPE 0.119 -> 0.097 ms, fc1 + GELU + aux 0.153 ->
   // 0.118, fc2-dgrad * GELU' 0.153 -> 0.141; K = 1408 -- qkv + RoPE 0.451 -> 0.429, proj + residual 0.167 -> 0.160,
@@ -1284,6 +1288,12 @@ static int pick_bn(long long N, long long M) {
 }
 
 }  // namespace vj
+
+extern "C" int vj_gemm_set_epi16_mode(int mode) {
+  const int old = vj::epi16_mode();
+  if (mode >= 0 && mode <= 2) vj::g_epi16_mode = mode;
+  return old;
+}
 
 extern "C" int vj_gemm_set_pair_mode(int mode) {
   const int old = vj::pair_mode();
