@@ -158,7 +158,7 @@ def test_train_step_vs_oracle_and_golden(dev, golden):
             got = efs.grad_view(efs.g32, p) / 65536.0
             # against the fp32 reference; measured on B200: <= 3.0e-2 (1-D: long cancelling sums of bf16 terms) and
             # <= 2.8e-2 (matrices) at this toy width -- the bf16-autocast reference itself is 1.5-1.8e-2 off fp32 at full
-            # width, where ours is 1.0-1.1e-2 (tests/test_gpu_fullwidth.py, profiles/r02v_fullwidth_parity.json)
+            # width, where ours is 1.0-1.1e-2 (tests/test_gpu_fullwidth.py, profiles/r02zz_fullwidth_parity.json)
             assert relerr(got, v) < 3.5e-2, (k, relerr(got, v))
         if k.startswith("step.gpred."):
             p = dict(pred.named_parameters())[k[len("step.gpred."):]]
