@@ -13,13 +13,16 @@
  *   - all pointers are device pointers unless named host_*; matrices are row-major.
  *   - no CPU fallback: on a machine without an sm_100 device every launch fails loudly.
  *   - threading: safe from any host thread; calls for ONE device must be enqueued on one stream at a time per
- *     entry point family (vj_colsum / vj_layernorm_bwd keep self-resetting per-column-group tickets in device
- *     memory, so two of them must not run CONCURRENTLY on the same device; back-to-back on one stream is the
- *     intended use).  Everything else keeps no device state.
+ *     entry point family (vj_colsum keeps self-resetting per-column-group tickets in device memory, so two of them
+ *     must not run CONCURRENTLY on the same device; back-to-back on one stream is the intended use).  vj_mask_collate
+ *     and vj_peer_barrier keep their state in caller-owned device memory.  Everything else keeps no device state.
  *   - tuning switches read once from the environment (all default to the measured-best setting):
  *     VJ_GEMM_2CTA = 0 | 1 | 2   1-CTA kernels only | CTA-pair (cta_group::2) kernel for M >= 1024 | always;
+ *     VJ_GEMM_EPI16 = 0 | 1      CTA-pair kernel: 8 epilogue warps always | 16 for every K-major-A shape (unset: by shape);
  *     VJ_ATTN_POLY = 0..4        eighths of the forward softmax exponentials evaluated on the FMA pipe (default 2);
- *     VJ_ATTN_BWD_POLY = 0..4    same for the backward recomputation (default 0).
+ *     VJ_ATTN_BWD_POLY = 0..4    same for the backward recomputation (default 0);
+ *     VJ_ATTN_BWD_PARTS = 2 | 4  compute threads per key row of the attention backward (default 2).
+ *     Host side (vjepa2_b200/train.py): VJ_DDP_COMM = peer | nccl, VJ_DDP_SYNC = overlap | end, VJ_DDP_BUCKET_MB.
  */
 #ifndef VJEPA2_B200_H
 #define VJEPA2_B200_H

@@ -524,3 +524,16 @@ def test_bucket_hook_merges_adjacent_block_ranges_and_covers_everything_once():
         assert covered[0][0] == 0 and covered[-1][1] == ranges[depth][1]
         assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))       # contiguous, no overlap, no gap
     assert len(got) == 1
+
+
+def test_bias_grad_pad_rule():
+    """LayerNorm pads its saved output with 8 ones-columns only where the wgrad GEMM can carry them for free: the last
+    256-column tile of D is partly filled, and every weight-gradient GEMM reading it is large enough for the CTA-pair
+    kernel (vjepa2_b200/ops.py: bias_grad_pad)."""
+    from vjepa2_b200 import ops
+    assert ops.bias_grad_pad(1408, 4224, 6144) == 8          # ViT-g: 1408 = 5 * 256 + 128
+    assert ops.bias_grad_pad(384, 1152, 1536) == 8           # predictor
+    assert ops.bias_grad_pad(1024, 3072, 4096) == 0          # ViT-L: D fills its tiles, an extra tile would cost more
+    assert ops.bias_grad_pad(1280, 3840, 5120) == 0          # ViT-H
+    assert ops.bias_grad_pad(128, 384, 512) == 0             # toy widths: wgrads below the pair kernel's M >= 1024
+    assert ops.bias_grad_pad(1408, 4224, 512) == 0
